@@ -1,0 +1,289 @@
+/*
+ * b200seed.h — C-ABI of the B200-native triplet track seeding + seed
+ * parameter estimation library (libb200seed.so).
+ *
+ * This is the drop-in boundary for the traccc hot path
+ *   traccc::cuda::triplet_seeding_algorithm
+ *       (reference: device/cuda/include/traccc/cuda/seeding/triplet_seeding_algorithm.hpp:23-111,
+ *        orchestration device/common/src/seeding/triplet_seeding_algorithm.cpp:56-262)
+ *   traccc::cuda::seed_parameter_estimation_algorithm
+ *       (reference: device/cuda/include/traccc/cuda/seeding/seed_parameter_estimation_algorithm.hpp:19-58,
+ *        orchestration device/common/src/seeding/seed_parameter_estimation_algorithm.cpp:31-63)
+ *
+ * Plain C, plain pointers and sizes. All `d_*` pointers are DEVICE pointers to
+ * the contiguous column arrays that live inside the reference's vecmem SoA
+ * views (edm::spacepoint_collection, edm::seed_collection,
+ * edm::measurement_collection). All `h_*` pointers are HOST pointers.
+ * Every function returns 0 on success, a negative B200SEED_E* code otherwise;
+ * b200seed_last_error() gives the message (the C++ adapter turns it into the
+ * exception the reference would throw).
+ */
+#ifndef B200SEED_H
+#define B200SEED_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------ */
+/* Configuration structs: byte-for-byte restatements of the reference PODs. */
+/* ------------------------------------------------------------------------ */
+
+/* traccc::seedfinder_config — core/include/traccc/seeding/detail/seeding_config.hpp:17-139
+ * (33 four-byte words, 132 bytes). The six "derived" members are filled by
+ * b200seed_finder_cfg_setup(), which restates seedfinder_config::setup() (:123-138). */
+typedef struct b200seed_finder_cfg {
+    float zMin, zMax, rMax, rMin;
+    float collisionRegionMin, collisionRegionMax;
+    float phiMin, phiMax;
+    float minPt;
+    float cotThetaMax;
+    float deltaRMin, deltaRMax;
+    float deltaZMax;
+    float impactMax;
+    float sigmaScattering;
+    float maxPtScattering;
+    uint32_t maxSeedsPerSpM;
+    float bFieldInZ;
+    float beamPos[2];
+    float radLengthPerSeed;
+    float zAlign, rAlign;
+    float sigmaError;
+    /* derived */
+    float highland;
+    float maxScatteringAngle2;
+    float pTPerHelixRadius;
+    float minHelixDiameter2;
+    float minHelixRadius;
+    float pT2perRadius;
+    int32_t phiBinDeflectionCoverage;
+    uint32_t neighbor_scope[2];
+} b200seed_finder_cfg;
+
+/* traccc::spacepoint_grid_config — seeding_config.hpp:142-189 (44 bytes). It is a
+ * COPY of eleven finder fields taken at construction (:145-156): later edits of the
+ * finder config do not propagate (tests/cpu/test_seeding.cpp:38-44 relies on that). */
+typedef struct b200seed_grid_cfg {
+    float bFieldInZ;
+    float minPt;
+    float rMax;
+    float zMax;
+    float zMin;
+    float deltaRMax;
+    float cotThetaMax;
+    float impactMax;
+    float phiMin;
+    float phiMax;
+    int32_t phiBinDeflectionCoverage;
+} b200seed_grid_cfg;
+
+/* traccc::seedfilter_config — seeding_config.hpp:191-219 (56 bytes with padding). */
+typedef struct b200seed_filter_cfg {
+    float deltaInvHelixDiameter;
+    float impactWeightFactor;
+    float compatSeedWeight;
+    float deltaRMin;
+    size_t compatSeedLimit;
+    float good_spB_min_radius;
+    float good_spB_weight_increase;
+    float good_spT_max_radius;
+    float good_spT_weight_increase;
+    float good_spB_min_weight;
+    float seed_min_weight;
+    float spB_min_radius;
+} b200seed_filter_cfg;
+
+/* traccc::track_params_estimation_config —
+ * core/include/traccc/seeding/detail/track_params_estimation_config.hpp:18-33 (56 bytes). */
+typedef struct b200seed_tpe_cfg {
+    float initial_sigma[6];
+    float initial_sigma_qopt;
+    float initial_sigma_pt_rel;
+    float initial_inflation[6];
+} b200seed_tpe_cfg;
+
+/* Fill the structs with the reference's in-class defaults (units: mm, GeV, T =
+ * 2.99792458e-4 GeV/(e mm) as in detray::unit<float>). finder_defaults also calls setup. */
+void b200seed_finder_cfg_defaults(b200seed_finder_cfg* cfg);
+void b200seed_finder_cfg_setup(b200seed_finder_cfg* cfg);
+void b200seed_grid_cfg_from_finder(const b200seed_finder_cfg* finder, b200seed_grid_cfg* grid);
+void b200seed_filter_cfg_defaults(b200seed_filter_cfg* cfg);
+void b200seed_tpe_cfg_defaults(b200seed_tpe_cfg* cfg);
+
+/* ------------------------------------------------------------------------ */
+/* Output record of the parameter estimation                                 */
+/* ------------------------------------------------------------------------ */
+
+/* One detray::bound_track_parameters<> worth of data (reference:
+ * core/include/traccc/edm/track_parameters.hpp:28-49). vec = (loc0, loc1, phi, theta,
+ * q/p, time); cov is the 6x6 covariance (only the diagonal is non-zero on this path,
+ * so row/column-major is immaterial). 176 bytes. */
+typedef struct b200seed_bound_params {
+    uint64_t surface_link;
+    float vec[6];
+    float cov[36];
+} b200seed_bound_params;
+
+/* Device-side counters of one event. Written by b200seed_run when d_counters != NULL;
+ * they replace the reference's D->H size reads (triplet_seeding_algorithm.cpp:64-224)
+ * for logging and for the parity tests. */
+typedef struct b200seed_counters {
+    uint32_t n_spacepoints;      /* input size */
+    uint32_t n_valid;            /* spacepoints passing is_valid_sp */
+    uint32_t n_active_middles;   /* middles with >=1 bottom and >=1 top doublet */
+    uint32_t n_mid_bot;          /* mid-bottom doublets of active middles */
+    uint32_t n_mid_top;          /* mid-top doublets of active middles */
+    uint32_t n_triplets;         /* triplets passing triplet_finding_helper::isCompatible */
+    uint32_t n_seeds;            /* seeds written (== *d_n_seeds) */
+    uint32_t overflow;           /* bit mask of B200SEED_OVF_* ; 0 == results complete */
+    uint64_t pair_tests;         /* sum over valid middles of candidate spacepoints scanned */
+    uint64_t triplet_tests;      /* sum over active middles of nMidBot * nMidTop */
+} b200seed_counters;
+
+#define B200SEED_OVF_DOUBLETS 1u /* doublet arena too small: raise max_doublets */
+#define B200SEED_OVF_SEEDS 2u    /* seed_capacity too small                     */
+#define B200SEED_OVF_DUMP 4u     /* debug triplet dump buffer too small         */
+#define B200SEED_OVF_TRIPLETS 8u /* one mid-bottom doublet has more triplets than the
+                                    shared-memory list holds (pathological)       */
+
+/* Error codes */
+#define B200SEED_OK 0
+#define B200SEED_EINVAL -1   /* bad argument / unsupported configuration (std::domain_error upstream) */
+#define B200SEED_ECUDA -2    /* CUDA runtime error (TRACCC_CUDA_ERROR_CHECK upstream) */
+#define B200SEED_ENOMEM -3   /* workspace too small */
+
+typedef struct b200seed_handle b200seed_handle;
+
+/* ------------------------------------------------------------------------ */
+/* Life cycle                                                                */
+/* ------------------------------------------------------------------------ */
+
+/* Replaces the constructors of cuda::triplet_seeding_algorithm
+ * (cuda/seeding/triplet_seeding_algorithm.hpp:35-40) and
+ * cuda::seed_parameter_estimation_algorithm (…/seed_parameter_estimation_algorithm.hpp:33-37).
+ * Computes the phi/z axes like get_axes (spacepoint_binning_helper.hpp:22-110); a
+ * configuration get_axes would reject with std::domain_error gives B200SEED_EINVAL.
+ * `tpe` may be NULL (defaults). One handle per host thread / stream, like the reference. */
+int b200seed_create(const b200seed_finder_cfg* finder, const b200seed_grid_cfg* grid,
+                    const b200seed_filter_cfg* filter, const b200seed_tpe_cfg* tpe,
+                    int device, b200seed_handle** out);
+void b200seed_destroy(b200seed_handle* h);
+/* Message of the last failure on this handle (or of the last failed create when h==NULL). */
+const char* b200seed_last_error(const b200seed_handle* h);
+
+/* Axes chosen at construction: phi is circular, z is regular/closed. */
+int b200seed_get_axes(const b200seed_handle* h, uint32_t* n_phi, float* phi_min, float* phi_max,
+                      uint32_t* n_z, float* z_min, float* z_max);
+
+/* Doublet arena capacity (entries per direction). 0 selects the default policy
+ * max(2^20, 4e-3 * max_spacepoints^2). */
+int b200seed_set_max_doublets(b200seed_handle* h, uint64_t max_doublets);
+
+/* Bytes of device scratch b200seed_run needs for events of up to max_spacepoints. */
+size_t b200seed_workspace_bytes(const b200seed_handle* h, uint32_t max_spacepoints);
+
+/* ------------------------------------------------------------------------ */
+/* The hot path                                                              */
+/* ------------------------------------------------------------------------ */
+
+/* Replaces device::triplet_seeding_algorithm::operator()
+ * (device/common/src/seeding/triplet_seeding_algorithm.cpp:56-262).
+ * In : spacepoint columns `global` (std::array<float,3>, stride 3 floats), z_variance,
+ *      radius_variance (edm/spacepoint_collection.hpp:223-234).
+ * Out: seed columns bottom/middle/top index + quality (edm/seed_collection.hpp:142-146),
+ *      the resizable buffer's size word *d_n_seeds, in the reference CPU's seed order.
+ * Everything is enqueued on `stream` (a cudaStream_t); no host synchronisation happens,
+ * like the reference "returns a buffer which is not necessarily filled yet".
+ * n_sp == 0 writes *d_n_seeds = 0 and returns. */
+int b200seed_run(b200seed_handle* h, void* stream, uint32_t n_sp, const float* d_xyz,
+                 const float* d_var_z, const float* d_var_r, void* d_workspace,
+                 size_t workspace_bytes, uint32_t seed_capacity, uint32_t* d_bottom,
+                 uint32_t* d_middle, uint32_t* d_top, float* d_quality, uint32_t* d_n_seeds,
+                 b200seed_counters* d_counters);
+
+/* Replaces device::seed_parameter_estimation_algorithm::operator()
+ * (device/common/src/seeding/seed_parameter_estimation_algorithm.cpp:31-63) with a
+ * homogeneous field `bfield` (3 floats, host memory, copied by value).
+ * d_sp_meas_index_1 : spacepoint column measurement_index_1
+ * d_meas_local      : measurement column local_position (stride 2 floats)
+ * d_meas_surface    : measurement column surface_link (64-bit identifier)
+ * The number of seeds is read on the device from *d_n_seeds (<= seed_capacity). */
+int b200seed_estimate_params(b200seed_handle* h, void* stream, const uint32_t* d_n_seeds,
+                             uint32_t seed_capacity, const uint32_t* d_bottom,
+                             const uint32_t* d_middle, const uint32_t* d_top,
+                             const float* d_xyz, const uint32_t* d_sp_meas_index_1,
+                             const float* d_meas_local, const uint64_t* d_meas_surface,
+                             const float bfield[3], b200seed_bound_params* d_params);
+
+/* End-to-end convenience with HOST buffers: H->D of the event, seeding, parameter
+ * estimation, D->H of seeds + parameters, stream synchronised before returning. This is
+ * what seeding_example_cuda.cpp:264-356 does around the two algorithms. Device staging
+ * buffers are owned by the handle and grow on demand. h_params may be NULL. */
+int b200seed_run_host(b200seed_handle* h, void* stream, uint32_t n_sp, const float* h_xyz,
+                      const float* h_var_z, const float* h_var_r,
+                      const uint32_t* h_sp_meas_index_1, uint32_t n_meas,
+                      const float* h_meas_local, const uint64_t* h_meas_surface,
+                      const float bfield[3], uint32_t seed_capacity, uint32_t* h_bottom,
+                      uint32_t* h_middle, uint32_t* h_top, float* h_quality,
+                      b200seed_bound_params* h_params, uint32_t* h_n_seeds,
+                      b200seed_counters* h_counters);
+
+/* ------------------------------------------------------------------------ */
+/* Introspection for the parity tests and the bench                          */
+/* ------------------------------------------------------------------------ */
+
+/* Byte offsets of the intermediate arrays inside the workspace for a given
+ * max_spacepoints (valid after b200seed_run on that workspace):
+ *   bin_offsets : uint32[n_bins + 1]   start of each (phi + n_phi * z) bin in sorted order
+ *   sorted_index: uint32[n_valid]      original spacepoint index per sorted position
+ *                                      (ascending inside each bin == CPU grid order)
+ *   sp_xyzr     : float4[n_valid]      {x, y, z, radius} per sorted position
+ *   mid_counts  : uint32[2][max_sp]    nMidBot / nMidTop per sorted position (0 if inactive)
+ *   mid_offsets : uint32[2][max_sp]    start of each middle's list in the doublet arena
+ *                                      (bump-allocated: list order is canonical, the placement
+ *                                      of the lists relative to each other is not)
+ *   doublets    : 32-byte records [2][max_doublets]: {cotTheta, iDeltaR, Er, U, V, Zo,
+ *                 radius of the other spacepoint, sorted position of the other spacepoint}
+ *   triplet_dump: 32-byte records {sorted pos bottom, middle, top (u32), index of the
+ *                 mid-bottom doublet, index of the mid-top doublet (u32), curvature, weight
+ *                 after the compatible-seed bonus, z_vertex (f32)} in no particular order;
+ *                 filled only when dumping is enabled. */
+typedef struct b200seed_ws_layout {
+    size_t bin_offsets;
+    size_t sorted_index;
+    size_t sp_xyzr;
+    size_t mid_counts;
+    size_t mid_offsets;
+    size_t doublets;
+    size_t triplet_dump;
+    size_t triplet_dump_count; /* uint32 */
+    uint64_t max_doublets;
+    uint64_t max_triplet_dump;
+    uint32_t n_bins;
+    uint32_t max_spacepoints;
+} b200seed_ws_layout;
+int b200seed_workspace_layout(const b200seed_handle* h, uint32_t max_spacepoints,
+                              b200seed_ws_layout* out);
+
+/* Enable (capacity > 0) or disable (0) the debug dump of every triplet. Changes
+ * b200seed_workspace_bytes. Off by default: the production path never materialises
+ * triplets in HBM. */
+int b200seed_set_triplet_dump(b200seed_handle* h, uint64_t max_triplets);
+
+/* Per-kernel device timing. When enabled, b200seed_run brackets every kernel with CUDA
+ * events on `stream`; b200seed_get_timings synchronises those events and returns the
+ * milliseconds of the last run. names/ms hold up to `cap` entries; returns the count. */
+int b200seed_set_timing(b200seed_handle* h, int enabled);
+int b200seed_get_timings(b200seed_handle* h, const char** names, float* ms, int cap);
+/* Number of kernels one b200seed_run (+ estimate_params) launches. */
+int b200seed_launches_per_event(const b200seed_handle* h, int with_params);
+
+const char* b200seed_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SEED_H */

@@ -1,0 +1,245 @@
+"""ctypes front-end of the CPU oracle (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs as the *checker*. The product package
+(traccc_b200) never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+
+class FinderCfg(C.Structure):
+    """b200seed_finder_cfg == traccc::seedfinder_config (seeding_config.hpp:17-139)."""
+
+    _fields_ = [(n, C.c_float) for n in (
+        "zMin", "zMax", "rMax", "rMin", "collisionRegionMin", "collisionRegionMax",
+        "phiMin", "phiMax", "minPt", "cotThetaMax", "deltaRMin", "deltaRMax", "deltaZMax",
+        "impactMax", "sigmaScattering", "maxPtScattering")] + [
+        ("maxSeedsPerSpM", C.c_uint32), ("bFieldInZ", C.c_float), ("beamPos", C.c_float * 2),
+        ("radLengthPerSeed", C.c_float), ("zAlign", C.c_float), ("rAlign", C.c_float),
+        ("sigmaError", C.c_float), ("highland", C.c_float), ("maxScatteringAngle2", C.c_float),
+        ("pTPerHelixRadius", C.c_float), ("minHelixDiameter2", C.c_float),
+        ("minHelixRadius", C.c_float), ("pT2perRadius", C.c_float),
+        ("phiBinDeflectionCoverage", C.c_int32), ("neighbor_scope", C.c_uint32 * 2)]
+
+
+class GridCfg(C.Structure):
+    """b200seed_grid_cfg == traccc::spacepoint_grid_config (seeding_config.hpp:142-189)."""
+
+    _fields_ = [(n, C.c_float) for n in (
+        "bFieldInZ", "minPt", "rMax", "zMax", "zMin", "deltaRMax", "cotThetaMax", "impactMax",
+        "phiMin", "phiMax")] + [("phiBinDeflectionCoverage", C.c_int32)]
+
+
+class FilterCfg(C.Structure):
+    """b200seed_filter_cfg == traccc::seedfilter_config (seeding_config.hpp:191-219)."""
+
+    _fields_ = [("deltaInvHelixDiameter", C.c_float), ("impactWeightFactor", C.c_float),
+                ("compatSeedWeight", C.c_float), ("deltaRMin", C.c_float),
+                ("compatSeedLimit", C.c_size_t), ("good_spB_min_radius", C.c_float),
+                ("good_spB_weight_increase", C.c_float), ("good_spT_max_radius", C.c_float),
+                ("good_spT_weight_increase", C.c_float), ("good_spB_min_weight", C.c_float),
+                ("seed_min_weight", C.c_float), ("spB_min_radius", C.c_float)]
+
+
+class TpeCfg(C.Structure):
+    """b200seed_tpe_cfg == traccc::track_params_estimation_config."""
+
+    _fields_ = [("initial_sigma", C.c_float * 6), ("initial_sigma_qopt", C.c_float),
+                ("initial_sigma_pt_rel", C.c_float), ("initial_inflation", C.c_float * 6)]
+
+
+BOUND_PARAMS_DTYPE = np.dtype([("surface_link", "<u8"), ("vec", "<f4", (6,)),
+                               ("cov", "<f4", (36,))])
+assert BOUND_PARAMS_DTYPE.itemsize == 176
+
+COUNTER_NAMES = ("n_valid", "pair_tests", "stage1_bot", "stage1_top", "n_mid_bot_all",
+                 "n_mid_top_all", "n_active_middles", "n_mid_bot", "n_mid_top", "triplet_tests",
+                 "triplet_cut1", "n_triplets", "max_q_middle", "weight_pairs")
+
+
+def build(force: bool = False) -> str:
+    """Compile liboracle.so (and oracle/_ref when /root/reference exists)."""
+    if force or not os.path.exists(_LIB_PATH) or (
+            os.path.getmtime(_LIB_PATH) < os.path.getmtime(os.path.join(_HERE, "seeding_oracle.cpp"))):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        L = C.CDLL(_LIB_PATH)
+        L.oracle_run.restype = C.c_void_p
+        L.oracle_run.argtypes = [C.POINTER(FinderCfg), C.POINTER(GridCfg), C.POINTER(FilterCfg),
+                                 C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.oracle_free.argtypes = [C.c_void_p]
+        L.oracle_status.argtypes = [C.c_void_p]
+        L.oracle_sizes.argtypes = [C.c_void_p, C.c_void_p]
+        L.oracle_counters.argtypes = [C.c_void_p, C.c_void_p]
+        L.oracle_axes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_copy_grid.argtypes = [C.c_void_p] * 3
+        L.oracle_copy_doublets.argtypes = [C.c_void_p] * 7
+        L.oracle_copy_triplets.argtypes = [C.c_void_p] * 7
+        L.oracle_copy_seeds.argtypes = [C.c_void_p] * 5
+        L.oracle_copy_params.argtypes = [C.c_void_p] * 2
+        L.oracle_estimate_params.argtypes = [C.c_void_p, C.POINTER(TpeCfg)] + [C.c_void_p] * 5
+        L.oracle_estimate_params_for.argtypes = [C.POINTER(TpeCfg), C.c_uint32] + [C.c_void_p] * 9
+        L.oracle_selftest_atan2f.restype = C.c_uint64
+        L.oracle_selftest_atan2f.argtypes = [C.c_uint64, C.c_float, C.c_uint64]
+        L.oracle_atan2f_fdlibm.restype = C.c_float
+        L.oracle_atan2f_fdlibm.argtypes = [C.c_float, C.c_float]
+        for name in ("oracle_axis_regular_bin", "oracle_axis_circular_bin"):
+            f = getattr(L, name)
+            f.restype = C.c_uint32
+            f.argtypes = [C.c_uint32, C.c_float, C.c_float, C.c_float]
+        L.oracle_axis_circular_remap.restype = C.c_uint32
+        L.oracle_axis_circular_remap.argtypes = [C.c_uint32, C.c_float, C.c_float, C.c_uint32, C.c_int]
+        for name in ("oracle_axis_regular_range", "oracle_axis_circular_range"):
+            getattr(L, name).argtypes = [C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_uint32,
+                                         C.c_uint32, C.c_void_p]
+        L.oracle_axis_zone.restype = C.c_uint32
+        L.oracle_axis_zone.argtypes = [C.c_int, C.c_uint32, C.c_float, C.c_float, C.c_float,
+                                       C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]
+        L.oracle_get_axes.argtypes = [C.POINTER(GridCfg)] + [C.c_void_p] * 6
+        L.oracle_doublet_is_compatible.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.POINTER(FinderCfg)]
+        L.oracle_transform_coordinates.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_triplet_is_compatible.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p,
+                                                   C.POINTER(FinderCfg), C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def default_configs():
+    """(finder, grid, filter, tpe) with the reference's in-class defaults."""
+    L = lib()
+    f, g, fl, t = FinderCfg(), GridCfg(), FilterCfg(), TpeCfg()
+    L.oracle_finder_cfg_defaults(C.byref(f))
+    L.oracle_grid_cfg_from_finder(C.byref(f), C.byref(g))
+    L.oracle_filter_cfg_defaults(C.byref(fl))
+    L.oracle_tpe_cfg_defaults(C.byref(t))
+    return f, g, fl, t
+
+
+def get_axes(grid: GridCfg):
+    n_phi, n_z = C.c_uint32(), C.c_uint32()
+    pmin, pmax, zmin, zmax = C.c_float(), C.c_float(), C.c_float(), C.c_float()
+    rc = lib().oracle_get_axes(C.byref(grid), C.byref(n_phi), C.byref(pmin), C.byref(pmax),
+                               C.byref(n_z), C.byref(zmin), C.byref(zmax))
+    if rc != 0:
+        raise ValueError("get_axes: std::domain_error in the reference")
+    return (n_phi.value, pmin.value, pmax.value), (n_z.value, zmin.value, zmax.value)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+@dataclass
+class OracleEvent:
+    n_phi: int
+    n_z: int
+    counters: dict
+    seeds: dict            # bottom, middle, top (u32), quality (f32)
+    bin_offsets: np.ndarray | None = None
+    bin_entries: np.ndarray | None = None
+    mb: dict | None = None  # mid, other (u32), lc (n,6 f32: Zo,cotTheta,iDeltaR,Er,U,V)
+    mt: dict | None = None
+    triplets: dict | None = None  # b, m, t, curvature, weight, z_vertex
+    params: np.ndarray | None = None
+
+
+def run(xyz, var_z=None, var_r=None, finder=None, grid=None, filt=None, dump=True,
+        tpe=None, sp_meas_index=None, meas_local=None, meas_surface=None, bfield=None) -> OracleEvent:
+    """host::seeding_algorithm (+ host::track_params_estimation when bfield is given)."""
+    L = lib()
+    d = default_configs()
+    finder = finder or d[0]
+    if grid is None:
+        grid = GridCfg()
+        L.oracle_grid_cfg_from_finder(C.byref(finder), C.byref(grid))
+    filt = filt or d[2]
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+    n = xyz.shape[0]
+    vz = None if var_z is None else np.ascontiguousarray(var_z, dtype=np.float32)
+    vr = None if var_r is None else np.ascontiguousarray(var_r, dtype=np.float32)
+    h = L.oracle_run(C.byref(finder), C.byref(grid), C.byref(filt), n, _ptr(xyz), _ptr(vz),
+                     _ptr(vr), 1 if dump else 0)
+    try:
+        if L.oracle_status(h) != 0:
+            raise ValueError("get_axes: std::domain_error in the reference")
+        params = None
+        if bfield is not None:
+            tpe = tpe or d[3]
+            bf = np.ascontiguousarray(bfield, dtype=np.float32)
+            smi = None if sp_meas_index is None else np.ascontiguousarray(sp_meas_index, dtype=np.uint32)
+            ml = None if meas_local is None else np.ascontiguousarray(meas_local, dtype=np.float32)
+            ms = None if meas_surface is None else np.ascontiguousarray(meas_surface, dtype=np.uint64)
+            L.oracle_estimate_params(h, C.byref(tpe), _ptr(xyz), _ptr(smi), _ptr(ml), _ptr(ms), _ptr(bf))
+        sizes = np.zeros(7, dtype=np.uint64)
+        L.oracle_sizes(h, _ptr(sizes))
+        cnt = np.zeros(len(COUNTER_NAMES), dtype=np.uint64)
+        L.oracle_counters(h, _ptr(cnt))
+        n_phi, n_z = C.c_uint32(), C.c_uint32()
+        L.oracle_axes(h, C.byref(n_phi), C.byref(n_z))
+        ns = int(sizes[5])
+        sd = {k: np.empty(ns, dtype=np.uint32) for k in ("bottom", "middle", "top")}
+        sd["quality"] = np.empty(ns, dtype=np.float32)
+        L.oracle_copy_seeds(h, _ptr(sd["bottom"]), _ptr(sd["middle"]), _ptr(sd["top"]), _ptr(sd["quality"]))
+        ev = OracleEvent(n_phi.value, n_z.value, {k: int(v) for k, v in zip(COUNTER_NAMES, cnt)}, sd)
+        if int(sizes[6]):
+            params = np.empty(int(sizes[6]), dtype=BOUND_PARAMS_DTYPE)
+            L.oracle_copy_params(h, _ptr(params))
+        ev.params = params
+        if dump:
+            ev.bin_offsets = np.empty(int(sizes[0]), dtype=np.uint32)
+            ev.bin_entries = np.empty(int(sizes[1]), dtype=np.uint32)
+            L.oracle_copy_grid(h, _ptr(ev.bin_offsets), _ptr(ev.bin_entries))
+            nb, nt = int(sizes[2]), int(sizes[3])
+            ev.mb = {"mid": np.empty(nb, np.uint32), "other": np.empty(nb, np.uint32),
+                     "lc": np.empty((nb, 6), np.float32)}
+            ev.mt = {"mid": np.empty(nt, np.uint32), "other": np.empty(nt, np.uint32),
+                     "lc": np.empty((nt, 6), np.float32)}
+            L.oracle_copy_doublets(h, _ptr(ev.mb["mid"]), _ptr(ev.mb["other"]), _ptr(ev.mb["lc"]),
+                                   _ptr(ev.mt["mid"]), _ptr(ev.mt["other"]), _ptr(ev.mt["lc"]))
+            ntr = int(sizes[4])
+            ev.triplets = {k: np.empty(ntr, np.uint32) for k in ("b", "m", "t")}
+            for k in ("curvature", "weight", "z_vertex"):
+                ev.triplets[k] = np.empty(ntr, np.float32)
+            L.oracle_copy_triplets(h, *[_ptr(ev.triplets[k]) for k in
+                                        ("b", "m", "t", "curvature", "weight", "z_vertex")])
+        return ev
+    finally:
+        L.oracle_free(h)
+
+
+def estimate_params_for(bottom, middle, top, xyz, bfield, tpe=None, sp_meas_index=None,
+                        meas_local=None, meas_surface=None) -> np.ndarray:
+    L = lib()
+    tpe = tpe or default_configs()[3]
+    b = np.ascontiguousarray(bottom, np.uint32)
+    m = np.ascontiguousarray(middle, np.uint32)
+    t = np.ascontiguousarray(top, np.uint32)
+    xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+    bf = np.ascontiguousarray(bfield, np.float32)
+    smi = None if sp_meas_index is None else np.ascontiguousarray(sp_meas_index, np.uint32)
+    ml = None if meas_local is None else np.ascontiguousarray(meas_local, np.float32)
+    ms = None if meas_surface is None else np.ascontiguousarray(meas_surface, np.uint64)
+    out = np.zeros(len(b), dtype=BOUND_PARAMS_DTYPE)
+    L.oracle_estimate_params_for(C.byref(tpe), len(b), _ptr(b), _ptr(m), _ptr(t), _ptr(xyz),
+                                 _ptr(smi), _ptr(ml), _ptr(ms), _ptr(bf), _ptr(out))
+    return out

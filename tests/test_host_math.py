@@ -1,0 +1,110 @@
+"""The device cut arithmetic (csrc/seed_math.cuh), compiled for the host inside
+libb200seed.so (b200seed_host_probe_*), against the CPU oracle — bit for bit, no GPU."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests.helpers import oracle_cfgs
+from traccc_b200 import _lib, seedfilter_config, seedfinder_config, spacepoint_grid_config, toy_detector
+
+
+def _devcfg(finder, grid, filt):
+    buf = (C.c_ubyte * 512)()
+    n = _lib.lib().b200seed_host_probe_devcfg(C.byref(finder), C.byref(grid), C.byref(filt), buf, 512)
+    assert n > 0
+    return buf
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def test_atan2f_matches_oracle_and_libm():
+    L = _lib.lib()
+    rng = np.random.default_rng(1)
+    xy = rng.uniform(-200, 200, (200000, 2)).astype(np.float32)
+    special = np.array([[0, 1], [0, -1], [1, 0], [-1, 0], [-1, -0.0], [1e-30, 1e30], [-1e30, 1e-30],
+                        [1, 1], [-1, 1], [-50, 0], [-50, -0.0]], np.float32)
+    for y, x in np.concatenate([xy, special]):
+        a = L.b200seed_host_probe_atan2f(float(y), float(x))
+        b = oracle.lib().oracle_atan2f_fdlibm(float(y), float(x))
+        assert np.float32(a).view(np.uint32) == np.float32(b).view(np.uint32), (y, x)
+    # and the fdlibm restatement is what this box's libm computes
+    assert oracle.lib().oracle_selftest_atan2f(5_000_000, 200.0, 7) == 0
+
+
+@pytest.mark.parametrize("n_particles,seed,kw", [(300, 1, {}), (1000, 2, dict(shuffle=True, variances=0.05))])
+def test_bins_doublets_triplets_bit_exact(n_particles, seed, kw):
+    L = _lib.lib()
+    finder = seedfinder_config()
+    grid = spacepoint_grid_config(finder)
+    filt = seedfilter_config()
+    dc = _devcfg(finder, grid, filt)
+    ev = toy_detector.generate_event(n_particles, seed, **kw)
+    of, og, ofl = oracle_cfgs(finder, grid, filt)
+    ref = oracle.run(ev.xyz, ev.var_z, ev.var_r, finder=of, grid=og, filt=ofl, dump=True)
+    n = ev.n_spacepoints
+    # --- bins
+    bins = np.zeros(n, np.uint32)
+    L.b200seed_host_probe_bins(dc, n, _p(ev.xyz), _p(bins))
+    ref_bin = np.full(n, 0xFFFFFFFF, np.uint32)
+    for b in range(len(ref.bin_offsets) - 1):
+        ref_bin[ref.bin_entries[ref.bin_offsets[b]:ref.bin_offsets[b + 1]]] = b
+    assert np.array_equal(bins, ref_bin)
+    # --- doublets: every (middle, candidate) pair of a sample of middles, all bins
+    sp5 = np.concatenate([ev.xyz, ev.var_z[:, None], ev.var_r[:, None]], axis=1).astype(np.float32)
+    rng = np.random.default_rng(3)
+    mids = rng.choice(ref.bin_entries, size=min(200, len(ref.bin_entries)), replace=False)
+    valid = ref.bin_entries
+    mm = np.repeat(mids, len(valid))
+    oo = np.tile(valid, len(mids))
+    kind = np.zeros(len(mm), np.int32)
+    lc = np.zeros((len(mm), 6), np.float32)
+    L.b200seed_host_probe_doublets(dc, len(mm), _p(np.ascontiguousarray(sp5[mm])),
+                                   _p(np.ascontiguousarray(sp5[oo])), _p(kind), _p(lc))
+    okind = np.array([2 * oracle.lib().oracle_doublet_is_compatible(0, _p(sp5[a]), _p(sp5[b]), C.byref(of))
+                      + oracle.lib().oracle_doublet_is_compatible(1, _p(sp5[a]), _p(sp5[b]), C.byref(of))
+                      for a, b in zip(mm[:20000], oo[:20000])], np.int32)
+    assert np.array_equal(kind[:20000], okind)
+    # all doublets the oracle found (neighbouring bins only) must be found identically
+    for which, r, k in (("bottom", ref.mb, 1), ("top", ref.mt, 2)):
+        m5 = np.ascontiguousarray(sp5[r["mid"]])
+        o5 = np.ascontiguousarray(sp5[r["other"]])
+        kk = np.zeros(len(m5), np.int32)
+        ll = np.zeros((len(m5), 6), np.float32)
+        L.b200seed_host_probe_doublets(dc, len(m5), _p(m5), _p(o5), _p(kk), _p(ll))
+        assert (kk == k).all(), which
+        assert np.array_equal(ll.view(np.uint32), r["lc"].view(np.uint32)), which
+    # --- triplets: all (mb, mt) combinations of the active middles
+    mb_mid, mt_mid = ref.mb["mid"], ref.mt["mid"]
+    rows_m, rows_b, rows_t = [], [], []
+    for m in np.unique(mb_mid)[:400]:
+        ib = np.flatnonzero(mb_mid == m)
+        it = np.flatnonzero(mt_mid == m)
+        rows_m.append(np.full(len(ib) * len(it), m))
+        rows_b.append(np.repeat(ib, len(it)))
+        rows_t.append(np.tile(it, len(ib)))
+    rm, rb, rt = (np.concatenate(x) for x in (rows_m, rows_b, rows_t))
+    ok = np.zeros(len(rm), np.int32)
+    c1 = np.zeros(len(rm), np.int32)
+    out = np.zeros((len(rm), 2), np.float32)
+    L.b200seed_host_probe_triplets(dc, len(rm), _p(np.ascontiguousarray(sp5[rm])),
+                                   _p(np.ascontiguousarray(ref.mb["lc"][rb])),
+                                   _p(np.ascontiguousarray(ref.mt["lc"][rt])), _p(ok), _p(c1), _p(out))
+    assert (c1 >= ok).all()            # cut-1 is a necessary condition
+    # compare with the oracle's triplet list restricted to these middles
+    key_ref = set(zip(ref.triplets["m"].tolist(), ref.triplets["b"].tolist(), ref.triplets["t"].tolist()))
+    got = set(zip(rm[ok == 1].tolist(), ref.mb["other"][rb[ok == 1]].tolist(),
+                  ref.mt["other"][rt[ok == 1]].tolist()))
+    sel = set(k for k in key_ref if k[0] in set(np.unique(mb_mid)[:400].tolist()))
+    assert got == sel
+    # curvature bit-exact for the accepted ones
+    ref_curv = {k: c for k, c in zip(zip(ref.triplets["m"].tolist(), ref.triplets["b"].tolist(),
+                                         ref.triplets["t"].tolist()),
+                                     ref.triplets["curvature"].view(np.uint32).tolist())}
+    acc = np.flatnonzero(ok == 1)
+    for i in acc:
+        k = (int(rm[i]), int(ref.mb["other"][rb[i]]), int(ref.mt["other"][rt[i]]))
+        assert ref_curv[k] == int(out[i, 0].view(np.uint32)), k

@@ -1,0 +1,32 @@
+"""Builds libb200seed.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels
+with the repository snapshot to the GPU box)."""
+from __future__ import annotations
+
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(_HERE, "csrc", "b200seed_api.cu")
+DEPS = [SRC, os.path.join(_HERE, "csrc", "seed_kernels.cuh"), os.path.join(_HERE, "csrc", "seed_math.cuh"),
+        os.path.join(_HERE, "..", "include", "b200seed.h")]
+OUT = os.path.join(_HERE, "libb200seed.so")
+
+# -fmad=false + IEEE div/sqrt (nvcc defaults) + no flush-to-zero: the cut arithmetic must
+# round like the reference's CPU build (see csrc/seed_math.cuh).
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+              "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-shared", "-cudart", "static"]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and os.path.exists(OUT) and all(
+            os.path.getmtime(OUT) >= os.path.getmtime(d) for d in DEPS):
+        return OUT
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

@@ -1,0 +1,844 @@
+// b200seed_api.cu — C-ABI of libb200seed.so (include/b200seed.h): handle, workspace
+// layout, kernel launch sequence, host-buffer convenience path, host probes.
+//
+// Host-side logic mirrors device::triplet_seeding_algorithm::operator()
+// (device/common/src/seeding/triplet_seeding_algorithm.cpp:56-262) minus its seven
+// blocking device->host reads: every size the reference reads back is consumed on the
+// device instead, and arenas are capacity bounded with an overflow flag.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstddef>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200seed.h"
+#include "seed_kernels.cuh"
+
+using namespace b200seed;
+
+namespace {
+
+constexpr float unit_mm = 1.f;
+constexpr float unit_GeV = 1.f;
+constexpr float unit_MeV = 1e-3f;
+constexpr float unit_T = static_cast<float>(0.000299792458);
+constexpr float unit_degree = static_cast<float>(0.017453292519943295);
+constexpr float unit_ns = static_cast<float>(1e-9 * 299792458000.0);
+
+thread_local std::string g_create_error;
+
+inline size_t align_up(size_t v, size_t a) {
+    return (v + a - 1) / a * a;
+}
+
+struct Layout {
+    size_t control, bin_of, blk_hist, bin_off, sorted_index, sorted_bin, sp4, var2, cnt, off,
+        seed_cnt, seed_off, seed_b, seed_t, seed_w, arena_b, arena_t, dump, total;
+    uint32_t nblk;
+    uint64_t max_doublets, max_dump;
+};
+
+struct TimingSlot {
+    const char* name;
+    cudaEvent_t start, stop;
+};
+
+}  // namespace
+
+struct b200seed_handle {
+    b200seed_finder_cfg finder;
+    b200seed_grid_cfg grid;
+    b200seed_filter_cfg filter;
+    b200seed_tpe_cfg tpe;
+    DevCfg dev;
+    int device = 0;
+    uint32_t nbins = 0;
+    uint64_t max_doublets_user = 0;
+    uint64_t max_dump = 0;
+    int num_sms = 148;
+    int smem_optin = 0;
+    bool timing = false;
+    std::vector<TimingSlot> slots;
+    int n_slots_used = 0;
+    mutable std::string error;
+    // staging for b200seed_run_host
+    void* d_stage = nullptr;
+    size_t d_stage_bytes = 0;
+    b200seed_counters* h_pinned = nullptr;  // counters + n_seeds read-back
+};
+
+namespace {
+
+int fail(const b200seed_handle* h, int code, const std::string& msg) {
+    if (h)
+        h->error = msg;
+    else
+        g_create_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                 \
+    do {                                                                                  \
+        cudaError_t e__ = (expr);                                                         \
+        if (e__ != cudaSuccess)                                                           \
+            return fail(h, B200SEED_ECUDA,                                                \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));             \
+    } while (0)
+
+uint64_t default_max_doublets(uint32_t max_sp) {
+    const double q = 4e-3 * double(max_sp) * double(max_sp);
+    uint64_t v = q < double(1u << 20) ? (1u << 20) : uint64_t(q);
+    if (v > 0xFFFF0000ull) v = 0xFFFF0000ull;
+    return v;
+}
+
+Layout make_layout(const b200seed_handle* h, uint32_t max_sp) {
+    Layout L{};
+    const size_t n = max_sp ? max_sp : 1;
+    L.nblk = uint32_t((n + BIN_THREADS - 1) / BIN_THREADS);
+    L.max_doublets = h->max_doublets_user ? h->max_doublets_user : default_max_doublets(max_sp);
+    L.max_dump = h->max_dump;
+    const size_t K = h->finder.maxSeedsPerSpM ? h->finder.maxSeedsPerSpM : 1;
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        const size_t at = o;
+        o = align_up(o + bytes, 256);
+        return at;
+    };
+    L.control = take(sizeof(Control));
+    L.bin_of = take(n * 4);
+    L.blk_hist = take(size_t(h->nbins) * L.nblk * 4);
+    L.bin_off = take((size_t(h->nbins) + 1) * 4);
+    L.sorted_index = take(n * 4);
+    L.sorted_bin = take(n * 4);
+    L.sp4 = take(n * 16);
+    L.var2 = take(n * 8);
+    L.cnt = take(2 * n * 4);
+    L.off = take(2 * n * 4);
+    L.seed_cnt = take(n * 4);
+    L.seed_off = take(n * 4);
+    L.seed_b = take(n * K * 4);
+    L.seed_t = take(n * K * 4);
+    L.seed_w = take(n * K * 4);
+    L.arena_b = take(L.max_doublets * sizeof(DoubletRec));
+    L.arena_t = take(L.max_doublets * sizeof(DoubletRec));
+    L.dump = take(L.max_dump * sizeof(TripletDumpRec));
+    L.total = o;
+    return L;
+}
+
+// get_axes — core/include/traccc/seeding/spacepoint_binning_helper.hpp:22-110
+int compute_axes(const b200seed_grid_cfg& g, DevCfg& d, std::string& why) {
+    uint32_t phiBins;
+    if (g.bFieldInZ == 0) {
+        phiBins = 100;
+    } else {
+        float minHelixRadius = g.minPt / g.bFieldInZ;
+        if (minHelixRadius < g.rMax / 2) {
+            why =
+                "The value of minHelixRadius cannot be smaller than rMax / 2. Please check the "
+                "configuration of bFieldInZ and minPt";
+            return -1;
+        }
+        float maxR2 = g.rMax * g.rMax;
+        float xOuter = maxR2 / (2 * minHelixRadius);
+        float yOuter = std::sqrt(maxR2 - xOuter * xOuter);
+        float outerAngle = std::atan(xOuter / yOuter);
+        float innerAngle = 0;
+        float rMin = g.rMax;
+        if (g.rMax > g.deltaRMax) {
+            rMin = g.rMax - g.deltaRMax;
+            float innerCircleR2 = (g.rMax - g.deltaRMax) * (g.rMax - g.deltaRMax);
+            float xInner = innerCircleR2 / (2 * minHelixRadius);
+            float yInner = std::sqrt(innerCircleR2 - xInner * xInner);
+            innerAngle = std::atan(xInner / yInner);
+        }
+        float deltaAngleWithMaxD0 =
+            std::fabs(std::asin(g.impactMax / (rMin)) - std::asin(g.impactMax / g.rMax));
+        float deltaPhi = (outerAngle - innerAngle + deltaAngleWithMaxD0) /
+                         static_cast<float>(g.phiBinDeflectionCoverage);
+        if (deltaPhi <= 0.) {
+            why =
+                "Delta phi value is equal to or less than zero, leading to an impossible number "
+                "of bins (negative or infinite)";
+            return -1;
+        }
+        phiBins = static_cast<uint32_t>(std::llround(2 * M_PI / deltaPhi + 0.5));
+    }
+    float zBinSize = g.cotThetaMax * g.deltaRMax;
+    uint32_t zBins = std::max(static_cast<uint32_t>(1),
+                              static_cast<uint32_t>(std::floor((g.zMax - g.zMin) / zBinSize)));
+    d.nPhi = phiBins;
+    d.phiAxisMin = g.phiMin;
+    d.phiAxisMax = g.phiMax;
+    d.nZ = zBins;
+    d.zAxisMin = g.zMin;
+    d.zAxisMax = g.zMax;
+    return 0;
+}
+
+void fill_devcfg(const b200seed_finder_cfg& f, const b200seed_filter_cfg& fl, DevCfg& d) {
+    d.zMin = f.zMin;
+    d.zMax = f.zMax;
+    d.phiMin = f.phiMin;
+    d.phiMax = f.phiMax;
+    d.beamX = f.beamPos[0];
+    d.beamY = f.beamPos[1];
+    // get_num_rbins: size_t(rMax + vector::norm(beamPos)) — seeding_config.hpp:110-113
+    d.numRBins = static_cast<size_t>(
+        f.rMax + std::sqrt(f.beamPos[0] * f.beamPos[0] + f.beamPos[1] * f.beamPos[1]));
+    d.scope0 = f.neighbor_scope[0];
+    d.scope1 = f.neighbor_scope[1];
+    d.deltaRMin = f.deltaRMin;
+    d.deltaRMax = f.deltaRMax;
+    d.cotThetaMax = f.cotThetaMax;
+    d.collisionRegionMin = f.collisionRegionMin;
+    d.collisionRegionMax = f.collisionRegionMax;
+    d.deltaZMax = f.deltaZMax;
+    d.minHelixRadius2 = f.minHelixRadius * f.minHelixRadius;
+    d.helixImpactMargin2 = (f.minHelixRadius - f.impactMax) * (f.minHelixRadius - f.impactMax);
+    d.maxScatteringAngle2 = f.maxScatteringAngle2;
+    d.sigmaScattering = f.sigmaScattering;
+    d.sigmaScattering2 = f.sigmaScattering * f.sigmaScattering;
+    d.minHelixDiameter2 = f.minHelixDiameter2;
+    d.pT2perRadius = f.pT2perRadius;
+    d.pTPerHelixRadius = f.pTPerHelixRadius;
+    d.maxPtScattering = f.maxPtScattering;
+    {
+        float pTscatter = f.highland / f.maxPtScattering;
+        d.pT2scatterMax = pTscatter * pTscatter;
+    }
+    d.impactMax = f.impactMax;
+    d.impactWeightFactor = fl.impactWeightFactor;
+    d.deltaInvHelixDiameter = fl.deltaInvHelixDiameter;
+    d.compatSeedWeight = fl.compatSeedWeight;
+    d.filterDeltaRMin = fl.deltaRMin;
+    d.compatSeedLimit = static_cast<uint32_t>(fl.compatSeedLimit);
+    d.maxSeedsPerSpM = f.maxSeedsPerSpM;
+    d.good_spB_min_radius = fl.good_spB_min_radius;
+    d.good_spB_weight_increase = fl.good_spB_weight_increase;
+    d.good_spT_max_radius = fl.good_spT_max_radius;
+    d.good_spT_weight_increase = fl.good_spT_weight_increase;
+    d.good_spB_min_weight = fl.good_spB_min_weight;
+    d.seed_min_weight = fl.seed_min_weight;
+    d.spB_min_radius = fl.spB_min_radius;
+}
+
+struct KernelTimer {
+    b200seed_handle* h;
+    cudaStream_t s;
+    int idx = -1;
+    KernelTimer(b200seed_handle* h_, cudaStream_t s_, const char* name) : h(h_), s(s_) {
+        if (!h->timing) return;
+        if (h->n_slots_used >= int(h->slots.size())) {
+            TimingSlot t{name, nullptr, nullptr};
+            cudaEventCreate(&t.start);
+            cudaEventCreate(&t.stop);
+            h->slots.push_back(t);
+        }
+        idx = h->n_slots_used++;
+        h->slots[idx].name = name;
+        cudaEventRecord(h->slots[idx].start, s);
+    }
+    ~KernelTimer() {
+        if (idx >= 0) cudaEventRecord(h->slots[idx].stop, s);
+    }
+};
+
+// doublet staging capacity per warp and direction (shared memory): sized so that the
+// common case never takes the two-pass fallback, bounded to keep >= 2 CTAs per SM.
+uint32_t doublet_stage_cap(uint32_t n_sp) {
+    if (n_sp <= 80000) return 512;
+    if (n_sp <= 300000) return 1024;
+    return 2048;
+}
+uint32_t triplet_list_cap(uint32_t n_sp) {
+    if (n_sp <= 80000) return 192;
+    if (n_sp <= 300000) return 384;
+    return 768;
+}
+size_t triplet_smem_per_warp(uint32_t cap) {
+    return 64 * 4 + size_t(cap) * 4 + size_t(cap) * 16 + MAX_TOPK * 5 * 4;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200seed_version(void) {
+    return "b200seed 0.1 (sm_100a)";
+}
+
+// seedfinder_config::setup() — seeding_config.hpp:123-138
+void b200seed_finder_cfg_setup(b200seed_finder_cfg* c) {
+    c->highland = 13.6f * unit_MeV * std::sqrt(c->radLengthPerSeed) *
+                  (1.f + 0.038f * std::log(c->radLengthPerSeed));
+    float maxScatteringAngle = c->highland / c->minPt;
+    c->maxScatteringAngle2 = maxScatteringAngle * maxScatteringAngle;
+    c->pTPerHelixRadius = c->bFieldInZ;
+    c->minHelixDiameter2 = std::pow(c->minPt * 2.f / c->pTPerHelixRadius, 2.f);
+    c->minHelixRadius = std::sqrt(c->minHelixDiameter2) / 2.f;
+    c->pT2perRadius = std::pow(c->highland / c->pTPerHelixRadius, 2.f);
+}
+
+// seedfinder_config in-class defaults — seeding_config.hpp:22-108
+void b200seed_finder_cfg_defaults(b200seed_finder_cfg* c) {
+    std::memset(c, 0, sizeof(*c));
+    c->zMin = -2000.f * unit_mm;
+    c->zMax = 2000.f * unit_mm;
+    c->rMax = 200.f * unit_mm;
+    c->rMin = 33.f * unit_mm;
+    c->collisionRegionMin = -250 * unit_mm;
+    c->collisionRegionMax = +250 * unit_mm;
+    c->phiMin = static_cast<float>(-M_PI);
+    c->phiMax = static_cast<float>(M_PI);
+    c->minPt = 500.f * unit_MeV;
+    c->cotThetaMax = 27.2845f;
+    c->deltaRMin = 20 * unit_mm;
+    c->deltaRMax = 80 * unit_mm;
+    c->deltaZMax = 450 * unit_mm;
+    c->impactMax = 10.f * unit_mm;
+    c->sigmaScattering = 3.0f;
+    c->maxPtScattering = 10.f * unit_GeV;
+    c->maxSeedsPerSpM = 5;
+    c->bFieldInZ = 1.99724f * unit_T;
+    c->beamPos[0] = -.0f * unit_mm;
+    c->beamPos[1] = -.0f * unit_mm;
+    c->radLengthPerSeed = 0.05f;
+    c->zAlign = 0 * unit_mm;
+    c->rAlign = 0 * unit_mm;
+    c->sigmaError = 5;
+    c->phiBinDeflectionCoverage = 1;
+    c->neighbor_scope[0] = 1;
+    c->neighbor_scope[1] = 1;
+    b200seed_finder_cfg_setup(c);
+}
+
+// spacepoint_grid_config(const seedfinder_config&) — seeding_config.hpp:145-156
+void b200seed_grid_cfg_from_finder(const b200seed_finder_cfg* f, b200seed_grid_cfg* g) {
+    g->bFieldInZ = f->bFieldInZ;
+    g->minPt = f->minPt;
+    g->rMax = f->rMax;
+    g->zMax = f->zMax;
+    g->zMin = f->zMin;
+    g->deltaRMax = f->deltaRMax;
+    g->cotThetaMax = f->cotThetaMax;
+    g->impactMax = f->impactMax;
+    g->phiMin = f->phiMin;
+    g->phiMax = f->phiMax;
+    g->phiBinDeflectionCoverage = f->phiBinDeflectionCoverage;
+}
+
+// seedfilter_config — seeding_config.hpp:191-219
+void b200seed_filter_cfg_defaults(b200seed_filter_cfg* c) {
+    std::memset(c, 0, sizeof(*c));
+    c->deltaInvHelixDiameter = 0.00003f / unit_mm;
+    c->impactWeightFactor = 1.f;
+    c->compatSeedWeight = 200.f;
+    c->deltaRMin = 5.f * unit_mm;
+    c->compatSeedLimit = 2;
+    c->good_spB_min_radius = 150.f * unit_mm;
+    c->good_spB_weight_increase = 400.f;
+    c->good_spT_max_radius = 150.f * unit_mm;
+    c->good_spT_weight_increase = 200.f;
+    c->good_spB_min_weight = 380.f;
+    c->seed_min_weight = 200.f;
+    c->spB_min_radius = 43.f * unit_mm;
+}
+
+// track_params_estimation_config — detail/track_params_estimation_config.hpp:18-33
+void b200seed_tpe_cfg_defaults(b200seed_tpe_cfg* c) {
+    const float s[6] = {1.f * unit_mm,     1.f * unit_mm,        1.f * unit_degree,
+                        1.f * unit_degree, 0.f * 1.f / unit_GeV, 1.f * unit_ns};
+    const float infl[6] = {1.f, 1.f, 1.f, 1.f, 1.f, 100.f};
+    for (int i = 0; i < 6; ++i) {
+        c->initial_sigma[i] = s[i];
+        c->initial_inflation[i] = infl[i];
+    }
+    c->initial_sigma_qopt = 0.1f * 1.f / unit_GeV;
+    c->initial_sigma_pt_rel = 0.1f;
+}
+
+int b200seed_create(const b200seed_finder_cfg* finder, const b200seed_grid_cfg* grid,
+                    const b200seed_filter_cfg* filter, const b200seed_tpe_cfg* tpe, int device,
+                    b200seed_handle** out) {
+    if (!finder || !grid || !filter || !out)
+        return fail(nullptr, B200SEED_EINVAL, "b200seed_create: null argument");
+    *out = nullptr;
+    DevCfg d{};
+    std::string why;
+    if (compute_axes(*grid, d, why) != 0) return fail(nullptr, B200SEED_EINVAL, why);
+    fill_devcfg(*finder, *filter, d);
+    const uint64_t nbins = uint64_t(d.nPhi) * d.nZ;
+    if (d.nPhi == 0 || nbins > 8192)
+        return fail(nullptr, B200SEED_EINVAL,
+                    "unsupported grid: " + std::to_string(d.nPhi) + " x " + std::to_string(d.nZ) +
+                        " bins (limit 8192)");
+    if (finder->maxSeedsPerSpM > uint32_t(MAX_TOPK))
+        return fail(nullptr, B200SEED_EINVAL, "maxSeedsPerSpM > 16 is not supported");
+    if (filter->compatSeedLimit > size_t(MAX_COMPAT))
+        return fail(nullptr, B200SEED_EINVAL, "compatSeedLimit > 8 is not supported");
+    if (!(finder->deltaRMin >= 0.f))
+        return fail(nullptr, B200SEED_EINVAL, "deltaRMin must be >= 0");
+    if (d.scope0 + d.scope1 + 1u > d.nPhi)
+        return fail(nullptr, B200SEED_EINVAL, "neighbor_scope wider than the phi axis");
+
+    // The product path needs a CUDA device: fail loudly, never fall back to the CPU.
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, B200SEED_ECUDA,
+                    std::string("no CUDA device available: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev)
+        return fail(nullptr, B200SEED_EINVAL, "invalid device ordinal");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess)
+        return fail(nullptr, B200SEED_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+
+    b200seed_handle* h = new b200seed_handle();
+    h->finder = *finder;
+    h->grid = *grid;
+    h->filter = *filter;
+    if (tpe)
+        h->tpe = *tpe;
+    else
+        b200seed_tpe_cfg_defaults(&h->tpe);
+    h->dev = d;
+    h->device = device;
+    h->nbins = uint32_t(nbins);
+    cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    // allow the large dynamic shared memory configurations
+    cudaFuncSetAttribute(k_doublets, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin);
+    cudaFuncSetAttribute(k_triplets, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        std::string msg = std::string("kernel image not usable on this device (built for sm_100a): ") +
+                          cudaGetErrorString(e);
+        delete h;
+        return fail(nullptr, B200SEED_ECUDA, msg);
+    }
+    *out = h;
+    return B200SEED_OK;
+}
+
+void b200seed_destroy(b200seed_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (auto& s : h->slots) {
+        cudaEventDestroy(s.start);
+        cudaEventDestroy(s.stop);
+    }
+    if (h->d_stage) cudaFree(h->d_stage);
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    delete h;
+}
+
+const char* b200seed_last_error(const b200seed_handle* h) {
+    return h ? h->error.c_str() : g_create_error.c_str();
+}
+
+int b200seed_get_axes(const b200seed_handle* h, uint32_t* n_phi, float* phi_min, float* phi_max,
+                      uint32_t* n_z, float* z_min, float* z_max) {
+    if (!h) return B200SEED_EINVAL;
+    if (n_phi) *n_phi = h->dev.nPhi;
+    if (phi_min) *phi_min = h->dev.phiAxisMin;
+    if (phi_max) *phi_max = h->dev.phiAxisMax;
+    if (n_z) *n_z = h->dev.nZ;
+    if (z_min) *z_min = h->dev.zAxisMin;
+    if (z_max) *z_max = h->dev.zAxisMax;
+    return B200SEED_OK;
+}
+
+// Axes for a grid config without creating a handle (no GPU needed).
+int b200seed_axes_for(const b200seed_grid_cfg* grid, uint32_t* n_phi, uint32_t* n_z) {
+    DevCfg d{};
+    std::string why;
+    if (!grid || compute_axes(*grid, d, why) != 0) return fail(nullptr, B200SEED_EINVAL, why);
+    *n_phi = d.nPhi;
+    *n_z = d.nZ;
+    return B200SEED_OK;
+}
+
+int b200seed_set_max_doublets(b200seed_handle* h, uint64_t max_doublets) {
+    if (!h) return B200SEED_EINVAL;
+    if (max_doublets > 0xFFFF0000ull) return fail(h, B200SEED_EINVAL, "max_doublets too large");
+    h->max_doublets_user = max_doublets;
+    return B200SEED_OK;
+}
+
+int b200seed_set_triplet_dump(b200seed_handle* h, uint64_t max_triplets) {
+    if (!h) return B200SEED_EINVAL;
+    if (max_triplets > 0xFFFF0000ull) return fail(h, B200SEED_EINVAL, "max_triplets too large");
+    h->max_dump = max_triplets;
+    return B200SEED_OK;
+}
+
+size_t b200seed_workspace_bytes(const b200seed_handle* h, uint32_t max_spacepoints) {
+    if (!h) return 0;
+    return make_layout(h, max_spacepoints).total;
+}
+
+int b200seed_workspace_layout(const b200seed_handle* h, uint32_t max_spacepoints,
+                              b200seed_ws_layout* out) {
+    if (!h || !out) return B200SEED_EINVAL;
+    const Layout L = make_layout(h, max_spacepoints);
+    const size_t n = max_spacepoints ? max_spacepoints : 1;
+    (void)n;
+    out->bin_offsets = L.bin_off;
+    out->sorted_index = L.sorted_index;
+    out->sp_xyzr = L.sp4;
+    out->mid_counts = L.cnt;
+    out->mid_offsets = L.off;
+    out->doublets = L.arena_b;
+    out->triplet_dump = L.dump;
+    out->triplet_dump_count = L.control + offsetof(Control, dump_cursor);
+    out->max_doublets = L.max_doublets;
+    out->max_triplet_dump = L.max_dump;
+    out->n_bins = h->nbins;
+    out->max_spacepoints = max_spacepoints;
+    return B200SEED_OK;
+}
+
+int b200seed_set_timing(b200seed_handle* h, int enabled) {
+    if (!h) return B200SEED_EINVAL;
+    h->timing = enabled != 0;
+    h->n_slots_used = 0;
+    return B200SEED_OK;
+}
+
+int b200seed_get_timings(b200seed_handle* h, const char** names, float* ms, int cap) {
+    if (!h) return B200SEED_EINVAL;
+    int n = 0;
+    for (int i = 0; i < h->n_slots_used && n < cap; ++i, ++n) {
+        cudaError_t e = cudaEventSynchronize(h->slots[i].stop);
+        if (e != cudaSuccess) return fail(h, B200SEED_ECUDA, cudaGetErrorString(e));
+        float t = 0.f;
+        cudaEventElapsedTime(&t, h->slots[i].start, h->slots[i].stop);
+        if (names) names[n] = h->slots[i].name;
+        if (ms) ms[n] = t;
+    }
+    return n;
+}
+
+int b200seed_launches_per_event(const b200seed_handle*, int with_params) {
+    // k_bin_count, k_scan, k_bin_scatter, k_doublets, k_triplets, k_scan, k_seed_gather
+    return 7 + (with_params ? 1 : 0);
+}
+
+int b200seed_run(b200seed_handle* h, void* stream, uint32_t n_sp, const float* d_xyz,
+                 const float* d_var_z, const float* d_var_r, void* d_workspace,
+                 size_t workspace_bytes, uint32_t seed_capacity, uint32_t* d_bottom,
+                 uint32_t* d_middle, uint32_t* d_top, float* d_quality, uint32_t* d_n_seeds,
+                 b200seed_counters* d_counters) {
+    if (!h) return B200SEED_EINVAL;
+    if (!d_n_seeds) return fail(h, B200SEED_EINVAL, "b200seed_run: d_n_seeds is null");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (h->timing) h->n_slots_used = 0;
+    if (n_sp == 0) {
+        // "If there are no spacepoints, return right away" — triplet_seeding_algorithm.cpp:75-77
+        CUDA_TRY(h, cudaMemsetAsync(d_n_seeds, 0, sizeof(uint32_t), s));
+        if (d_counters) CUDA_TRY(h, cudaMemsetAsync(d_counters, 0, sizeof(b200seed_counters), s));
+        return B200SEED_OK;
+    }
+    if (!d_xyz || !d_workspace || (seed_capacity && (!d_bottom || !d_middle || !d_top || !d_quality)))
+        return fail(h, B200SEED_EINVAL, "b200seed_run: null device pointer");
+    if (reinterpret_cast<uintptr_t>(d_workspace) % 256 != 0)
+        return fail(h, B200SEED_EINVAL, "b200seed_run: workspace must be 256-byte aligned");
+    const Layout L = make_layout(h, n_sp);
+    if (workspace_bytes < L.total)
+        return fail(h, B200SEED_ENOMEM,
+                    "b200seed_run: workspace of " + std::to_string(workspace_bytes) +
+                        " bytes, need " + std::to_string(L.total));
+    unsigned char* ws = static_cast<unsigned char*>(d_workspace);
+    auto at = [&](size_t off) { return ws + off; };
+    Control* ctrl = reinterpret_cast<Control*>(at(L.control));
+    uint32_t* bin_of = reinterpret_cast<uint32_t*>(at(L.bin_of));
+    uint32_t* blk_hist = reinterpret_cast<uint32_t*>(at(L.blk_hist));
+    uint32_t* bin_off = reinterpret_cast<uint32_t*>(at(L.bin_off));
+    uint32_t* sorted_index = reinterpret_cast<uint32_t*>(at(L.sorted_index));
+    uint32_t* sorted_bin = reinterpret_cast<uint32_t*>(at(L.sorted_bin));
+    float4* sp4 = reinterpret_cast<float4*>(at(L.sp4));
+    float2* var2 = reinterpret_cast<float2*>(at(L.var2));
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(at(L.cnt));
+    uint32_t* off = reinterpret_cast<uint32_t*>(at(L.off));
+    uint32_t* seed_cnt = reinterpret_cast<uint32_t*>(at(L.seed_cnt));
+    uint32_t* seed_off = reinterpret_cast<uint32_t*>(at(L.seed_off));
+    uint32_t* seed_b = reinterpret_cast<uint32_t*>(at(L.seed_b));
+    uint32_t* seed_t = reinterpret_cast<uint32_t*>(at(L.seed_t));
+    float* seed_w = reinterpret_cast<float*>(at(L.seed_w));
+    const uint32_t nblk = L.nblk;
+    const uint32_t K = h->finder.maxSeedsPerSpM;
+
+    CUDA_TRY(h, cudaMemsetAsync(ctrl, 0, sizeof(Control), s));
+    {
+        KernelTimer t(h, s, "bin_count");
+        k_bin_count<<<nblk, BIN_THREADS, h->nbins * sizeof(uint32_t), s>>>(
+            h->dev, n_sp, d_xyz, bin_of, blk_hist, h->nbins, nblk);
+    }
+    {
+        KernelTimer t(h, s, "scan_bins");
+        k_scan<<<1, SCAN_THREADS, 0, s>>>(blk_hist, blk_hist, h->nbins * nblk, nullptr, &ctrl->n_valid,
+                                          bin_off, h->nbins, nblk);
+    }
+    {
+        KernelTimer t(h, s, "bin_scatter");
+        k_bin_scatter<<<nblk, BIN_THREADS, 0, s>>>(n_sp, d_xyz, d_var_z, d_var_r, bin_of, blk_hist,
+                                                   nblk, sp4, var2, sorted_index, sorted_bin);
+    }
+    {
+        DoubletArgs a{};
+        a.bin_off = bin_off;
+        a.sp4 = sp4;
+        a.var2 = var2;
+        a.sorted_bin = sorted_bin;
+        a.cnt_b = cnt;
+        a.cnt_t = cnt + n_sp;
+        a.off_b = off;
+        a.off_t = off + n_sp;
+        a.arena_b = reinterpret_cast<DoubletRec*>(at(L.arena_b));
+        a.arena_t = reinterpret_cast<DoubletRec*>(at(L.arena_t));
+        a.ctrl = ctrl;
+        a.max_doublets = uint32_t(L.max_doublets);
+        a.stage_cap = doublet_stage_cap(n_sp);
+        const size_t smem = size_t(WARPS_PER_CTA) * (64 + 2 * a.stage_cap) * 4;
+        uint32_t grid = (n_sp + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+        const uint32_t max_grid = uint32_t(h->num_sms) * 8;
+        if (grid > max_grid) grid = max_grid;
+        KernelTimer t(h, s, "doublets");
+        k_doublets<<<grid, WARPS_PER_CTA * 32, smem, s>>>(h->dev, a);
+    }
+    {
+        TripletArgs a{};
+        a.sp4 = sp4;
+        a.var2 = var2;
+        a.cnt_b = cnt;
+        a.cnt_t = cnt + n_sp;
+        a.off_b = off;
+        a.off_t = off + n_sp;
+        a.arena_b = reinterpret_cast<DoubletRec*>(at(L.arena_b));
+        a.arena_t = reinterpret_cast<DoubletRec*>(at(L.arena_t));
+        a.ctrl = ctrl;
+        a.seed_cnt = seed_cnt;
+        a.seed_b = seed_b;
+        a.seed_t = seed_t;
+        a.seed_w = seed_w;
+        a.dump = L.max_dump ? reinterpret_cast<TripletDumpRec*>(at(L.dump)) : nullptr;
+        a.max_dump = uint32_t(L.max_dump);
+        a.list_cap = triplet_list_cap(n_sp);
+        const size_t smem = triplet_smem_per_warp(a.list_cap) * WARPS_PER_CTA;
+        uint32_t grid = (n_sp + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+        const uint32_t max_grid = uint32_t(h->num_sms) * 6;
+        if (grid > max_grid) grid = max_grid;
+        KernelTimer t(h, s, "triplets");
+        k_triplets<<<grid, WARPS_PER_CTA * 32, smem, s>>>(h->dev, a);
+    }
+    {
+        KernelTimer t(h, s, "scan_seeds");
+        // seed_off = exclusive scan of seed_cnt over the n_valid sorted positions
+        k_scan<<<1, SCAN_THREADS, 0, s>>>(seed_cnt, seed_off, n_sp, &ctrl->n_valid,
+                                          &ctrl->n_seeds_total, nullptr, 0, 0);
+    }
+    {
+        KernelTimer t(h, s, "seed_gather");
+        k_seed_gather<<<(n_sp + 255) / 256, 256, 0, s>>>(
+            n_sp, K, ctrl, seed_cnt, seed_off, seed_b, seed_t, seed_w, sorted_index, seed_capacity,
+            d_bottom, d_middle, d_top, d_quality, d_n_seeds, d_counters);
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    return B200SEED_OK;
+}
+
+int b200seed_estimate_params(b200seed_handle* h, void* stream, const uint32_t* d_n_seeds,
+                             uint32_t seed_capacity, const uint32_t* d_bottom,
+                             const uint32_t* d_middle, const uint32_t* d_top,
+                             const float* d_xyz, const uint32_t* d_sp_meas_index_1,
+                             const float* d_meas_local, const uint64_t* d_meas_surface,
+                             const float bfield[3], b200seed_bound_params* d_params) {
+    if (!h) return B200SEED_EINVAL;
+    if (seed_capacity == 0) return B200SEED_OK;
+    if (!d_n_seeds || !d_bottom || !d_middle || !d_top || !d_xyz || !bfield || !d_params)
+        return fail(h, B200SEED_EINVAL, "b200seed_estimate_params: null pointer");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    {
+        KernelTimer t(h, s, "estimate_params");
+        k_estimate_params<<<(seed_capacity + 127) / 128, 128, 0, s>>>(
+            h->tpe, d_n_seeds, seed_capacity, d_bottom, d_middle, d_top, d_xyz, d_sp_meas_index_1,
+            d_meas_local, d_meas_surface, bfield[0], bfield[1], bfield[2], d_params);
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    return B200SEED_OK;
+}
+
+int b200seed_run_host(b200seed_handle* h, void* stream, uint32_t n_sp, const float* h_xyz,
+                      const float* h_var_z, const float* h_var_r,
+                      const uint32_t* h_sp_meas_index_1, uint32_t n_meas,
+                      const float* h_meas_local, const uint64_t* h_meas_surface,
+                      const float bfield[3], uint32_t seed_capacity, uint32_t* h_bottom,
+                      uint32_t* h_middle, uint32_t* h_top, float* h_quality,
+                      b200seed_bound_params* h_params, uint32_t* h_n_seeds,
+                      b200seed_counters* h_counters) {
+    if (!h) return B200SEED_EINVAL;
+    if (!h_n_seeds) return fail(h, B200SEED_EINVAL, "b200seed_run_host: h_n_seeds is null");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    *h_n_seeds = 0;
+    if (h_counters) std::memset(h_counters, 0, sizeof(*h_counters));
+    if (n_sp == 0) return B200SEED_OK;
+    if (!h_xyz) return fail(h, B200SEED_EINVAL, "b200seed_run_host: h_xyz is null");
+    const bool want_params = h_params != nullptr;
+    if (want_params && !bfield) return fail(h, B200SEED_EINVAL, "b200seed_run_host: bfield is null");
+
+    // device staging: inputs | outputs | workspace
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        const size_t at = o;
+        o = align_up(o + bytes, 256);
+        return at;
+    };
+    const size_t o_xyz = take(size_t(n_sp) * 12), o_vz = take(size_t(n_sp) * 4),
+                 o_vr = take(size_t(n_sp) * 4), o_smi = take(size_t(n_sp) * 4),
+                 o_ml = take(size_t(n_meas) * 8), o_ms = take(size_t(n_meas) * 8),
+                 o_b = take(size_t(seed_capacity) * 4), o_m = take(size_t(seed_capacity) * 4),
+                 o_t = take(size_t(seed_capacity) * 4), o_q = take(size_t(seed_capacity) * 4),
+                 o_p = take(want_params ? size_t(seed_capacity) * sizeof(b200seed_bound_params) : 0),
+                 o_n = take(256), o_c = take(sizeof(b200seed_counters));
+    const size_t ws_bytes = b200seed_workspace_bytes(h, n_sp);
+    const size_t o_ws = take(ws_bytes);
+    if (o > h->d_stage_bytes) {
+        if (h->d_stage) CUDA_TRY(h, cudaFree(h->d_stage));
+        h->d_stage = nullptr;
+        h->d_stage_bytes = 0;
+        const size_t want = o + o / 4;
+        CUDA_TRY(h, cudaMalloc(&h->d_stage, want));
+        h->d_stage_bytes = want;
+    }
+    if (!h->h_pinned) CUDA_TRY(h, cudaMallocHost(&h->h_pinned, 256));
+    unsigned char* d = static_cast<unsigned char*>(h->d_stage);
+    float* d_xyz = reinterpret_cast<float*>(d + o_xyz);
+    float* d_vz = h_var_z ? reinterpret_cast<float*>(d + o_vz) : nullptr;
+    float* d_vr = h_var_r ? reinterpret_cast<float*>(d + o_vr) : nullptr;
+    uint32_t* d_smi = h_sp_meas_index_1 ? reinterpret_cast<uint32_t*>(d + o_smi) : nullptr;
+    float* d_ml = h_meas_local ? reinterpret_cast<float*>(d + o_ml) : nullptr;
+    uint64_t* d_ms = h_meas_surface ? reinterpret_cast<uint64_t*>(d + o_ms) : nullptr;
+    uint32_t* d_b = reinterpret_cast<uint32_t*>(d + o_b);
+    uint32_t* d_m = reinterpret_cast<uint32_t*>(d + o_m);
+    uint32_t* d_t = reinterpret_cast<uint32_t*>(d + o_t);
+    float* d_q = reinterpret_cast<float*>(d + o_q);
+    b200seed_bound_params* d_p = reinterpret_cast<b200seed_bound_params*>(d + o_p);
+    uint32_t* d_n = reinterpret_cast<uint32_t*>(d + o_n);
+    b200seed_counters* d_c = reinterpret_cast<b200seed_counters*>(d + o_c);
+
+    CUDA_TRY(h, cudaMemcpyAsync(d_xyz, h_xyz, size_t(n_sp) * 12, cudaMemcpyHostToDevice, s));
+    if (d_vz) CUDA_TRY(h, cudaMemcpyAsync(d_vz, h_var_z, size_t(n_sp) * 4, cudaMemcpyHostToDevice, s));
+    if (d_vr) CUDA_TRY(h, cudaMemcpyAsync(d_vr, h_var_r, size_t(n_sp) * 4, cudaMemcpyHostToDevice, s));
+    if (want_params) {
+        if (d_smi)
+            CUDA_TRY(h, cudaMemcpyAsync(d_smi, h_sp_meas_index_1, size_t(n_sp) * 4,
+                                        cudaMemcpyHostToDevice, s));
+        if (d_ml)
+            CUDA_TRY(h, cudaMemcpyAsync(d_ml, h_meas_local, size_t(n_meas) * 8,
+                                        cudaMemcpyHostToDevice, s));
+        if (d_ms)
+            CUDA_TRY(h, cudaMemcpyAsync(d_ms, h_meas_surface, size_t(n_meas) * 8,
+                                        cudaMemcpyHostToDevice, s));
+    }
+    int rc = b200seed_run(h, s, n_sp, d_xyz, d_vz, d_vr, d + o_ws, ws_bytes, seed_capacity, d_b, d_m,
+                          d_t, d_q, d_n, d_c);
+    if (rc != B200SEED_OK) return rc;
+    if (want_params) {
+        rc = b200seed_estimate_params(h, s, d_n, seed_capacity, d_b, d_m, d_t, d_xyz, d_smi, d_ml,
+                                      d_ms, bfield, d_p);
+        if (rc != B200SEED_OK) return rc;
+    }
+    // the counters struct carries n_seeds: one small read-back, then the sized copies
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_pinned, d_c, sizeof(b200seed_counters), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    const uint32_t n = h->h_pinned->n_seeds;
+    *h_n_seeds = n;
+    if (h_counters) *h_counters = *h->h_pinned;
+    if (n) {
+        if (h_bottom) CUDA_TRY(h, cudaMemcpyAsync(h_bottom, d_b, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
+        if (h_middle) CUDA_TRY(h, cudaMemcpyAsync(h_middle, d_m, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
+        if (h_top) CUDA_TRY(h, cudaMemcpyAsync(h_top, d_t, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
+        if (h_quality) CUDA_TRY(h, cudaMemcpyAsync(h_quality, d_q, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
+        if (want_params)
+            CUDA_TRY(h, cudaMemcpyAsync(h_params, d_p, size_t(n) * sizeof(b200seed_bound_params),
+                                        cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(h, cudaStreamSynchronize(s));
+    }
+    return B200SEED_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Host probes: the device cut arithmetic (seed_math.cuh) compiled for the host, so the
+// CPU test-suite can compare it with the oracle bit for bit without a GPU. Not used by
+// any product path.
+// ---------------------------------------------------------------------------
+int b200seed_host_probe_devcfg(const b200seed_finder_cfg* f, const b200seed_grid_cfg* g,
+                               const b200seed_filter_cfg* fl, void* out, size_t out_bytes) {
+    if (!f || !g || !fl || !out || out_bytes < sizeof(DevCfg)) return B200SEED_EINVAL;
+    DevCfg d{};
+    std::string why;
+    if (compute_axes(*g, d, why) != 0) return fail(nullptr, B200SEED_EINVAL, why);
+    fill_devcfg(*f, *fl, d);
+    std::memcpy(out, &d, sizeof(d));
+    return int(sizeof(DevCfg));
+}
+float b200seed_host_probe_atan2f(float y, float x) {
+    return fd_atan2f(y, x);
+}
+// bins of n spacepoints (0xFFFFFFFF = invalid)
+void b200seed_host_probe_bins(const void* devcfg, uint32_t n, const float* xyz, uint32_t* bins) {
+    const DevCfg& d = *static_cast<const DevCfg*>(devcfg);
+    for (uint32_t i = 0; i < n; ++i) bins[i] = sp_bin(d, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+}
+// doublet decision for n (middle, other) pairs: 0 none, 1 bottom, 2 top; lin_circle of
+// accepted pairs (Zo,cotTheta,iDeltaR,Er,U,V). m/o = {x,y,z,varZ,varR} per pair.
+void b200seed_host_probe_doublets(const void* devcfg, uint32_t n, const float* m, const float* o,
+                                  int32_t* kind, float* lc) {
+    const DevCfg& d = *static_cast<const DevCfg*>(devcfg);
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* a = m + 5 * size_t(i);
+        const float* b = o + 5 * size_t(i);
+        const float rM = sp_radius(a[0], a[1]), r2 = sp_radius(b[0], b[1]);
+        int st = doublet_stage1(d, rM, a[2], r2, b[2]);
+        if (st && !doublet_stage2(d, a[0], a[1], b[0], b[1])) st = 0;
+        kind[i] = st;
+        if (st) {
+            const LinCircle l = transform_coordinates(st == 1, a[0], a[1], a[2], rM, a[3], a[4], b[0],
+                                                      b[1], b[2], b[3], b[4]);
+            float* q = lc + 6 * size_t(i);
+            q[0] = l.Zo, q[1] = l.cotTheta, q[2] = l.iDeltaR, q[3] = l.Er, q[4] = l.U, q[5] = l.V;
+        }
+    }
+}
+// triplet decision for n (middle, lb, lt) combinations; out = {curvature, impact}
+void b200seed_host_probe_triplets(const void* devcfg, uint32_t n, const float* m, const float* lb,
+                                  const float* lt, int32_t* ok, int32_t* cut1, float* out) {
+    const DevCfg& d = *static_cast<const DevCfg*>(devcfg);
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* a = m + 5 * size_t(i);
+        const float* pb = lb + 6 * size_t(i);
+        const float* pt = lt + 6 * size_t(i);
+        const LinCircle b{pb[0], pb[1], pb[2], pb[3], pb[4], pb[5]};
+        const LinCircle t{pt[0], pt[1], pt[2], pt[3], pt[4], pt[5]};
+        float is2, s2;
+        triplet_row_constants(d, b.cotTheta, is2, s2);
+        cut1[i] = triplet_cut1(b.cotTheta, b.iDeltaR, b.Er, t.cotTheta, t.iDeltaR, t.Er, a[4], a[3], s2)
+                      ? 1
+                      : 0;
+        float c = 0.f, ip = 0.f;
+        ok[i] = triplet_is_compatible(d, sp_radius(a[0], a[1]), a[4], a[3], b, t, is2, s2, c, ip) ? 1 : 0;
+        out[2 * size_t(i)] = c;
+        out[2 * size_t(i) + 1] = ip;
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,855 @@
+// seed_kernels.cuh — hand-written sm_100a kernels of the triplet seeding path.
+//
+// Pipeline of one event (all on one stream, no host synchronisation, every intermediate
+// addressed through the workspace):
+//
+//   k_bin_count      is_valid_sp + bin index per spacepoint, per-block bin histogram
+//   k_scan           single-CTA exclusive scan of the [bin][block] histogram matrix
+//   k_bin_scatter    stable scatter into bin-sorted float4 {x,y,z,r} / float2 {varZ,varR}
+//   k_doublets       warp per middle: stage-1 cuts on all neighbour-bin candidates,
+//                    ballot/popc compaction, stage-2 on survivors only, lin_circle, arena write
+//   k_triplets       warp per middle (atomic ticket queue): lane-owns-mid-bottom x loop over
+//                    mid-tops, cut-1 -> ballot compaction -> full cut, compatible-seed bonus,
+//                    per-middle top-N in shared memory
+//   k_scan           exclusive scan of the per-middle seed counts
+//   k_seed_gather    seeds in the reference CPU's order, original spacepoint indices
+//   k_estimate_params one thread per seed
+//
+// Replaces device/cuda/src/seeding/triplet_seeding_algorithm.cu:30-160 (9 kernels, 7
+// blocking D->H reads between them) and seed_parameter_estimation_algorithm.cu:22-33.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/b200seed.h"
+#include "seed_math.cuh"
+
+namespace b200seed {
+
+constexpr uint32_t INVALID_BIN = 0xFFFFFFFFu;
+constexpr int BIN_THREADS = 256;    // spacepoints per binning block
+constexpr int SCAN_THREADS = 1024;  // single-CTA scan
+constexpr int SCAN_ITEMS = 4;
+constexpr int WARPS_PER_CTA = 8;
+constexpr int MAX_TOPK = 16;        // upper bound on maxSeedsPerSpM
+constexpr int MAX_COMPAT = 8;       // upper bound on compatSeedLimit
+
+// Small control block at the start of the workspace, zeroed at the start of each event.
+struct Control {
+    uint32_t cursor[2];       // doublet arena bump pointers (bottom / top)
+    uint32_t ticket;          // k_triplets work queue
+    uint32_t n_active;
+    uint32_t n_mid_bot;
+    uint32_t n_mid_top;
+    uint32_t n_triplets;
+    uint32_t overflow;
+    unsigned long long pair_tests;
+    unsigned long long triplet_tests;
+    uint32_t dump_cursor;
+    uint32_t n_valid;         // written by the first scan
+    uint32_t n_seeds_total;   // written by the second scan
+    uint32_t pad[3];
+};
+
+// One doublet record in the arena: two float4.
+//   a = {cotTheta, iDeltaR, Er, U}     b = {V, Zo, radius(other), bits(sorted pos of other)}
+struct __align__(16) DoubletRec {
+    float4 a, b;
+};
+
+// Debug dump record (32 bytes), see b200seed.h
+struct __align__(16) TripletDumpRec {
+    uint32_t pos_b, pos_m, pos_t, mb_idx;
+    uint32_t mt_idx;
+    float curvature, weight, z_vertex;
+};
+
+// ---------------------------------------------------------------------------
+// (1) binning: count
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(BIN_THREADS)
+k_bin_count(const DevCfg cfg, const uint32_t n_sp, const float* __restrict__ xyz,
+            uint32_t* __restrict__ bin_of, uint32_t* __restrict__ blk_hist, const uint32_t nbins,
+            const uint32_t nblk) {
+    extern __shared__ uint32_t s_hist[];
+    for (uint32_t b = threadIdx.x; b < nbins; b += BIN_THREADS) s_hist[b] = 0;
+    __syncthreads();
+    const uint32_t i = blockIdx.x * BIN_THREADS + threadIdx.x;
+    if (i < n_sp) {
+        const float x = __ldg(xyz + 3 * size_t(i));
+        const float y = __ldg(xyz + 3 * size_t(i) + 1);
+        const float z = __ldg(xyz + 3 * size_t(i) + 2);
+        const uint32_t bin = sp_bin(cfg, x, y, z);
+        bin_of[i] = bin;
+        if (bin != INVALID_BIN) atomicAdd(&s_hist[bin], 1u);
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < nbins; b += BIN_THREADS)
+        blk_hist[size_t(b) * nblk + blockIdx.x] = s_hist[b];
+}
+
+// ---------------------------------------------------------------------------
+// single-CTA exclusive scan of in[] into data[] (may alias). len_dev, if not null,
+// overrides len. Epilogue: total -> *total_out; if bin_off != null,
+// bin_off[b] = data[b * stride].
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan(const uint32_t* in, uint32_t* data, uint32_t len, const uint32_t* __restrict__ len_dev,
+       uint32_t* __restrict__ total_out, uint32_t* __restrict__ bin_off, const uint32_t nbins,
+       const uint32_t stride) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_total;
+    if (len_dev) len = *len_dev;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t carry = 0;
+    constexpr uint32_t CHUNK = SCAN_THREADS * SCAN_ITEMS;
+    for (uint32_t base = 0; base < len; base += CHUNK) {
+        const uint32_t idx = base + threadIdx.x * SCAN_ITEMS;
+        uint32_t v[SCAN_ITEMS];
+        uint32_t s = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            v[k] = (idx + k < len) ? in[idx + k] : 0u;
+            s += v[k];
+        }
+        uint32_t incl = s;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= uint32_t(off)) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t ws = s_warp[lane];
+            uint32_t wincl = ws;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, wincl, off);
+                if (lane >= uint32_t(off)) wincl += t;
+            }
+            s_warp[lane] = wincl - ws;
+            if (lane == 31) s_total = wincl;
+        }
+        __syncthreads();
+        uint32_t run = carry + s_warp[warp] + incl - s;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            if (idx + k < len) data[idx + k] = run;
+            run += v[k];
+        }
+        carry += s_total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = carry;
+    if (bin_off) {
+        __syncthreads();  // make the scanned values of this CTA visible to all its threads
+        for (uint32_t b = threadIdx.x; b < nbins; b += SCAN_THREADS)
+            bin_off[b] = data[size_t(b) * stride];
+        if (threadIdx.x == 0) bin_off[nbins] = carry;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// (1) binning: stable scatter into the bin-sorted SoA
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(BIN_THREADS)
+k_bin_scatter(const uint32_t n_sp, const float* __restrict__ xyz, const float* __restrict__ var_z,
+              const float* __restrict__ var_r, const uint32_t* __restrict__ bin_of,
+              const uint32_t* __restrict__ blk_scan, const uint32_t nblk,
+              float4* __restrict__ sp4, float2* __restrict__ var2,
+              uint32_t* __restrict__ sorted_index, uint32_t* __restrict__ sorted_bin) {
+    __shared__ uint32_t s_bin[BIN_THREADS];
+    const uint32_t i = blockIdx.x * BIN_THREADS + threadIdx.x;
+    const uint32_t bin = (i < n_sp) ? bin_of[i] : INVALID_BIN;
+    s_bin[threadIdx.x] = bin;
+    __syncthreads();
+    if (bin == INVALID_BIN) return;
+    // rank among the earlier spacepoints of this block that fall into the same bin:
+    // ascending original index inside every bin, like the CPU's push_back loop
+    // (core/src/seeding/spacepoint_binning.cpp:40-50).
+    uint32_t rank = 0;
+    for (uint32_t t = 0; t < threadIdx.x; ++t) rank += (s_bin[t] == bin) ? 1u : 0u;
+    const uint32_t pos = blk_scan[size_t(bin) * nblk + blockIdx.x] + rank;
+    const float x = __ldg(xyz + 3 * size_t(i));
+    const float y = __ldg(xyz + 3 * size_t(i) + 1);
+    const float z = __ldg(xyz + 3 * size_t(i) + 2);
+    sp4[pos] = make_float4(x, y, z, sp_radius(x, y));
+    var2[pos] = make_float2(var_z ? __ldg(var_z + i) : 0.f, var_r ? __ldg(var_r + i) : 0.f);
+    sorted_index[pos] = i;
+    sorted_bin[pos] = bin;
+}
+
+// ---------------------------------------------------------------------------
+// (2)+(3) doublets
+// ---------------------------------------------------------------------------
+struct DoubletArgs {
+    const uint32_t* bin_off;      // [nbins+1]
+    const float4* sp4;            // sorted {x,y,z,r}
+    const float2* var2;           // sorted {varZ,varR}
+    const uint32_t* sorted_bin;   // [n_valid]
+    uint32_t* cnt_b;              // [n_sp] doublets per middle (0 if inactive)
+    uint32_t* cnt_t;
+    uint32_t* off_b;              // [n_sp] arena offsets
+    uint32_t* off_t;
+    DoubletRec* arena_b;
+    DoubletRec* arena_t;
+    Control* ctrl;
+    uint32_t max_doublets;
+    uint32_t stage_cap;           // staged candidates per direction per warp (shared memory)
+};
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// Generator of the neighbour-bin candidate ranges of a middle, in the reference's order:
+// phi bins outer (circular zone, axis.hpp:336-362), z bins inner (regular zone,
+// axis.hpp:162-173), as in doublet_finding.hpp:67-80. Ranges that are adjacent in the
+// bin-sorted array are merged (with one z bin the three phi neighbours are contiguous
+// unless they wrap around).
+struct NeighbourWalk {
+    uint32_t r0, n_phi_seq, z0, nz, q, nq;
+    __device__ __forceinline__ void init(const DevCfg& cfg, uint32_t bin, float zM) {
+        const uint32_t phi_bin = bin % cfg.nPhi;
+        r0 = circular_remap(cfg.nPhi, phi_bin, -int(cfg.scope0));
+        const uint32_t r1 = circular_remap(cfg.nPhi, phi_bin, int(cfg.scope1));
+        n_phi_seq = (r0 < r1) ? (r1 - r0 + 1u) : (cfg.nPhi - r0 + r1 + 1u);
+        const int ibin = axis_ibin(cfg.zAxisMin, cfg.zAxisMax, cfg.nZ, zM);
+        const int ibinmin = ibin - int(cfg.scope0);
+        const int ibinmax = ibin + int(cfg.scope1);
+        z0 = (ibinmin >= 0) ? uint32_t(ibinmin) : 0u;
+        const uint32_t z1 = (ibinmax < int(cfg.nZ)) ? uint32_t(ibinmax) : cfg.nZ - 1u;
+        nz = (z1 + 1u > z0) ? (z1 + 1u - z0) : 0u;
+        q = 0;
+        nq = n_phi_seq * nz;
+    }
+    __device__ __forceinline__ void rewind() { q = 0; }
+    // Next merged range [lo, hi); returns false when exhausted.
+    __device__ __forceinline__ bool next(const DevCfg& cfg, const uint32_t* __restrict__ bin_off,
+                                         uint32_t& lo, uint32_t& hi) {
+        lo = hi = 0;
+        while (q < nq) {
+            uint32_t pb = r0 + q / nz;
+            if (pb > cfg.nPhi - 1u) pb -= cfg.nPhi;
+            const uint32_t b = pb + (z0 + q % nz) * cfg.nPhi;
+            const uint32_t blo = __ldg(bin_off + b), bhi = __ldg(bin_off + b + 1);
+            if (blo == bhi) {
+                ++q;
+            } else if (lo == hi) {
+                lo = blo;
+                hi = bhi;
+                ++q;
+            } else if (blo == hi) {
+                hi = bhi;
+                ++q;
+            } else {
+                break;
+            }
+        }
+        return hi != lo;
+    }
+};
+
+// Shared memory per warp of k_doublets: 64-entry compaction ring + 2 staging lists.
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+k_doublets(const DevCfg cfg, const DoubletArgs a) {
+    extern __shared__ uint32_t s_mem[];
+    __shared__ unsigned long long s_pairs;
+    __shared__ uint32_t s_acc[3];  // active, nb, nt
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t ltmask = lanemask_lt();
+    uint32_t* ring = s_mem + size_t(warp) * (64 + 2 * a.stage_cap);
+    uint32_t* stage_b = ring + 64;
+    uint32_t* stage_t = stage_b + a.stage_cap;
+    if (threadIdx.x == 0) {
+        s_pairs = 0ull;
+        s_acc[0] = s_acc[1] = s_acc[2] = 0u;
+    }
+    __syncthreads();
+    const uint32_t n_valid = a.ctrl->n_valid;
+    const uint32_t total_warps = gridDim.x * WARPS_PER_CTA;
+    unsigned long long pairs = 0ull;
+    uint32_t acc_active = 0, acc_nb = 0, acc_nt = 0;
+
+    for (uint32_t m = blockIdx.x * WARPS_PER_CTA + warp; m < n_valid; m += total_warps) {
+        const float4 M = __ldg(a.sp4 + m);
+        const float2 VM = __ldg(a.var2 + m);  // {varZ, varR}
+        NeighbourWalk walk;
+        walk.init(cfg, __ldg(a.sorted_bin + m), M.z);
+
+        uint32_t nB = 0, nT = 0;
+        uint32_t offB = 0, offT = 0;
+        // pass 0: stage the survivors' positions in shared memory. pass 1 (only when a
+        // staging list overflowed): same scan, records written straight to the arena.
+        for (int pass = 0; pass < 2; ++pass) {
+            const bool direct = (pass == 1);
+            uint32_t qhead = 0, qn = 0;
+            uint32_t wB = 0, wT = 0;  // survivors so far in this pass
+            walk.rewind();
+            bool more = true;
+            while (more || qn > 0) {
+                uint32_t lo = 0, hi = 0;
+                if (more) more = walk.next(cfg, a.bin_off, lo, hi);
+                if (pass == 0 && lane == 0) pairs += (hi - lo);
+                uint32_t c0 = lo;
+                // scan this range; when it is the final flush (more == false) only drain
+                while (c0 < hi || (!more && qn > 0)) {
+                    if (c0 < hi) {
+                        const uint32_t c = c0 + lane;
+                        int st = 0;
+                        if (c < hi) {
+                            const float4 P = __ldg(a.sp4 + c);
+                            st = doublet_stage1(cfg, M.w, M.z, P.w, P.z);
+                        }
+                        const uint32_t mask = __ballot_sync(0xffffffffu, st != 0);
+                        if (st != 0)
+                            ring[(qhead + qn + __popc(mask & ltmask)) & 63u] =
+                                c | (st == 2 ? 0x80000000u : 0u);
+                        qn += __popc(mask);
+                        c0 += 32;
+                        __syncwarp();
+                        if (qn < 32) continue;
+                    }
+                    // drain up to 32 stage-1 survivors: full-warp stage-2 evaluation
+                    const uint32_t take = qn < 32 ? qn : 32;
+                    bool ok = false, top = false;
+                    uint32_t c = 0;
+                    float4 P = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (lane < take) {
+                        const uint32_t e = ring[(qhead + lane) & 63u];
+                        c = e & 0x7fffffffu;
+                        top = (e >> 31) != 0u;
+                        P = __ldg(a.sp4 + c);
+                        ok = doublet_stage2(cfg, M.x, M.y, P.x, P.y);
+                    }
+                    const uint32_t mB = __ballot_sync(0xffffffffu, ok && !top);
+                    const uint32_t mT = __ballot_sync(0xffffffffu, ok && top);
+                    if (ok) {
+                        const uint32_t k = top ? (wT + __popc(mT & ltmask))
+                                               : (wB + __popc(mB & ltmask));
+                        if (!direct) {
+                            if (k < a.stage_cap) (top ? stage_t : stage_b)[k] = c;
+                        } else {
+                            const float2 V = __ldg(a.var2 + c);
+                            const LinCircle l = transform_coordinates(
+                                !top, M.x, M.y, M.z, M.w, VM.x, VM.y, P.x, P.y, P.z, V.x, V.y);
+                            DoubletRec r;
+                            r.a = make_float4(l.cotTheta, l.iDeltaR, l.Er, l.U);
+                            r.b = make_float4(l.V, l.Zo, P.w, __uint_as_float(c));
+                            (top ? a.arena_t + offT : a.arena_b + offB)[k] = r;
+                        }
+                    }
+                    wB += __popc(mB);
+                    wT += __popc(mT);
+                    qhead = (qhead + take) & 63u;
+                    qn -= take;
+                    __syncwarp();
+                }
+            }
+            if (direct) break;
+            nB = wB;
+            nT = wT;
+            // A middle continues only with >= 1 bottom and >= 1 top (seed_finding.cpp:85-95)
+            if (nB == 0 || nT == 0) {
+                nB = nT = 0;
+                break;
+            }
+            if (lane == 0) {
+                offB = atomicAdd(&a.ctrl->cursor[0], nB);
+                offT = atomicAdd(&a.ctrl->cursor[1], nT);
+            }
+            offB = __shfl_sync(0xffffffffu, offB, 0);
+            offT = __shfl_sync(0xffffffffu, offT, 0);
+            if (offB > a.max_doublets || nB > a.max_doublets - offB || offT > a.max_doublets ||
+                nT > a.max_doublets - offT) {
+                if (lane == 0) atomicOr(&a.ctrl->overflow, B200SEED_OVF_DOUBLETS);
+                nB = nT = 0;
+                break;
+            }
+            if (nB > a.stage_cap || nT > a.stage_cap) continue;  // rare: redo in direct mode
+            // common path: lin_circle of every staged survivor, full lanes
+            for (int dir = 0; dir < 2; ++dir) {
+                const uint32_t n = dir ? nT : nB;
+                const uint32_t* stage = dir ? stage_t : stage_b;
+                DoubletRec* out = dir ? a.arena_t + offT : a.arena_b + offB;
+                for (uint32_t k = lane; k < n; k += 32) {
+                    const uint32_t c = stage[k];
+                    const float4 P = __ldg(a.sp4 + c);
+                    const float2 V = __ldg(a.var2 + c);
+                    const LinCircle l = transform_coordinates(dir == 0, M.x, M.y, M.z, M.w, VM.x,
+                                                              VM.y, P.x, P.y, P.z, V.x, V.y);
+                    DoubletRec r;
+                    r.a = make_float4(l.cotTheta, l.iDeltaR, l.Er, l.U);
+                    r.b = make_float4(l.V, l.Zo, P.w, __uint_as_float(c));
+                    out[k] = r;
+                }
+            }
+            break;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            a.cnt_b[m] = nB;
+            a.cnt_t[m] = nT;
+            a.off_b[m] = offB;
+            a.off_t[m] = offT;
+        }
+        if (nB) {
+            ++acc_active;
+            acc_nb += nB;
+            acc_nt += nT;
+        }
+    }
+    if (lane == 0) {
+        atomicAdd(&s_pairs, pairs);
+        atomicAdd(&s_acc[0], acc_active);
+        atomicAdd(&s_acc[1], acc_nb);
+        atomicAdd(&s_acc[2], acc_nt);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_pairs) atomicAdd(&a.ctrl->pair_tests, s_pairs);
+        if (s_acc[0]) {
+            atomicAdd(&a.ctrl->n_active, s_acc[0]);
+            atomicAdd(&a.ctrl->n_mid_bot, s_acc[1]);
+            atomicAdd(&a.ctrl->n_mid_top, s_acc[2]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// (3)+(4) triplets, compatible-seed bonus, per-middle top-N
+// ---------------------------------------------------------------------------
+struct TripletArgs {
+    const float4* sp4;
+    const float2* var2;
+    const uint32_t* cnt_b;
+    const uint32_t* cnt_t;
+    const uint32_t* off_b;
+    const uint32_t* off_t;
+    const DoubletRec* arena_b;
+    const DoubletRec* arena_t;
+    Control* ctrl;
+    uint32_t* seed_cnt;     // [n_sp]
+    uint32_t* seed_b;       // [n_sp * K] sorted position of the bottom spacepoint
+    uint32_t* seed_t;       // [n_sp * K]
+    float* seed_w;          // [n_sp * K]
+    TripletDumpRec* dump;   // optional
+    uint32_t max_dump;
+    uint32_t list_cap;      // triplets of one 32-row block kept in shared memory
+};
+
+// One triplet of the current row block (shared memory, 16 bytes).
+struct __align__(16) BlockTriplet {
+    uint32_t key;     // (row in block) << 27 | mid-top index
+    float curvature;
+    float weight;     // -impact * impactWeightFactor, later the final weight
+    float rT;         // radius of the top spacepoint, later the sorter sum
+};
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+k_triplets(const DevCfg cfg, const TripletArgs a) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ uint32_t s_ntrip;
+    __shared__ unsigned long long s_tests;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t ltmask = lanemask_lt();
+    // per-warp shared memory: ring[64] | bonus[list_cap] | list[list_cap] | top-K arrays
+    const size_t per_warp = 64 * 4 + size_t(a.list_cap) * 4 + size_t(a.list_cap) * 16 +
+                            MAX_TOPK * 5 * 4;
+    unsigned char* base = s_raw + per_warp * warp;
+    BlockTriplet* list = reinterpret_cast<BlockTriplet*>(base);
+    uint32_t* ring = reinterpret_cast<uint32_t*>(base + size_t(a.list_cap) * 16);
+    uint32_t* bonus = ring + 64;  // compatible seeds found per triplet
+    float* top_w = reinterpret_cast<float*>(bonus + a.list_cap);
+    float* top_s = top_w + MAX_TOPK;
+    float* top_rb = top_s + MAX_TOPK;
+    uint32_t* top_b = reinterpret_cast<uint32_t*>(top_rb + MAX_TOPK);
+    uint32_t* top_t = top_b + MAX_TOPK;
+    if (threadIdx.x == 0) {
+        s_ntrip = 0;
+        s_tests = 0ull;
+    }
+    __syncthreads();
+    const uint32_t n_valid = a.ctrl->n_valid;
+    const uint32_t K = cfg.maxSeedsPerSpM;
+    uint32_t acc_trip = 0;
+    unsigned long long acc_tests = 0ull;
+
+    while (true) {
+        uint32_t m = 0;
+        if (lane == 0) m = atomicAdd(&a.ctrl->ticket, 1u);
+        m = __shfl_sync(0xffffffffu, m, 0);
+        if (m >= n_valid) break;
+        const uint32_t nb = a.cnt_b[m], nt = a.cnt_t[m];
+        if (nb == 0 || nt == 0) {
+            if (lane == 0) a.seed_cnt[m] = 0;
+            continue;
+        }
+        acc_tests += (unsigned long long)nb * nt;
+        const DoubletRec* LB = a.arena_b + a.off_b[m];
+        const DoubletRec* LT = a.arena_t + a.off_t[m];
+        const float4 M = __ldg(a.sp4 + m);
+        const float2 VM = __ldg(a.var2 + m);  // {varZ, varR}
+        const float rM = M.w, varZM = VM.x, varRM = VM.y;
+        uint32_t ntop = 0;  // entries in the per-middle top-K (warp-uniform)
+
+        uint32_t row0 = 0;
+        uint32_t rows = 32;  // rows of the current block (shrinks only on list overflow)
+        while (row0 < nb) {
+            const uint32_t nrows = (nb - row0 < rows) ? (nb - row0) : rows;
+            // lane-owned mid-bottom doublet
+            const bool has_row = lane < nrows;
+            float4 la = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_row) la = __ldg(&LB[row0 + lane].a);
+            float iSinTheta2, sir2;
+            triplet_row_constants(cfg, la.x, iSinTheta2, sir2);
+            uint32_t qhead = 0, qn = 0, nlist = 0;
+            bool overflow = false;
+            for (uint32_t t = 0; t <= nt; ++t) {
+                const bool flush = (t == nt);
+                if (!flush) {
+                    const float4 ta = __ldg(&LT[t].a);  // same address for all lanes
+                    const bool p1 = has_row && triplet_cut1(la.x, la.y, la.z, ta.x, ta.y, ta.z,
+                                                            varRM, varZM, sir2);
+                    const uint32_t mask = __ballot_sync(0xffffffffu, p1);
+                    if (mask == 0u) continue;
+                    if (p1) ring[(qhead + qn + __popc(mask & ltmask)) & 63u] = (lane << 27) | t;
+                    qn += __popc(mask);
+                    __syncwarp();
+                    if (qn < 32) continue;
+                }
+                // drain: full cut on up to 32 cut-1 survivors (all of them when flushing)
+                while (qn > 0) {
+                    const uint32_t take = qn < 32 ? qn : 32;
+                    bool ok = false;
+                    uint32_t key = 0;
+                    float curvature = 0.f, impact = 0.f, rT = 0.f;
+                    if (lane < take) {
+                        key = ring[(qhead + lane) & 63u];
+                        const uint32_t row = key >> 27, tt = key & 0x07ffffffu;
+                        const float4 ba = __ldg(&LB[row0 + row].a);
+                        const float4 bb = __ldg(&LB[row0 + row].b);
+                        const float4 ta = __ldg(&LT[tt].a);
+                        const float4 tb = __ldg(&LT[tt].b);
+                        LinCircle lb, lt;
+                        lb.cotTheta = ba.x, lb.iDeltaR = ba.y, lb.Er = ba.z, lb.U = ba.w;
+                        lb.V = bb.x, lb.Zo = bb.y;
+                        lt.cotTheta = ta.x, lt.iDeltaR = ta.y, lt.Er = ta.z, lt.U = ta.w;
+                        lt.V = tb.x, lt.Zo = tb.y;
+                        float is2, s2;
+                        triplet_row_constants(cfg, lb.cotTheta, is2, s2);
+                        ok = triplet_is_compatible(cfg, rM, varRM, varZM, lb, lt, is2, s2,
+                                                   curvature, impact);
+                        rT = tb.z;
+                    }
+                    const uint32_t mk = __ballot_sync(0xffffffffu, ok);
+                    const uint32_t k = nlist + __popc(mk & ltmask);
+                    if (ok) {
+                        if (k < a.list_cap) {
+                            BlockTriplet e;
+                            e.key = key;
+                            e.curvature = curvature;
+                            e.weight = -impact * cfg.impactWeightFactor;
+                            e.rT = rT;
+                            list[k] = e;
+                        }
+                    }
+                    nlist += __popc(mk);
+                    qhead = (qhead + take) & 63u;
+                    qn -= take;
+                    __syncwarp();
+                    if (!flush) break;
+                }
+                if (nlist > a.list_cap) {
+                    overflow = true;
+                    break;
+                }
+            }
+            if (overflow) {
+                if (rows > 1) {
+                    rows >>= 1;  // redo this block with fewer rows
+                    continue;
+                }
+                // a single row with more triplets than the list holds: keep the first
+                // list_cap and flag the event (cannot happen for list_cap >= nt).
+                if (lane == 0) atomicOr(&a.ctrl->overflow, B200SEED_OVF_TRIPLETS);
+                nlist = a.list_cap;
+            }
+            acc_trip += nlist;
+
+            // ---- compatible-seed bonus (triplet_finding.hpp:107-179), lane per triplet ----
+            for (uint32_t i0 = 0; i0 < nlist; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                if (i < nlist) {
+                    const BlockTriplet cur = list[i];
+                    const uint32_t row = cur.key >> 27;
+                    const float lower = cur.curvature - cfg.deltaInvHelixDiameter;
+                    const float upper = cur.curvature + cfg.deltaInvHelixDiameter;
+                    float compat[MAX_COMPAT];
+                    uint32_t ncompat = 0;
+                    for (uint32_t j = 0; j < nlist; ++j) {
+                        if (j == i) continue;
+                        const BlockTriplet o = list[j];
+                        if ((o.key >> 27) != row) continue;
+                        const float deltaR = cur.rT - o.rT;
+                        if (absf(deltaR) < cfg.filterDeltaRMin) continue;
+                        if (o.curvature < lower) continue;
+                        if (o.curvature > upper) continue;
+                        bool newCompSeed = true;
+#pragma unroll
+                        for (uint32_t q = 0; q < MAX_COMPAT; ++q) {
+                            if (q < ncompat && absf(compat[q] - o.rT) < cfg.filterDeltaRMin)
+                                newCompSeed = false;
+                        }
+                        if (newCompSeed) {
+#pragma unroll
+                            for (uint32_t q = 0; q < MAX_COMPAT; ++q)
+                                if (q == ncompat) compat[q] = o.rT;
+                            ++ncompat;
+                        }
+                        if (ncompat >= cfg.compatSeedLimit) break;
+                    }
+                    bonus[i] = ncompat;
+                }
+            }
+            __syncwarp();
+            // ---- final weight, single-seed cut, sorter sum; optional dump ----
+            for (uint32_t i0 = 0; i0 < nlist; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                if (i < nlist) {
+                    BlockTriplet cur = list[i];
+                    const uint32_t row = cur.key >> 27, tt = cur.key & 0x07ffffffu;
+                    // the reference adds compatSeedWeight one at a time (:171)
+                    float w = cur.weight;
+                    for (uint32_t q = bonus[i]; q > 0; --q) w += cfg.compatSeedWeight;
+                    const float4 bb = __ldg(&LB[row0 + row].b);
+                    const float4 tb = __ldg(&LT[tt].b);
+                    const uint32_t pos_b = __float_as_uint(bb.w), pos_t = __float_as_uint(tb.w);
+                    if (a.dump) {
+                        const uint32_t d = atomicAdd(&a.ctrl->dump_cursor, 1u);
+                        if (d < a.max_dump) {
+                            TripletDumpRec r;
+                            r.pos_b = pos_b, r.pos_m = m, r.pos_t = pos_t, r.mb_idx = row0 + row;
+                            r.mt_idx = tt, r.curvature = cur.curvature, r.weight = w;
+                            r.z_vertex = bb.y;
+                            a.dump[d] = r;
+                        } else {
+                            atomicOr(&a.ctrl->overflow, B200SEED_OVF_DUMP);
+                        }
+                    }
+                    const float rB = bb.z, rT = tb.z;
+                    w += seed_weight_increase(cfg, rB, rT);
+                    const bool keep = single_seed_cut(cfg, rB, w);
+                    const float4 PB = __ldg(a.sp4 + pos_b);
+                    const float4 PT = __ldg(a.sp4 + pos_t);
+                    cur.weight = w;
+                    cur.rT = sorter_sum(PB.y, PB.z, PT.y, PT.z);
+                    cur.curvature = rB;
+                    cur.key = keep ? cur.key : 0xFFFFFFFFu;
+                    list[i] = cur;
+                }
+            }
+            __syncwarp();
+            // ---- merge into the per-middle top-K (triplet_sorter order, earlier first on
+            //      full ties); sequential on lane 0, the lists are short ----
+            if (lane == 0) {
+                for (uint32_t i = 0; i < nlist; ++i) {
+                    const BlockTriplet c = list[i];
+                    if (c.key == 0xFFFFFFFFu) continue;
+                    uint32_t p = ntop;
+                    while (p > 0 && seed_before(c.weight, c.rT, top_w[p - 1], top_s[p - 1])) --p;
+                    if (p >= K) continue;
+                    const uint32_t last = (ntop < K) ? ntop : (K - 1);
+                    for (uint32_t q = last; q > p; --q) {
+                        top_w[q] = top_w[q - 1];
+                        top_s[q] = top_s[q - 1];
+                        top_rb[q] = top_rb[q - 1];
+                        top_b[q] = top_b[q - 1];
+                        top_t[q] = top_t[q - 1];
+                    }
+                    const uint32_t row = c.key >> 27, tt = c.key & 0x07ffffffu;
+                    top_w[p] = c.weight;
+                    top_s[p] = c.rT;
+                    top_rb[p] = c.curvature;
+                    top_b[p] = __float_as_uint(__ldg(&LB[row0 + row].b).w);
+                    top_t[p] = __float_as_uint(__ldg(&LT[tt].b).w);
+                    if (ntop < K) ++ntop;
+                }
+            }
+            ntop = __shfl_sync(0xffffffffu, ntop, 0);
+            __syncwarp();
+            row0 += nrows;
+            rows = 32;
+        }
+        // ---- final per-middle selection (seed_filtering.cpp:84-122) ----
+        if (lane == 0) {
+            uint32_t nout = 0;
+            for (uint32_t i = 0; i < ntop; ++i) {
+                if (i == 0 || cut_per_middle_sp(cfg, top_rb[i], top_w[i])) {
+                    a.seed_b[size_t(m) * K + nout] = top_b[i];
+                    a.seed_t[size_t(m) * K + nout] = top_t[i];
+                    a.seed_w[size_t(m) * K + nout] = top_w[i];
+                    ++nout;
+                }
+            }
+            a.seed_cnt[m] = nout;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        atomicAdd(&s_ntrip, acc_trip);
+        atomicAdd(&s_tests, acc_tests);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_ntrip) atomicAdd(&a.ctrl->n_triplets, s_ntrip);
+        if (s_tests) atomicAdd(&a.ctrl->triplet_tests, s_tests);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// seeds in CPU order + counters
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_seed_gather(const uint32_t n_sp, const uint32_t K, const Control* __restrict__ ctrl,
+              const uint32_t* __restrict__ seed_cnt, const uint32_t* __restrict__ seed_off,
+              const uint32_t* __restrict__ seed_b, const uint32_t* __restrict__ seed_t,
+              const float* __restrict__ seed_w, const uint32_t* __restrict__ sorted_index,
+              const uint32_t seed_capacity, uint32_t* __restrict__ out_b,
+              uint32_t* __restrict__ out_m, uint32_t* __restrict__ out_t,
+              float* __restrict__ out_q, uint32_t* __restrict__ out_n,
+              b200seed_counters* __restrict__ counters) {
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_valid = ctrl->n_valid;
+    if (m < n_valid) {
+        const uint32_t n = seed_cnt[m];
+        const uint32_t off = seed_off[m];
+        const uint32_t mi = sorted_index[m];
+        for (uint32_t k = 0; k < n; ++k) {
+            const uint32_t o = off + k;
+            if (o < seed_capacity) {
+                out_b[o] = sorted_index[seed_b[size_t(m) * K + k]];
+                out_m[o] = mi;
+                out_t[o] = sorted_index[seed_t[size_t(m) * K + k]];
+                out_q[o] = seed_w[size_t(m) * K + k];
+            }
+        }
+    }
+    if (m == 0) {
+        const uint32_t total = ctrl->n_seeds_total;
+        const uint32_t n = total < seed_capacity ? total : seed_capacity;
+        *out_n = n;
+        if (counters) {
+            b200seed_counters c;
+            c.n_spacepoints = n_sp;
+            c.n_valid = n_valid;
+            c.n_active_middles = ctrl->n_active;
+            c.n_mid_bot = ctrl->n_mid_bot;
+            c.n_mid_top = ctrl->n_mid_top;
+            c.n_triplets = ctrl->n_triplets;
+            c.n_seeds = n;
+            c.overflow = ctrl->overflow | (total > seed_capacity ? B200SEED_OVF_SEEDS : 0u);
+            c.pair_tests = ctrl->pair_tests;
+            c.triplet_tests = ctrl->triplet_tests;
+            *counters = c;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// seed parameter estimation: one thread per seed
+// (track_params_estimation_helper.hpp:47-129, estimate_track_params.ipp:29-87)
+// ---------------------------------------------------------------------------
+struct V3 {
+    float x, y, z;
+};
+__device__ __forceinline__ V3 v3sub(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ float v3dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 v3cross(V3 a, V3 b) {
+    return {a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y};
+}
+__device__ __forceinline__ V3 v3normalize(V3 a) {
+    const float s = 1.f / sqrt_rn(v3dot(a, a));
+    return {s * a.x, s * a.y, s * a.z};
+}
+__device__ __forceinline__ float perp2(float x, float y) { return sqrt_rn(x * x + y * y); }
+
+__global__ void __launch_bounds__(128)
+k_estimate_params(const b200seed_tpe_cfg cfg, const uint32_t* __restrict__ n_seeds_dev,
+                  const uint32_t seed_capacity, const uint32_t* __restrict__ sd_b,
+                  const uint32_t* __restrict__ sd_m, const uint32_t* __restrict__ sd_t,
+                  const float* __restrict__ xyz, const uint32_t* __restrict__ sp_meas,
+                  const float* __restrict__ meas_local, const uint64_t* __restrict__ meas_surface,
+                  const float bx, const float by, const float bz,
+                  b200seed_bound_params* __restrict__ out) {
+    uint32_t n = *n_seeds_dev;
+    if (n > seed_capacity) n = seed_capacity;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t ib = sd_b[i], im = sd_m[i], it = sd_t[i];
+    const V3 p0{xyz[3 * size_t(ib)], xyz[3 * size_t(ib) + 1], xyz[3 * size_t(ib) + 2]};
+    const V3 p1{xyz[3 * size_t(im)], xyz[3 * size_t(im) + 1], xyz[3 * size_t(im) + 2]};
+    const V3 p2{xyz[3 * size_t(it)], xyz[3 * size_t(it) + 1], xyz[3 * size_t(it) + 2]};
+    const V3 bfield{bx, by, bz};
+    const V3 relVec = v3sub(p1, p0);
+    const V3 newZ = v3normalize(bfield);
+    const V3 newY = v3normalize(v3cross(newZ, relVec));
+    const V3 newX = v3cross(newY, newZ);
+    const V3 d1 = v3sub(p1, p0), d2 = v3sub(p2, p0);
+    const V3 local1{v3dot(newX, d1), v3dot(newY, d1), v3dot(newZ, d1)};
+    const V3 local2{v3dot(newX, d2), v3dot(newY, d2), v3dot(newZ, d2)};
+    const float den1 = local1.x * local1.x + local1.y * local1.y;
+    const float den2 = local2.x * local2.x + local2.y * local2.y;
+    const float u1 = local1.x / den1, v1 = local1.y / den1;
+    const float u2 = local2.x / den2, v2 = local2.y / den2;
+    const float A = (v2 - v1) / (u2 - u1);
+    const float B = v2 - A * u2;
+    const float R = -perp2(1.f, A) / (2.f * B);
+    const float invTanTheta =
+        local2.z / (2.f * R * asinf(perp2(local2.x, local2.y) / (2.f * R)));
+    const V3 td{1.f, A, perp2(1.f, A) * invTanTheta};
+    const V3 nd = v3normalize(td);
+    const V3 dir{newX.x * nd.x + newY.x * nd.y + newZ.x * nd.z,
+                 newX.y * nd.x + newY.y * nd.y + newZ.y * nd.z,
+                 newX.z * nd.x + newY.z * nd.y + newZ.z * nd.z};
+    const float phi = atan2f(dir.y, dir.x);
+    const float theta = atan2f(perp2(dir.x, dir.y), dir.z);
+    const float qOverPt = 1.f / (R * sqrt_rn(v3dot(bfield, bfield)));
+    const float qop = qOverPt / perp2(1.f, invTanTheta);
+    const uint32_t mi = sp_meas ? sp_meas[ib] : ib;
+
+    b200seed_bound_params* o = out + i;
+    float2* o2 = reinterpret_cast<float2*>(o);  // 176 bytes = 22 float2, 8-byte aligned
+#pragma unroll
+    for (int k = 0; k < 22; ++k) o2[k] = make_float2(0.f, 0.f);
+    o->surface_link = meas_surface ? meas_surface[mi] : 0ull;
+    o->vec[0] = meas_local ? meas_local[2 * size_t(mi)] : 0.f;
+    o->vec[1] = meas_local ? meas_local[2 * size_t(mi) + 1] : 0.f;
+    o->vec[2] = phi;
+    o->vec[3] = theta;
+    o->vec[4] = qop;
+    o->vec[5] = 0.f;
+    float var_theta = 0.f;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        float var = cfg.initial_sigma[j] * cfg.initial_sigma[j];
+        if (j == 4) {
+            const float sigma_qopt = cfg.initial_sigma_qopt * sinf(theta);
+            var += sigma_qopt * sigma_qopt;
+            const float sigma_pt_rel = cfg.initial_sigma_pt_rel * qop;
+            var += sigma_pt_rel * sigma_pt_rel;
+            const float sigma_theta = qop / tanf(theta);
+            var += var_theta * sigma_theta * sigma_theta;
+        }
+        var *= cfg.initial_inflation[j];
+        if (j == 3) var_theta = var;
+        o->cov[j * 6 + j] = var;
+    }
+}
+
+}  // namespace b200seed

@@ -1,0 +1,361 @@
+"""Host-side mirror of the reference's algorithm classes for the seeding path.
+
+    traccc::cuda::triplet_seeding_algorithm
+        device/cuda/include/traccc/cuda/seeding/triplet_seeding_algorithm.hpp:23-111
+    traccc::cuda::seed_parameter_estimation_algorithm
+        device/cuda/include/traccc/cuda/seeding/seed_parameter_estimation_algorithm.hpp:19-58
+
+Same names, argument meaning and error behaviour; the containers are the column arrays of
+the reference's SoA collections held as torch CUDA tensors (torch is only the device
+allocator / stream provider here). All compute goes through the C-ABI of libb200seed.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (B200SeedError, Counters, WsLayout, seedfilter_config, seedfinder_config,
+                   spacepoint_grid_config, track_params_estimation_config)
+
+BOUND_PARAMS_DTYPE = np.dtype([("surface_link", "<u8"), ("vec", "<f4", (6,)),
+                               ("cov", "<f4", (36,))])
+
+
+@dataclass
+class spacepoint_collection:
+    """edm::spacepoint_collection columns (core/include/traccc/edm/spacepoint_collection.hpp:223-234)."""
+
+    xyz: torch.Tensor                      # (N,3) f32  "global"
+    z_variance: torch.Tensor | None        # (N,) f32
+    radius_variance: torch.Tensor | None   # (N,) f32
+    measurement_index_1: torch.Tensor | None = None   # (N,) i32 (bit pattern of u32)
+
+    @property
+    def size(self) -> int:
+        return int(self.xyz.shape[0])
+
+    @staticmethod
+    def from_event(ev, device="cuda") -> "spacepoint_collection":
+        dev = torch.device(device)
+        return spacepoint_collection(
+            torch.from_numpy(ev.xyz).to(dev), torch.from_numpy(ev.var_z).to(dev),
+            torch.from_numpy(ev.var_r).to(dev),
+            torch.from_numpy(ev.meas_index.view(np.int32)).to(dev))
+
+
+@dataclass
+class measurement_collection:
+    """The two edm::measurement_collection columns the path reads
+    (core/include/traccc/edm/measurement_collection.hpp:241-260)."""
+
+    local_position: torch.Tensor   # (M,2) f32
+    surface_link: torch.Tensor     # (M,) i64 (bit pattern of the 64-bit identifier)
+
+    @staticmethod
+    def from_event(ev, device="cuda") -> "measurement_collection":
+        dev = torch.device(device)
+        return measurement_collection(torch.from_numpy(ev.meas_local).to(dev),
+                                      torch.from_numpy(ev.meas_surface.view(np.int64)).to(dev))
+
+
+@dataclass
+class seed_collection:
+    """edm::seed_collection buffer (core/include/traccc/edm/seed_collection.hpp:142-146):
+    resizable — `n_seeds` is the size word in device memory, the columns have `capacity`."""
+
+    bottom_index: torch.Tensor   # i32 bit patterns of u32
+    middle_index: torch.Tensor
+    top_index: torch.Tensor
+    quality: torch.Tensor
+    n_seeds: torch.Tensor        # (1,) i32, device
+    counters: torch.Tensor       # raw b200seed_counters bytes, device
+
+    @property
+    def capacity(self) -> int:
+        return int(self.bottom_index.shape[0])
+
+    def size(self) -> int:
+        """copy.get_size(): blocking read of the size word."""
+        return int(self.n_seeds.item())
+
+    def to_host(self) -> dict:
+        n = self.size()
+        return {"bottom": self.bottom_index[:n].cpu().numpy().view(np.uint32),
+                "middle": self.middle_index[:n].cpu().numpy().view(np.uint32),
+                "top": self.top_index[:n].cpu().numpy().view(np.uint32),
+                "quality": self.quality[:n].cpu().numpy()}
+
+    def host_counters(self) -> dict:
+        raw = self.counters.cpu().numpy().tobytes()
+        return Counters.from_buffer_copy(raw).as_dict()
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream_handle(stream) -> C.c_void_p:
+    if stream is None:
+        stream = torch.cuda.current_stream()
+    return C.c_void_p(stream.cuda_stream)
+
+
+class _Handle:
+    def __init__(self, finder, grid, filt, tpe, device):
+        self.lib = _lib.lib()
+        if not torch.cuda.is_available():
+            raise B200SeedError("no CUDA device: the seeding path has no CPU fallback")
+        h = C.c_void_p()
+        rc = self.lib.b200seed_create(C.byref(finder), C.byref(grid), C.byref(filt),
+                                      C.byref(tpe) if tpe is not None else None, int(device),
+                                      C.byref(h))
+        _lib.check(rc, None)
+        self.h = h
+        self.device = int(device)
+
+    def __del__(self):
+        h = getattr(self, "h", None)
+        if h:
+            self.lib.b200seed_destroy(h)
+            self.h = None
+
+
+class triplet_seeding_algorithm:
+    """Drop-in for traccc::cuda::triplet_seeding_algorithm.
+
+    ctor(finder_config, grid_config, filter_config, device, stream) replaces
+    (finder, grid, filter, memory_resource, copy, stream_wrapper, logger); __call__ takes
+    the spacepoint view and returns the (not necessarily filled yet) seed buffer.
+    """
+
+    def __init__(self, finder_config: seedfinder_config, grid_config: spacepoint_grid_config,
+                 filter_config: seedfilter_config, device: int = 0, stream=None,
+                 max_doublets: int = 0, triplet_dump: int = 0):
+        self._hd = _Handle(finder_config, grid_config, filter_config, None, device)
+        self.lib = self._hd.lib
+        self.h = self._hd.h
+        self.device = int(device)
+        self.stream = stream
+        self.finder_config = finder_config
+        self._ws = None
+        self._ws_n = 0
+        if max_doublets:
+            _lib.check(self.lib.b200seed_set_max_doublets(self.h, int(max_doublets)), self.h)
+        if triplet_dump:
+            _lib.check(self.lib.b200seed_set_triplet_dump(self.h, int(triplet_dump)), self.h)
+
+    # --- introspection -------------------------------------------------------------
+    def axes(self):
+        n_phi, n_z = C.c_uint32(), C.c_uint32()
+        pmin, pmax, zmin, zmax = C.c_float(), C.c_float(), C.c_float(), C.c_float()
+        _lib.check(self.lib.b200seed_get_axes(self.h, C.byref(n_phi), C.byref(pmin), C.byref(pmax),
+                                              C.byref(n_z), C.byref(zmin), C.byref(zmax)), self.h)
+        return (n_phi.value, pmin.value, pmax.value), (n_z.value, zmin.value, zmax.value)
+
+    def workspace_bytes(self, n: int) -> int:
+        return int(self.lib.b200seed_workspace_bytes(self.h, int(n)))
+
+    def layout(self, n: int) -> WsLayout:
+        out = WsLayout()
+        _lib.check(self.lib.b200seed_workspace_layout(self.h, int(n), C.byref(out)), self.h)
+        return out
+
+    def set_timing(self, on: bool):
+        _lib.check(self.lib.b200seed_set_timing(self.h, 1 if on else 0), self.h)
+
+    def timings(self) -> dict:
+        names = (C.c_char_p * 16)()
+        ms = (C.c_float * 16)()
+        n = _lib.check(self.lib.b200seed_get_timings(self.h, names, ms, 16), self.h)
+        out = {}
+        for i in range(n):
+            out[names[i].decode()] = out.get(names[i].decode(), 0.0) + float(ms[i])
+        return out
+
+    def launches_per_event(self, with_params: bool) -> int:
+        return int(self.lib.b200seed_launches_per_event(self.h, 1 if with_params else 0))
+
+    # --- the hot path ----------------------------------------------------------------
+    def workspace(self, n: int) -> torch.Tensor:
+        need = self.workspace_bytes(n)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=f"cuda:{self.device}")
+        self._ws_n = n
+        return self._ws
+
+    def __call__(self, spacepoints: spacepoint_collection, out: seed_collection | None = None,
+                 stream=None) -> seed_collection:
+        n = spacepoints.size
+        dev = f"cuda:{self.device}"
+        K = max(int(self.finder_config.maxSeedsPerSpM), 1)
+        if out is None:
+            cap = max(n * K, 1)
+            out = seed_collection(
+                torch.empty(cap, dtype=torch.int32, device=dev),
+                torch.empty(cap, dtype=torch.int32, device=dev),
+                torch.empty(cap, dtype=torch.int32, device=dev),
+                torch.empty(cap, dtype=torch.float32, device=dev),
+                torch.zeros(1, dtype=torch.int32, device=dev),
+                torch.zeros(C.sizeof(Counters), dtype=torch.uint8, device=dev))
+        ws = self.workspace(n) if n else None
+        rc = self.lib.b200seed_run(
+            self.h, _stream_handle(stream or self.stream), n, _ptr(spacepoints.xyz),
+            _ptr(spacepoints.z_variance), _ptr(spacepoints.radius_variance), _ptr(ws),
+            ws.numel() if ws is not None else 0, out.capacity, _ptr(out.bottom_index),
+            _ptr(out.middle_index), _ptr(out.top_index), _ptr(out.quality), _ptr(out.n_seeds),
+            _ptr(out.counters))
+        _lib.check(rc, self.h)
+        return out
+
+    def read_workspace(self, n: int) -> dict:
+        """Intermediate arrays of the last event of n spacepoints (parity tests)."""
+        L = self.layout(n)
+        torch.cuda.synchronize()
+        ws = self._ws.cpu().numpy()
+
+        def arr(off, dtype, count):
+            return np.frombuffer(ws, dtype=dtype, count=count, offset=off).copy()
+
+        nb = L.n_bins
+        bin_offsets = arr(L.bin_offsets, np.uint32, nb + 1)
+        nv = int(bin_offsets[-1])
+        res = {"bin_offsets": bin_offsets,
+               "sorted_index": arr(L.sorted_index, np.uint32, nv),
+               "sp_xyzr": arr(L.sp_xyzr, np.float32, 4 * nv).reshape(nv, 4),
+               "mid_counts": arr(L.mid_counts, np.uint32, 2 * n).reshape(2, n)[:, :nv],
+               "mid_offsets": arr(L.mid_offsets, np.uint32, 2 * n).reshape(2, n)[:, :nv]}
+        md = int(L.max_doublets)
+        rec = np.dtype([("cotTheta", "<f4"), ("iDeltaR", "<f4"), ("Er", "<f4"), ("U", "<f4"),
+                        ("V", "<f4"), ("Zo", "<f4"), ("r", "<f4"), ("pos", "<u4")])
+        for d, name in ((0, "bottom"), (1, "top")):
+            cnt = res["mid_counts"][d].astype(np.int64)
+            off = res["mid_offsets"][d].astype(np.int64)
+            used = int((off + cnt).max()) if nv and cnt.sum() else 0
+            a = np.frombuffer(ws, dtype=rec, count=used, offset=L.doublets + d * _align(md * 32))
+            # gather the per-middle lists in sorted-position (canonical) order
+            idx = np.concatenate([np.arange(o, o + c) for o, c in zip(off, cnt) if c]) if used else np.zeros(0, np.int64)
+            res[f"doublets_{name}"] = a[idx].copy()
+            res[f"doublets_{name}_mid"] = np.repeat(np.arange(nv), cnt)
+        if L.max_triplet_dump:
+            ndump = int(arr(L.triplet_dump_count, np.uint32, 1)[0])
+            trec = np.dtype([("pos_b", "<u4"), ("pos_m", "<u4"), ("pos_t", "<u4"), ("mb_idx", "<u4"),
+                             ("mt_idx", "<u4"), ("curvature", "<f4"), ("weight", "<f4"),
+                             ("z_vertex", "<f4")])
+            t = np.frombuffer(ws, dtype=trec, count=min(ndump, int(L.max_triplet_dump)),
+                              offset=L.triplet_dump).copy()
+            order = np.lexsort((t["mt_idx"], t["mb_idx"], t["pos_m"]))
+            res["triplets"] = t[order]
+        return res
+
+
+def _align(v, a=256):
+    return (v + a - 1) // a * a
+
+
+class seed_parameter_estimation_algorithm:
+    """Drop-in for traccc::cuda::seed_parameter_estimation_algorithm: ctor(config, device,
+    stream); __call__(bfield, measurements, spacepoints, seeds) -> bound track parameters
+    buffer (one 176-byte record per seed capacity slot; the first n_seeds are filled)."""
+
+    def __init__(self, config: track_params_estimation_config | None = None, device: int = 0,
+                 stream=None):
+        finder = seedfinder_config()
+        self.config = config or track_params_estimation_config()
+        self._hd = _Handle(finder, spacepoint_grid_config(finder), seedfilter_config(), self.config,
+                           device)
+        self.lib = self._hd.lib
+        self.h = self._hd.h
+        self.device = int(device)
+        self.stream = stream
+
+    def __call__(self, bfield, measurements: measurement_collection,
+                 spacepoints: spacepoint_collection, seeds: seed_collection,
+                 out: torch.Tensor | None = None, stream=None) -> torch.Tensor:
+        cap = seeds.capacity
+        if out is None:
+            out = torch.empty(cap * BOUND_PARAMS_DTYPE.itemsize, dtype=torch.uint8,
+                              device=f"cuda:{self.device}")
+        bf = (C.c_float * 3)(*[float(b) for b in bfield])
+        rc = self.lib.b200seed_estimate_params(
+            self.h, _stream_handle(stream or self.stream), _ptr(seeds.n_seeds), cap,
+            _ptr(seeds.bottom_index), _ptr(seeds.middle_index), _ptr(seeds.top_index),
+            _ptr(spacepoints.xyz), _ptr(spacepoints.measurement_index_1),
+            _ptr(measurements.local_position), _ptr(measurements.surface_link), C.byref(bf),
+            _ptr(out))
+        _lib.check(rc, self.h)
+        return out
+
+    @staticmethod
+    def to_host(params: torch.Tensor, n: int) -> np.ndarray:
+        raw = params[: n * BOUND_PARAMS_DTYPE.itemsize].cpu().numpy()
+        return np.frombuffer(raw.tobytes(), dtype=BOUND_PARAMS_DTYPE)
+
+
+class HostPipeline:
+    """The end-to-end call with HOST buffers (b200seed_run_host): H->D of the event,
+    seeding, parameter estimation, D->H of seeds and parameters — what
+    examples/run/cuda/apps/seeding_example_cuda.cpp:264-356 does around the two algorithms."""
+
+    def __init__(self, finder_config=None, grid_config=None, filter_config=None, tpe_config=None,
+                 device: int = 0, max_seeds: int = 0):
+        self.finder = finder_config or seedfinder_config()
+        self.grid = grid_config or spacepoint_grid_config(self.finder)
+        self.filter = filter_config or seedfilter_config()
+        self.tpe = tpe_config or track_params_estimation_config()
+        self._hd = _Handle(self.finder, self.grid, self.filter, self.tpe, device)
+        self.lib = self._hd.lib
+        self.h = self._hd.h
+        self.device = int(device)
+        self._cap = 0
+        self._out = None
+        if max_seeds:
+            self._alloc(max_seeds)
+
+    def _alloc(self, cap):
+        pin = dict(pin_memory=True)
+        self._out = {"bottom": torch.empty(cap, dtype=torch.int32, **pin),
+                     "middle": torch.empty(cap, dtype=torch.int32, **pin),
+                     "top": torch.empty(cap, dtype=torch.int32, **pin),
+                     "quality": torch.empty(cap, dtype=torch.float32, **pin),
+                     "params": torch.empty(cap * BOUND_PARAMS_DTYPE.itemsize, dtype=torch.uint8, **pin)}
+        self._cap = cap
+
+    def run(self, xyz, var_z, var_r, meas_index, meas_local, meas_surface, bfield, stream=None,
+            with_params=True):
+        """All inputs are host tensors / numpy arrays (pinned for asynchronous copies)."""
+        def hp(a):
+            if a is None:
+                return None
+            if isinstance(a, torch.Tensor):
+                return C.c_void_p(a.data_ptr())
+            return a.ctypes.data_as(C.c_void_p)
+
+        n = int(xyz.shape[0])
+        n_meas = int(meas_local.shape[0]) if meas_local is not None else 0
+        K = max(int(self.finder.maxSeedsPerSpM), 1)
+        if self._cap < n * K:
+            self._alloc(max(n * K, 1))
+        bf = (C.c_float * 3)(*[float(b) for b in bfield])
+        n_seeds = C.c_uint32(0)
+        cnt = Counters()
+        rc = self.lib.b200seed_run_host(
+            self.h, _stream_handle(stream), n, hp(xyz), hp(var_z), hp(var_r), hp(meas_index), n_meas,
+            hp(meas_local), hp(meas_surface), C.byref(bf), self._cap, hp(self._out["bottom"]),
+            hp(self._out["middle"]), hp(self._out["top"]), hp(self._out["quality"]),
+            hp(self._out["params"]) if with_params else None, C.byref(n_seeds), C.byref(cnt))
+        _lib.check(rc, self.h)
+        ns = int(n_seeds.value)
+        res = {"n_seeds": ns, "counters": cnt.as_dict(),
+               "bottom": self._out["bottom"][:ns].numpy().view(np.uint32),
+               "middle": self._out["middle"][:ns].numpy().view(np.uint32),
+               "top": self._out["top"][:ns].numpy().view(np.uint32),
+               "quality": self._out["quality"][:ns].numpy()}
+        if with_params:
+            res["params"] = np.frombuffer(
+                self._out["params"][: ns * BOUND_PARAMS_DTYPE.itemsize].numpy().tobytes(),
+                dtype=BOUND_PARAMS_DTYPE)
+        return res
