@@ -1,0 +1,444 @@
+#!/usr/bin/env python
+"""bench.py — seeded events/s of the triplet-seeding + parameter-estimation path.
+
+    python bench.py --gpus N --steps K --warmup W          (our CUDA path)
+    python bench.py --impl reference --gpus N ...          (reference CPU algorithm on host cores)
+
+Workload (BASELINE.json configs[1]): synthetic toy-detector events with 10k particles
+(~46k spacepoints) each. One *step* = one batch of `--events` distinct events pushed
+through `--streams` algorithm instances / CUDA streams of one GPU (the reference's
+throughput apps run one full_chain_algorithm + stream per host thread the same way,
+examples/run/common/include/traccc/examples/impl/throughput_mt.ipp:170-298).
+`value` = whole-job events/s with the events resident in HBM; `e2e` = the same through
+b200seed_run_host with pinned HOST buffers (H->D and D->H inside the timed region).
+Events are independent: with N GPUs every rank processes its own batch (weak scaling),
+no data-path collective; torch.distributed is only used for the timing barrier / max.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "seeded_events_per_second"
+UNIT = "events/s"
+N_PARTICLES = 10000
+WORKLOAD = "toy detector, 10k particles/event (~46k spacepoints), default seeding config (78x1 bins)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--events", type=int, default=32, help="events per step per GPU")
+    ap.add_argument("--streams", type=int, default=8, help="algorithm instances / streams per GPU")
+    ap.add_argument("--particles", type=int, default=N_PARTICLES)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-one", action="store_true",
+                    help="run a single event once (for ncu) and exit")
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def gen_events(n_events, particles, base_seed):
+    from traccc_b200 import toy_detector
+    return [toy_detector.generate_event(particles, base_seed + i) for i in range(n_events)]
+
+
+# ----------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle's restatement of host::seeding_algorithm +
+# host::track_params_estimation on the host cores, one event per thread
+# (the pattern of throughput_mt.ipp:202-298).
+# ----------------------------------------------------------------------------------
+def cpu_threads():
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(n, 64))
+
+
+def cpu_step(events, threads, bins=None):
+    """Process len(events) events on `threads` host threads; returns seconds."""
+    from oracle import oracle
+    oracle.lib()
+    work = list(range(len(events)))
+    lock = threading.Lock()
+
+    def worker():
+        while True:
+            with lock:
+                if not work:
+                    return
+                i = work.pop()
+            ev = events[i]
+            oracle.run(ev.xyz, ev.var_z, ev.var_r, dump=False, sp_meas_index=ev.meas_index,
+                       meas_local=ev.meas_local, meas_surface=ev.meas_surface, bfield=ev.bfield,
+                       bins=bins)
+
+    ts = [threading.Thread(target=worker) for _ in range(threads)]
+    t0 = time.perf_counter()
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    threads = cpu_threads()
+    events = gen_events(threads, args.particles, 1000)
+    n_phi = 78
+    # bounded sample: keep the whole run within a few minutes by processing only the
+    # middles of the first `nb` phi bins of every event (exactly proportional work)
+    t_probe = cpu_step(events[:threads], threads, bins=(0, 4))
+    per_bin = t_probe / 4.0
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    nb = int(max(1, min(n_phi, budget / max(per_bin, 1e-6))))
+    frac = nb / n_phi
+    for _ in range(args.warmup):
+        cpu_step(events, threads, bins=(0, nb))
+    total = 0.0
+    for _ in range(args.steps):
+        total += cpu_step(events, threads, bins=(0, nb))
+    ev_per_s = args.steps * len(events) * frac / total
+    sample = (f"{len(events)} events x {nb}/{n_phi} phi-bins of middles per step, one event per "
+              f"thread, oracle port of host::seeding_algorithm + track_params_estimation")
+    line = {"impl": "reference", "metric": METRIC, "value": ev_per_s, "unit": UNIT,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "events_per_step": len(events) * frac},
+            "cpu_baseline": {"value": ev_per_s, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": ev_per_s, "unit": UNIT, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "spacepoints_per_second": ev_per_s * float(np.mean([e.n_spacepoints for e in events]))}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        self.gpu = gpu_index
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(gpu_index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for ln in open(self.path):
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        finally:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from traccc_b200 import (_lib, seedfilter_config, seedfinder_config, seeding,
+                             spacepoint_grid_config)
+
+    rank, world, local = dist_env()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    E, S = args.events, max(1, min(args.streams, args.events))
+    events = gen_events(E, args.particles, 100 + 1000 * rank)
+    finder = seedfinder_config()
+    grid = spacepoint_grid_config(finder)
+    filt = seedfilter_config()
+    streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
+    algs = [seeding.triplet_seeding_algorithm(finder, grid, filt, device=local) for _ in range(S)]
+    tpes = [seeding.seed_parameter_estimation_algorithm(device=local) for _ in range(S)]
+    max_n = max(e.n_spacepoints for e in events)
+    for a in algs:
+        a.workspace(max_n)
+    K5 = max(int(finder.maxSeedsPerSpM), 1)
+
+    # device-resident inputs + preallocated outputs (one set per event)
+    d_sps = [seeding.spacepoint_collection.from_event(e, dev) for e in events]
+    d_meas = [seeding.measurement_collection.from_event(e, dev) for e in events]
+
+    def new_out(n):
+        cap = n * K5
+        return seeding.seed_collection(
+            torch.empty(cap, dtype=torch.int32, device=dev), torch.empty(cap, dtype=torch.int32, device=dev),
+            torch.empty(cap, dtype=torch.int32, device=dev), torch.empty(cap, dtype=torch.float32, device=dev),
+            torch.zeros(1, dtype=torch.int32, device=dev), torch.zeros(48, dtype=torch.uint8, device=dev))
+
+    d_out = [new_out(e.n_spacepoints) for e in events]
+    d_par = [torch.empty(o.capacity * 176, dtype=torch.uint8, device=dev) for o in d_out]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step_device():
+        for i in range(E):
+            s = streams[i % S]
+            algs[i % S](d_sps[i], out=d_out[i], stream=s)
+            tpes[i % S](events[i].bfield, d_meas[i], d_sps[i], d_out[i], out=d_par[i], stream=s)
+
+    def timed(step_fn, k, w):
+        main = torch.cuda.current_stream()
+        for _ in range(w):
+            step_fn()
+            torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        total_ms = 0.0
+        for _ in range(k):
+            flush.fill_(1)                       # evict L2 between timed iterations (untimed)
+            torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(main)
+            for s in streams:
+                s.wait_event(e0)
+            step_fn()
+            for s in streams:
+                ev = torch.cuda.Event()
+                ev.record(s)
+                main.wait_event(ev)
+            e1.record(main)
+            e1.synchronize()
+            total_ms += e0.elapsed_time(e1)
+        torch.cuda.synchronize()
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    if args.profile_one:
+        algs[0](d_sps[0], out=d_out[0], stream=streams[0])
+        tpes[0](events[0].bfield, d_meas[0], d_sps[0], d_out[0], out=d_par[0], stream=streams[0])
+        torch.cuda.synchronize()
+        algs[0](d_sps[0], out=d_out[0], stream=streams[0])
+        tpes[0](events[0].bfield, d_meas[0], d_sps[0], d_out[0], out=d_par[0], stream=streams[0])
+        torch.cuda.synchronize()
+        print(json.dumps(d_out[0].host_counters()))
+        return
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    total_ms = timed(step_device, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    ev_per_s = world * E * args.steps / (total_ms * 1e-3)
+    counters = [o.host_counters() for o in d_out]
+    assert all(c["overflow"] == 0 for c in counters), "overflow flag set: results incomplete"
+    mean_sp = float(np.mean([e.n_spacepoints for e in events]))
+
+    # ---- end to end through the host-buffer C-ABI call, one host thread per stream ----
+    pipes = [seeding.HostPipeline(finder, grid, filt, device=local, max_seeds=max_n * K5) for _ in range(S)]
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_in = [(pin(e.xyz), pin(e.var_z), pin(e.var_r), pin(e.meas_index.view(np.int32)),
+             pin(e.meas_local), pin(e.meas_surface.view(np.int64))) for e in events]
+    h2d = sum(sum(t.numel() * t.element_size() for t in x) for x in h_in)
+    d2h_box = [0]
+    errs = []
+
+    def e2e_worker(k, acc):
+        try:
+            torch.cuda.set_device(local)
+            n = 0
+            for i in range(k, E, S):
+                r = pipes[k].run(*h_in[i], events[i].bfield, stream=streams[k])
+                n += 48 + r["n_seeds"] * (16 + 176)
+            acc[k] = n
+        except Exception as ex:   # surface errors from worker threads
+            errs.append(ex)
+
+    def step_e2e():
+        acc = [0] * S
+        ts = [threading.Thread(target=e2e_worker, args=(k, acc)) for k in range(S)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        if errs:
+            raise errs[0]
+        d2h_box[0] = sum(acc)
+
+    def timed_wall(step_fn, k, w):
+        for _ in range(w):
+            step_fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            step_fn()
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    e2e_s = timed_wall(step_e2e, args.steps, args.warmup)
+    e2e_ev_per_s = world * E * args.steps / e2e_s
+
+    # ---- per-kernel device times (CUDA events on the launching stream) for the roofline ----
+    algs[0].set_timing(True)
+    kt = {}
+    reps = 8
+    for i in range(reps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        algs[0](d_sps[i % E], out=d_out[i % E], stream=streams[0])
+        for k, v in algs[0].timings().items():
+            kt[k] = kt.get(k, 0.0) + v / reps
+    algs[0].set_timing(False)
+    c_mean = {k: float(np.mean([c[k] for c in counters])) for k in counters[0]}
+
+    line = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s"
+        fp32 = C.c_double(0)
+        _lib.check(_lib.lib().b200seed_measure_fp32_peak(local, C.byref(fp32)))
+        fp32_peak_tops = fp32.value / 1e12
+        # dominant kernel = the one with the largest share of the per-event device time
+        dom = max(kt, key=kt.get)
+        # algorithmic FP32 ops of the two search kernels:
+        #   doublets: 2*14 ops per scanned pair (both directions) + 38 per stage-1 survivor
+        #             (survivors are not counted on the device: lower bound uses final doublets)
+        #             + 25 per lin_circle;   triplets: 51 per (mid-bot, mid-top) combination
+        ops = {"doublets": c_mean["pair_tests"] * 28 + (c_mean["n_mid_bot"] + c_mean["n_mid_top"]) * (38 + 25),
+               "triplets": c_mean["triplet_tests"] * 51}
+        # algorithmic HBM bytes of the streaming kernels
+        n_sp, n_valid = c_mean["n_spacepoints"], c_mean["n_valid"]
+        byts = {"bin_count": n_sp * (12 + 4), "bin_scatter": n_sp * (12 + 8 + 4) + n_valid * (16 + 8 + 4 + 4),
+                "seed_gather": c_mean["n_seeds"] * 16 + n_valid * 8,
+                "estimate_params": c_mean["n_seeds"] * (16 + 36 + 16 + 176)}
+        if dom in ops:
+            ach = ops[dom] / (kt[dom] * 1e-3) / 1e12
+            roof = {"bound": "fp32", "kernel": "k_" + dom, "achieved": ach, "peak": fp32_peak_tops,
+                    "unit": "Tops/s (non-fused fp32, algorithmic full-cost ops)",
+                    "frac": ach / fp32_peak_tops if fp32_peak_tops else None, "traffic": None,
+                    "peak_source": "measured in-run by b200seed_measure_fp32_peak (FMUL+FADD chains, -fmad=false)",
+                    "ms_per_launch": kt[dom]}
+        else:
+            ach = byts.get(dom, 0.0) / (kt[dom] * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": "k_" + dom, "achieved": ach, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                    "ms_per_launch": kt[dom]}
+        ev_bytes = sum(byts.values()) + (c_mean["n_mid_bot"] + c_mean["n_mid_top"]) * 32 * 2
+        ev_ms = sum(kt.values())
+        roof["per_kernel_ms"] = kt
+        roof["whole_event"] = {
+            "device_ms_serial": ev_ms,
+            "fp32_frac": (sum(ops.values()) / (ev_ms * 1e-3) / 1e12) / fp32_peak_tops if fp32_peak_tops else None,
+            "hbm_frac": (ev_bytes / (ev_ms * 1e-3) / 1e9) / hbm_peak, "hbm_peak_source": hbm_src}
+        line = {"metric": METRIC, "value": ev_per_s, "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "events_per_step_per_gpu": E, "streams_per_gpu": S,
+                           "spacepoints_per_event": mean_sp, "parallelism": f"events sharded over {world} GPU(s), no collective",
+                           "l2": "flushed between timed steps (256 MiB write, untimed)"},
+                "spacepoints_per_second": ev_per_s * mean_sp,
+                "gpu_launches": E * args.steps * algs[0].launches_per_event(True),
+                "e2e": {"value": e2e_ev_per_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h_box[0],
+                        "how": f"b200seed_run_host from pinned host buffers, {S} host threads/streams"},
+                "roofline": roof, "clocks": clocks,
+                "event_counters_mean": c_mean}
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ----
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = cpu_threads()
+        evs = (events * ((threads + E - 1) // E))[:threads]
+        t_probe = cpu_step(evs, threads, bins=(0, 2))
+        nb = int(max(1, min(78, 12.0 / max(t_probe / 2.0, 1e-6))))
+        t = cpu_step(evs, threads, bins=(0, nb))
+        v = len(evs) * (nb / 78.0) / t
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"{len(evs)} events x {nb}/78 phi-bins of middles, one event per thread "
+                                          f"({t:.1f} s), oracle port of host::seeding_algorithm + track_params_estimation"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

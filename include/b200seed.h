@@ -281,6 +281,10 @@ int b200seed_get_timings(b200seed_handle* h, const char** names, float* ms, int 
 /* Number of kernels one b200seed_run (+ estimate_params) launches. */
 int b200seed_launches_per_event(const b200seed_handle* h, int with_params);
 
+/* Measured non-fused FP32 rate of `device` in ops/s (FMUL/FADD issue rate; the library is
+ * built without FMA contraction): the FP32 roofline denominator of bench.py. */
+int b200seed_measure_fp32_peak(int device, double* ops_per_s);
+
 const char* b200seed_version(void);
 
 #ifdef __cplusplus

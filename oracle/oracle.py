@@ -87,6 +87,8 @@ def lib() -> C.CDLL:
         L.oracle_run.restype = C.c_void_p
         L.oracle_run.argtypes = [C.POINTER(FinderCfg), C.POINTER(GridCfg), C.POINTER(FilterCfg),
                                  C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.oracle_run_bins.restype = C.c_void_p
+        L.oracle_run_bins.argtypes = L.oracle_run.argtypes + [C.c_uint32, C.c_uint32]
         L.oracle_free.argtypes = [C.c_void_p]
         L.oracle_status.argtypes = [C.c_void_p]
         L.oracle_sizes.argtypes = [C.c_void_p, C.c_void_p]
@@ -164,7 +166,8 @@ class OracleEvent:
 
 
 def run(xyz, var_z=None, var_r=None, finder=None, grid=None, filt=None, dump=True,
-        tpe=None, sp_meas_index=None, meas_local=None, meas_surface=None, bfield=None) -> OracleEvent:
+        tpe=None, sp_meas_index=None, meas_local=None, meas_surface=None, bfield=None,
+        bins=None) -> OracleEvent:
     """host::seeding_algorithm (+ host::track_params_estimation when bfield is given)."""
     L = lib()
     d = default_configs()
@@ -177,8 +180,9 @@ def run(xyz, var_z=None, var_r=None, finder=None, grid=None, filt=None, dump=Tru
     n = xyz.shape[0]
     vz = None if var_z is None else np.ascontiguousarray(var_z, dtype=np.float32)
     vr = None if var_r is None else np.ascontiguousarray(var_r, dtype=np.float32)
-    h = L.oracle_run(C.byref(finder), C.byref(grid), C.byref(filt), n, _ptr(xyz), _ptr(vz),
-                     _ptr(vr), 1 if dump else 0)
+    lo, hi = bins if bins is not None else (0, 0xFFFFFFFF)
+    h = L.oracle_run_bins(C.byref(finder), C.byref(grid), C.byref(filt), n, _ptr(xyz), _ptr(vz),
+                          _ptr(vr), 1 if dump else 0, lo, hi)
     try:
         if L.oracle_status(h) != 0:
             raise ValueError("get_axes: std::domain_error in the reference")

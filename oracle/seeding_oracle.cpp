@@ -515,6 +515,7 @@ struct Oracle {
     std::vector<Sp> sps;
     Grid grid;
     int dump = 0;
+    uint32_t bin_lo = 0, bin_hi = 0xFFFFFFFFu;  // middle bins to process (bounded samples)
     oracle_result* res = nullptr;
 
     const Sp& at(const SpLoc& l) const { return sps[grid.bins[l.bin_idx][l.sp_idx]]; }
@@ -684,7 +685,7 @@ struct Oracle {
         std::vector<SpLoc> bots, tops;
         std::vector<LinCircle> bot_lcs, top_lcs;
         std::vector<Triplet> triplets, for_mid_bot;
-        for (uint32_t i = 0; i < grid.nbins(); ++i) {
+        for (uint32_t i = bin_lo; i < grid.nbins() && i < bin_hi; ++i) {
             const auto& middle_indices = grid.bins[i];
             for (uint32_t j = 0; j < middle_indices.size(); ++j) {
                 SpLoc spM_location{i, j};
@@ -1024,11 +1025,25 @@ int oracle_triplet_is_compatible(const float m[5], const float lb[6], const floa
 
 // host::seeding_algorithm::operator() — core/src/seeding/seeding_algorithm.cpp:24-28.
 // dump != 0 additionally records grid, doublets and triplets.
+// oracle_run_bins restricts the middle-spacepoint loop (seed_finding.cpp:69) to the bins
+// [bin_lo, bin_hi): a bounded, exactly proportional sample of an event for CPU timing.
+oracle_result* oracle_run_bins(const b200seed_finder_cfg* finder, const b200seed_grid_cfg* grid,
+                               const b200seed_filter_cfg* filter, uint32_t n_sp, const float* xyz,
+                               const float* var_z, const float* var_r, int dump, uint32_t bin_lo,
+                               uint32_t bin_hi);
 oracle_result* oracle_run(const b200seed_finder_cfg* finder, const b200seed_grid_cfg* grid,
                           const b200seed_filter_cfg* filter, uint32_t n_sp, const float* xyz,
                           const float* var_z, const float* var_r, int dump) {
+    return oracle_run_bins(finder, grid, filter, n_sp, xyz, var_z, var_r, dump, 0, 0xFFFFFFFFu);
+}
+oracle_result* oracle_run_bins(const b200seed_finder_cfg* finder, const b200seed_grid_cfg* grid,
+                               const b200seed_filter_cfg* filter, uint32_t n_sp, const float* xyz,
+                               const float* var_z, const float* var_r, int dump, uint32_t bin_lo,
+                               uint32_t bin_hi) {
     oracle_result* res = new oracle_result();
     Oracle o;
+    o.bin_lo = bin_lo;
+    o.bin_hi = bin_hi;
     o.fc = *finder;
     o.flc = *filter;
     o.dump = dump;

@@ -21,9 +21,14 @@ def oracle_cfgs(finder=None, grid=None, filt=None):
 def rel_close(a, b, tol=1e-5):
     """The reference comparator's formula: |a-b| <= tol * (|a|+|b|)/2
     (performance/src/performance/details/is_same_scalar.cpp:16-22)."""
+    a32, b32 = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    same_bits = a32.view(np.uint32) == b32.view(np.uint32)     # covers +-inf
+    both_nan = np.isnan(a32) & np.isnan(b32)                   # degenerate (collinear) seeds
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
-    return np.abs(a - b) <= tol * 0.5 * (np.abs(a) + np.abs(b)) + 1e-300
+    with np.errstate(invalid="ignore"):
+        close = np.abs(a - b) <= tol * 0.5 * (np.abs(a) + np.abs(b)) + 1e-300
+    return close | same_bits | both_nan
 
 
 def canonical_doublets(ws, which):

@@ -104,7 +104,8 @@ EXPORTS = (
     "b200seed_destroy", "b200seed_last_error", "b200seed_get_axes", "b200seed_set_max_doublets",
     "b200seed_workspace_bytes", "b200seed_run", "b200seed_estimate_params", "b200seed_run_host",
     "b200seed_workspace_layout", "b200seed_set_triplet_dump", "b200seed_set_timing",
-    "b200seed_get_timings", "b200seed_launches_per_event", "b200seed_version")
+    "b200seed_get_timings", "b200seed_launches_per_event", "b200seed_measure_fp32_peak",
+    "b200seed_version")
 
 _lib = None
 
@@ -149,6 +150,7 @@ def lib() -> C.CDLL:
     L.b200seed_get_timings.argtypes = [vp, vp, vp, C.c_int]
     L.b200seed_launches_per_event.argtypes = [vp, C.c_int]
     L.b200seed_version.restype = C.c_char_p
+    L.b200seed_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.b200seed_host_probe_devcfg.argtypes = [C.POINTER(seedfinder_config),
                                              C.POINTER(spacepoint_grid_config),
                                              C.POINTER(seedfilter_config), vp, sz]

@@ -413,8 +413,11 @@ int b200seed_create(const b200seed_finder_cfg* finder, const b200seed_grid_cfg* 
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     // allow the large dynamic shared memory configurations
-    cudaFuncSetAttribute(k_doublets, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin);
-    cudaFuncSetAttribute(k_triplets, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin);
+    // (static shared memory counts against the same limit, hence the margin)
+    cudaFuncSetAttribute(k_doublets, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         h->smem_optin - 1024);
+    cudaFuncSetAttribute(k_triplets, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         h->smem_optin - 1024);
     e = cudaGetLastError();
     if (e != cudaSuccess) {
         std::string msg = std::string("kernel image not usable on this device (built for sm_100a): ") +
@@ -662,7 +665,8 @@ int b200seed_estimate_params(b200seed_handle* h, void* stream, const uint32_t* d
                              const float bfield[3], b200seed_bound_params* d_params) {
     if (!h) return B200SEED_EINVAL;
     if (seed_capacity == 0) return B200SEED_OK;
-    if (!d_n_seeds || !d_bottom || !d_middle || !d_top || !d_xyz || !bfield || !d_params)
+    if (!d_xyz) return B200SEED_OK;  // no spacepoints => no seeds (…estimation_algorithm.cpp:49-51)
+    if (!d_n_seeds || !d_bottom || !d_middle || !d_top || !bfield || !d_params)
         return fail(h, B200SEED_EINVAL, "b200seed_estimate_params: null pointer");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     CUDA_TRY(h, cudaSetDevice(h->device));
@@ -773,6 +777,39 @@ int b200seed_run_host(b200seed_handle* h, void* stream, uint32_t n_sp, const flo
                                         cudaMemcpyDeviceToHost, s));
         CUDA_TRY(h, cudaStreamSynchronize(s));
     }
+    return B200SEED_OK;
+}
+
+// Measured non-fused FP32 rate of the device (ops/s) — the denominator bench.py uses for the
+// FP32-issue roofline of the doublet / triplet kernels.
+int b200seed_measure_fp32_peak(int device, double* ops_per_s) {
+    if (!ops_per_s) return B200SEED_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, B200SEED_ECUDA, "cudaSetDevice");
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    float* d = nullptr;
+    if (cudaMalloc(&d, 256) != cudaSuccess) return fail(nullptr, B200SEED_ECUDA, "cudaMalloc");
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int iters = 20000, blocks = sms * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        k_fp32_probe<<<blocks, 256>>>(d, iters, 1.0000001f, 1e-7f);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double ops = double(blocks) * 256.0 * iters * 16.0;
+        if (ms > 0.f && ops / (ms * 1e-3) > best) best = ops / (ms * 1e-3);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(nullptr, B200SEED_ECUDA, cudaGetErrorString(e));
+    *ops_per_s = best;
     return B200SEED_OK;
 }
 

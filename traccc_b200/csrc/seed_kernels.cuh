@@ -852,4 +852,21 @@ k_estimate_params(const b200seed_tpe_cfg cfg, const uint32_t* __restrict__ n_see
     }
 }
 
+// ---------------------------------------------------------------------------
+// FP32 issue-rate probe for the roofline denominator: 8 independent chains of
+// non-fused FMUL + FADD per thread (this library is built with -fmad=false because the
+// cut arithmetic may not contract), 16 ops per inner iteration.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fp32_probe(float* out, const int iters, const float a,
+                                                    const float b) {
+    float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f,
+          x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+    for (int i = 0; i < iters; ++i) {
+        x0 = x0 * a + b, x1 = x1 * a + b, x2 = x2 * a + b, x3 = x3 * a + b;
+        x4 = x4 * a + b, x5 = x5 * a + b, x6 = x6 * a + b, x7 = x7 * a + b;
+    }
+    const float r = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (r == 12345.678f) out[0] = r;  // never true; keeps the chains alive
+}
+
 }  // namespace b200seed

@@ -354,8 +354,7 @@ class HostPipeline:
                "middle": self._out["middle"][:ns].numpy().view(np.uint32),
                "top": self._out["top"][:ns].numpy().view(np.uint32),
                "quality": self._out["quality"][:ns].numpy()}
-        if with_params:
-            res["params"] = np.frombuffer(
-                self._out["params"][: ns * BOUND_PARAMS_DTYPE.itemsize].numpy().tobytes(),
-                dtype=BOUND_PARAMS_DTYPE)
+        if with_params:   # zero-copy view of the pinned output buffer
+            res["params"] = self._out["params"][: ns * BOUND_PARAMS_DTYPE.itemsize].numpy().view(
+                BOUND_PARAMS_DTYPE)
         return res
