@@ -122,8 +122,49 @@ def lib() -> C.CDLL:
         L.oracle_transform_coordinates.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_triplet_is_compatible.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p,
                                                    C.POINTER(FinderCfg), C.c_void_p]
+        L.oracle_seed_select.restype = C.c_float
+        L.oracle_seed_select.argtypes = [C.POINTER(FilterCfg), C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+        for name in ("oracle_sp_radius", "oracle_sp_phi"):
+            getattr(L, name).restype = C.c_float
+            getattr(L, name).argtypes = [C.c_void_p]
         _lib = L
     return _lib
+
+
+REF_LIB_PATH = os.path.join(_HERE, "_ref", "libtraccc_ref.so")
+_ref = None
+
+
+def ref_lib():
+    """oracle/_ref/libtraccc_ref.so: the reference's own helper headers compiled verbatim
+    (oracle/ref_probe.cpp). None when it was never built (no /root/reference at build time)."""
+    global _ref
+    if _ref is None:
+        if not os.path.exists(REF_LIB_PATH):
+            if os.path.isdir("/root/reference/core/include/traccc"):
+                subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+            else:
+                return None
+        R = C.CDLL(REF_LIB_PATH)
+        R.ref_doublet_is_compatible.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.POINTER(FinderCfg)]
+        R.ref_transform_coordinates.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        R.ref_triplet_is_compatible.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(FinderCfg), C.c_void_p]
+        R.ref_seed_select.restype = C.c_float
+        R.ref_seed_select.argtypes = [C.POINTER(FilterCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+        for name in ("ref_sp_radius", "ref_sp_phi"):
+            getattr(R, name).restype = C.c_float
+            getattr(R, name).argtypes = [C.c_void_p]
+        for name in ("ref_axis_regular_bin", "ref_axis_circular_bin"):
+            getattr(R, name).restype = C.c_uint32
+            getattr(R, name).argtypes = [C.c_uint32, C.c_float, C.c_float, C.c_float]
+        R.ref_axis_circular_remap.restype = C.c_uint32
+        R.ref_axis_circular_remap.argtypes = [C.c_uint32, C.c_float, C.c_float, C.c_uint32, C.c_int]
+        for name in ("ref_axis_regular_range", "ref_axis_circular_range"):
+            getattr(R, name).argtypes = [C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_uint32, C.c_uint32, C.c_void_p]
+        R.ref_axis_zone.restype = C.c_uint32
+        R.ref_axis_zone.argtypes = [C.c_int, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]
+        _ref = R
+    return _ref
 
 
 def default_configs():

@@ -1023,6 +1023,25 @@ int oracle_triplet_is_compatible(const float m[5], const float lb[6], const floa
                : 0;
 }
 
+// seed_selecting_helper probe: returns the updated weight; flags = {single_seed_cut, cut_per_middle_sp}
+float oracle_seed_select(const b200seed_filter_cfg* c, const float b[5], const float t[5],
+                         float weight, int flags[2]) {
+    Oracle o;
+    o.flc = *c;
+    const Sp spB{b[0], b[1], b[2], b[3], b[4]}, spT{t[0], t[1], t[2], t[3], t[4]};
+    float w = weight;
+    o.seed_weight(spB, spT, w);
+    flags[0] = o.single_seed_cut(spB, w) ? 1 : 0;
+    flags[1] = o.cut_per_middle_sp(spB, w) ? 1 : 0;
+    return w;
+}
+float oracle_sp_radius(const float p[5]) {
+    return Sp{p[0], p[1], p[2], p[3], p[4]}.radius();
+}
+float oracle_sp_phi(const float p[5]) {
+    return Sp{p[0], p[1], p[2], p[3], p[4]}.phi();
+}
+
 // host::seeding_algorithm::operator() — core/src/seeding/seeding_algorithm.cpp:24-28.
 // dump != 0 additionally records grid, doublets and triplets.
 // oracle_run_bins restricts the middle-spacepoint loop (seed_finding.cpp:69) to the bins
