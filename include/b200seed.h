@@ -246,7 +246,9 @@ int b200seed_run_host(b200seed_handle* h, void* stream, uint32_t n_sp, const flo
  *                                      (bump-allocated: list order is canonical, the placement
  *                                      of the lists relative to each other is not)
  *   doublets    : 32-byte records [2][max_doublets]: {cotTheta, iDeltaR, Er, U, V, Zo,
- *                 radius of the other spacepoint, sorted position of the other spacepoint}
+ *                 radius of the other spacepoint, sorted position of the other spacepoint};
+ *                 mid-bottom lists are in the reference's order; mid-top lists are sorted by
+ *                 cotTheta and carry their canonical index (u32 bits) in the Zo slot
  *   triplet_dump: 32-byte records {sorted pos bottom, middle, top (u32), index of the
  *                 mid-bottom doublet, index of the mid-top doublet (u32), curvature, weight
  *                 after the compatible-seed bonus, z_vertex (f32)} in no particular order;

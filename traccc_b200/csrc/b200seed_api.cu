@@ -261,9 +261,6 @@ uint32_t triplet_list_cap(uint32_t n_sp) {
     if (n_sp <= 300000) return 384;
     return 768;
 }
-size_t triplet_smem_per_warp(uint32_t cap) {
-    return 64 * 4 + size_t(cap) * 4 + size_t(cap) * 16 + MAX_TOPK * 5 * 4;
-}
 
 }  // namespace
 
@@ -609,7 +606,7 @@ int b200seed_run(b200seed_handle* h, void* stream, uint32_t n_sp, const float* d
         a.ctrl = ctrl;
         a.max_doublets = uint32_t(L.max_doublets);
         a.stage_cap = doublet_stage_cap(n_sp);
-        const size_t smem = size_t(WARPS_PER_CTA) * (64 + 2 * a.stage_cap) * 4;
+        const size_t smem = size_t(WARPS_PER_CTA) * (64 + 3 * a.stage_cap) * 4;
         uint32_t grid = (n_sp + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
         const uint32_t max_grid = uint32_t(h->num_sms) * 8;
         if (grid > max_grid) grid = max_grid;

@@ -255,7 +255,25 @@ struct NeighbourWalk {
     }
 };
 
-// Shared memory per warp of k_doublets: 64-entry compaction ring + 2 staging lists.
+// Rank of element k in the ascending (value, index) order of v[0..n) — O(n) per element,
+// used for the short per-middle mid-top lists.
+template <typename LoadF>
+__device__ __forceinline__ uint32_t rank_by_value(LoadF load, uint32_t n, uint32_t k, float vk) {
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < n; ++j) {
+        const float vj = load(j);
+        rank += ((vj < vk) || (vj == vk && j < k)) ? 1u : 0u;
+    }
+    return rank;
+}
+
+// Shared memory per warp of k_doublets: 64-entry compaction ring + 2 staging lists + the
+// cotTheta keys of the staged mid-top doublets.
+// Arena records: mid-bottom lists keep the reference's order (phi bins outer, z bins inner,
+// position in bin); mid-top lists are sorted by cotTheta so that k_triplets can binary-search
+// the scattering window of each mid-bottom doublet, and carry their canonical index.
+//   bottom: a = {cotTheta, iDeltaR, Er, U}  b = {V, Zo,               r_other, pos_other}
+//   top   : a = {cotTheta, iDeltaR, Er, U}  b = {V, bits(canonical k), r_other, pos_other}
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 k_doublets(const DevCfg cfg, const DoubletArgs a) {
     extern __shared__ uint32_t s_mem[];
@@ -263,9 +281,10 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
     __shared__ uint32_t s_acc[3];  // active, nb, nt
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t ltmask = lanemask_lt();
-    uint32_t* ring = s_mem + size_t(warp) * (64 + 2 * a.stage_cap);
+    uint32_t* ring = s_mem + size_t(warp) * (64 + 3 * a.stage_cap);
     uint32_t* stage_b = ring + 64;
     uint32_t* stage_t = stage_b + a.stage_cap;
+    float* cot_s = reinterpret_cast<float*>(stage_t + a.stage_cap);
     if (threadIdx.x == 0) {
         s_pairs = 0ull;
         s_acc[0] = s_acc[1] = s_acc[2] = 0u;
@@ -340,8 +359,10 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
                                 !top, M.x, M.y, M.z, M.w, VM.x, VM.y, P.x, P.y, P.z, V.x, V.y);
                             DoubletRec r;
                             r.a = make_float4(l.cotTheta, l.iDeltaR, l.Er, l.U);
-                            r.b = make_float4(l.V, l.Zo, P.w, __uint_as_float(c));
-                            (top ? a.arena_t + offT : a.arena_b + offB)[k] = r;
+                            r.b = make_float4(l.V, top ? __uint_as_float(k) : l.Zo, P.w,
+                                              __uint_as_float(c));
+                            // unsorted tops go to the second half of a 2*nT allocation
+                            (top ? a.arena_t + offT + nT : a.arena_b + offB)[k] = r;
                         }
                     }
                     wB += __popc(mB);
@@ -351,7 +372,19 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
                     __syncwarp();
                 }
             }
-            if (direct) break;
+            if (direct) {
+                // sort the mid-top records by cotTheta: second half -> first half
+                const DoubletRec* src = a.arena_t + offT + nT;
+                DoubletRec* dst = a.arena_t + offT;
+                __syncwarp();
+                for (uint32_t k = lane; k < nT; k += 32) {
+                    const DoubletRec r = src[k];
+                    const uint32_t rank = rank_by_value(
+                        [&](uint32_t j) { return src[j].a.x; }, nT, k, r.a.x);
+                    dst[rank] = r;
+                }
+                break;
+            }
             nB = wB;
             nT = wT;
             // A middle continues only with >= 1 bottom and >= 1 top (seed_finding.cpp:85-95)
@@ -359,35 +392,54 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
                 nB = nT = 0;
                 break;
             }
+            const bool spill = (nB > a.stage_cap || nT > a.stage_cap);
+            const uint32_t allocT = spill ? 2u * nT : nT;  // room to sort in place
             if (lane == 0) {
                 offB = atomicAdd(&a.ctrl->cursor[0], nB);
-                offT = atomicAdd(&a.ctrl->cursor[1], nT);
+                offT = atomicAdd(&a.ctrl->cursor[1], allocT);
             }
             offB = __shfl_sync(0xffffffffu, offB, 0);
             offT = __shfl_sync(0xffffffffu, offT, 0);
             if (offB > a.max_doublets || nB > a.max_doublets - offB || offT > a.max_doublets ||
-                nT > a.max_doublets - offT) {
+                allocT > a.max_doublets - offT) {
                 if (lane == 0) atomicOr(&a.ctrl->overflow, B200SEED_OVF_DOUBLETS);
                 nB = nT = 0;
                 break;
             }
-            if (nB > a.stage_cap || nT > a.stage_cap) continue;  // rare: redo in direct mode
+            if (spill) continue;  // rare: redo the scan in direct mode
             // common path: lin_circle of every staged survivor, full lanes
-            for (int dir = 0; dir < 2; ++dir) {
-                const uint32_t n = dir ? nT : nB;
-                const uint32_t* stage = dir ? stage_t : stage_b;
-                DoubletRec* out = dir ? a.arena_t + offT : a.arena_b + offB;
-                for (uint32_t k = lane; k < n; k += 32) {
-                    const uint32_t c = stage[k];
-                    const float4 P = __ldg(a.sp4 + c);
-                    const float2 V = __ldg(a.var2 + c);
-                    const LinCircle l = transform_coordinates(dir == 0, M.x, M.y, M.z, M.w, VM.x,
-                                                              VM.y, P.x, P.y, P.z, V.x, V.y);
-                    DoubletRec r;
-                    r.a = make_float4(l.cotTheta, l.iDeltaR, l.Er, l.U);
-                    r.b = make_float4(l.V, l.Zo, P.w, __uint_as_float(c));
-                    out[k] = r;
-                }
+            for (uint32_t k = lane; k < nB; k += 32) {
+                const uint32_t c = stage_b[k];
+                const float4 P = __ldg(a.sp4 + c);
+                const float2 V = __ldg(a.var2 + c);
+                const LinCircle l = transform_coordinates(true, M.x, M.y, M.z, M.w, VM.x, VM.y, P.x,
+                                                          P.y, P.z, V.x, V.y);
+                DoubletRec r;
+                r.a = make_float4(l.cotTheta, l.iDeltaR, l.Er, l.U);
+                r.b = make_float4(l.V, l.Zo, P.w, __uint_as_float(c));
+                a.arena_b[offB + k] = r;
+            }
+            // mid-tops: cotTheta keys first, then each record goes to its sorted position
+            for (uint32_t k = lane; k < nT; k += 32) {
+                const uint32_t c = stage_t[k];
+                const float4 P = __ldg(a.sp4 + c);
+                const float2 V = __ldg(a.var2 + c);
+                cot_s[k] = transform_coordinates(false, M.x, M.y, M.z, M.w, VM.x, VM.y, P.x, P.y,
+                                                 P.z, V.x, V.y).cotTheta;
+            }
+            __syncwarp();
+            for (uint32_t k = lane; k < nT; k += 32) {
+                const uint32_t c = stage_t[k];
+                const float4 P = __ldg(a.sp4 + c);
+                const float2 V = __ldg(a.var2 + c);
+                const LinCircle l = transform_coordinates(false, M.x, M.y, M.z, M.w, VM.x, VM.y, P.x,
+                                                          P.y, P.z, V.x, V.y);
+                const uint32_t rank =
+                    rank_by_value([&](uint32_t j) { return cot_s[j]; }, nT, k, cot_s[k]);
+                DoubletRec r;
+                r.a = make_float4(cot_s[k], l.iDeltaR, l.Er, l.U);
+                r.b = make_float4(l.V, __uint_as_float(k), P.w, __uint_as_float(c));
+                a.arena_t[offT + rank] = r;
             }
             break;
         }
@@ -445,12 +497,62 @@ struct TripletArgs {
 
 // One triplet of the current row block (shared memory, 16 bytes).
 struct __align__(16) BlockTriplet {
-    uint32_t key;     // (row in block) << 27 | mid-top index
-    float curvature;
+    uint32_t key;     // (row in block) << 27 | canonical mid-top index
+    float curvature;  // later: radius of the bottom spacepoint
     float weight;     // -impact * impactWeightFactor, later the final weight
     float rT;         // radius of the top spacepoint, later the sorter sum
 };
 
+// first t in [0, n) with cot(t) >= v  (mid-top records are sorted by cotTheta)
+__device__ __forceinline__ uint32_t cot_lower_bound(const DoubletRec* __restrict__ LT, uint32_t n,
+                                                    float v) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(&LT[mid].a.x) < v)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+// first t in [0, n) with cot(t) > v
+__device__ __forceinline__ uint32_t cot_upper_bound(const DoubletRec* __restrict__ LT, uint32_t n,
+                                                    float v) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(&LT[mid].a.x) <= v)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Per-warp shared memory of k_triplets.
+__host__ __device__ inline size_t triplet_smem_per_warp(uint32_t list_cap) {
+    return size_t(list_cap) * (16 + 4 + 4) + MAX_TOPK * 5 * 4;
+}
+
+// Warp per middle spacepoint (atomic ticket queue). For every block of 32 mid-bottom doublets
+// (one per lane) the lane binary-searches, in the cotTheta-sorted mid-top list, the window
+// outside of which the first scattering cut of triplet_finding_helper::isCompatible (:57-78)
+// must fail; the (row, top) pairs inside the windows are flattened with a warp scan and
+// evaluated 32 at a time at full lane occupancy with the exact reference arithmetic.
+// The window is conservative (see the margin below), so the accepted set is identical to
+// testing all nMidBot x nMidTop combinations.
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 k_triplets(const DevCfg cfg, const TripletArgs a) {
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -458,13 +560,10 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
     __shared__ unsigned long long s_tests;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t ltmask = lanemask_lt();
-    // per-warp shared memory: ring[64] | bonus[list_cap] | list[list_cap] | top-K arrays
-    const size_t per_warp = 64 * 4 + size_t(a.list_cap) * 4 + size_t(a.list_cap) * 16 +
-                            MAX_TOPK * 5 * 4;
-    unsigned char* base = s_raw + per_warp * warp;
+    unsigned char* base = s_raw + triplet_smem_per_warp(a.list_cap) * warp;
     BlockTriplet* list = reinterpret_cast<BlockTriplet*>(base);
-    uint32_t* ring = reinterpret_cast<uint32_t*>(base + size_t(a.list_cap) * 16);
-    uint32_t* bonus = ring + 64;  // compatible seeds found per triplet
+    uint32_t* lpos = reinterpret_cast<uint32_t*>(base + size_t(a.list_cap) * 16);  // pos of top
+    uint32_t* bonus = lpos + a.list_cap;  // compatible seeds found per triplet
     float* top_w = reinterpret_cast<float*>(bonus + a.list_cap);
     float* top_s = top_w + MAX_TOPK;
     float* top_rb = top_s + MAX_TOPK;
@@ -496,81 +595,111 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
         const float4 M = __ldg(a.sp4 + m);
         const float2 VM = __ldg(a.var2 + m);  // {varZ, varR}
         const float rM = M.w, varZM = VM.x, varRM = VM.y;
-        uint32_t ntop = 0;  // entries in the per-middle top-K (warp-uniform)
 
+        // bounds over the mid-tops for the conservative window
+        float maxEr = 0.f, minEr = 0.f, maxIDR = 0.f, maxAbsCot = 0.f;
+        for (uint32_t t = lane; t < nt; t += 32) {
+            const float4 ta = __ldg(&LT[t].a);
+            maxEr = fmaxf(maxEr, ta.z);
+            minEr = fminf(minEr, ta.z);
+            maxIDR = fmaxf(maxIDR, ta.y);
+            maxAbsCot = fmaxf(maxAbsCot, absf(ta.x));
+        }
+        maxEr = warp_max(maxEr);
+        minEr = warp_min(minEr);
+        maxIDR = warp_max(maxIDR);
+        maxAbsCot = warp_max(maxAbsCot);
+        // with negative or non-finite error terms the reference's sqrt() yields NaN and the
+        // cut passes everything: no pruning then
+        const bool sane = (varRM >= 0.f) && (varZM >= 0.f) && (minEr >= 0.f) && (maxEr < 1e30f) &&
+                          (maxIDR < 1e30f) && (maxAbsCot < 1e30f);
+
+        uint32_t ntop = 0;  // entries in the per-middle top-K (warp-uniform)
         uint32_t row0 = 0;
         uint32_t rows = 32;  // rows of the current block (shrinks only on list overflow)
         while (row0 < nb) {
             const uint32_t nrows = (nb - row0 < rows) ? (nb - row0) : rows;
-            // lane-owned mid-bottom doublet
             const bool has_row = lane < nrows;
             float4 la = make_float4(0.f, 0.f, 0.f, 0.f);
             if (has_row) la = __ldg(&LB[row0 + lane].a);
             float iSinTheta2, sir2;
             triplet_row_constants(cfg, la.x, iSinTheta2, sir2);
-            uint32_t qhead = 0, qn = 0, nlist = 0;
-            bool overflow = false;
-            for (uint32_t t = 0; t <= nt; ++t) {
-                const bool flush = (t == nt);
-                if (!flush) {
-                    const float4 ta = __ldg(&LT[t].a);  // same address for all lanes
-                    const bool p1 = has_row && triplet_cut1(la.x, la.y, la.z, ta.x, ta.y, ta.z,
-                                                            varRM, varZM, sir2);
-                    const uint32_t mask = __ballot_sync(0xffffffffu, p1);
-                    if (mask == 0u) continue;
-                    if (p1) ring[(qhead + qn + __popc(mask & ltmask)) & 63u] = (lane << 27) | t;
-                    qn += __popc(mask);
-                    __syncwarp();
-                    if (qn < 32) continue;
-                }
-                // drain: full cut on up to 32 cut-1 survivors (all of them when flushing)
-                while (qn > 0) {
-                    const uint32_t take = qn < 32 ? qn : 32;
-                    bool ok = false;
-                    uint32_t key = 0;
-                    float curvature = 0.f, impact = 0.f, rT = 0.f;
-                    if (lane < take) {
-                        key = ring[(qhead + lane) & 63u];
-                        const uint32_t row = key >> 27, tt = key & 0x07ffffffu;
-                        const float4 ba = __ldg(&LB[row0 + row].a);
-                        const float4 bb = __ldg(&LB[row0 + row].b);
-                        const float4 ta = __ldg(&LT[tt].a);
-                        const float4 tb = __ldg(&LT[tt].b);
-                        LinCircle lb, lt;
-                        lb.cotTheta = ba.x, lb.iDeltaR = ba.y, lb.Er = ba.z, lb.U = ba.w;
-                        lb.V = bb.x, lb.Zo = bb.y;
-                        lt.cotTheta = ta.x, lt.iDeltaR = ta.y, lt.Er = ta.z, lt.U = ta.w;
-                        lt.V = tb.x, lt.Zo = tb.y;
-                        float is2, s2;
-                        triplet_row_constants(cfg, lb.cotTheta, is2, s2);
-                        ok = triplet_is_compatible(cfg, rM, varRM, varZM, lb, lt, is2, s2,
-                                                   curvature, impact);
-                        rT = tb.z;
-                    }
-                    const uint32_t mk = __ballot_sync(0xffffffffu, ok);
-                    const uint32_t k = nlist + __popc(mk & ltmask);
-                    if (ok) {
-                        if (k < a.list_cap) {
-                            BlockTriplet e;
-                            e.key = key;
-                            e.curvature = curvature;
-                            e.weight = -impact * cfg.impactWeightFactor;
-                            e.rT = rT;
-                            list[k] = e;
-                        }
-                    }
-                    nlist += __popc(mk);
-                    qhead = (qhead + take) & 63u;
-                    qn -= take;
-                    __syncwarp();
-                    if (!flush) break;
-                }
-                if (nlist > a.list_cap) {
-                    overflow = true;
-                    break;
-                }
+            // Window half-width. The cut rejects iff d2 - e2 > 0 and (|d| - e)^2 > sir2
+            // (d = cot_b - cot_t, e^2 = error2 <= e2max), i.e. surely when
+            // |d| > e + sqrt(sir2); the factors absorb float rounding including the
+            // cancellation in d2 + e2 - 2|d|e (relative error <= 1e-6 (d^2 + e^2)).
+            uint32_t lo = 0, hi = 0;
+            if (has_row) {
+                const float e2max = la.z + maxEr +
+                                    2.f * (absf(la.x) * maxAbsCot * varRM + varZM) * la.y * maxIDR;
+                const float W = 1.004f * sqrt_rn(e2max) + 1.002f * sqrt_rn(sir2) +
+                                4e-6f * (absf(la.x) + maxAbsCot) + 1e-30f;
+                const bool prune = sane && (la.z >= 0.f) && (W < 1e30f) && (sir2 >= 0.f);
+                lo = prune ? cot_lower_bound(LT, nt, la.x - W) : 0u;
+                hi = prune ? cot_upper_bound(LT, nt, la.x + W) : nt;
+                if (hi < lo) hi = lo;
             }
-            if (overflow) {
+            const uint32_t wdt = hi - lo;
+            uint32_t incl = wdt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= uint32_t(o)) incl += v;
+            }
+            const uint32_t excl = incl - wdt;
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+
+            uint32_t nlist = 0;
+            for (uint32_t p0 = 0; p0 < total; p0 += 32) {
+                const uint32_t p = p0 + lane;
+                const bool valid = p < total;
+                // row of pair p: number of rows whose inclusive prefix is <= p
+                uint32_t r = 0;
+#pragma unroll
+                for (uint32_t step = 16; step >= 1; step >>= 1) {
+                    const uint32_t v = __shfl_sync(0xffffffffu, incl, (r + step - 1) & 31u);
+                    if (v <= p) r += step;
+                }
+                r &= 31u;
+                const uint32_t er = __shfl_sync(0xffffffffu, excl, r);
+                const uint32_t lor = __shfl_sync(0xffffffffu, lo, r);
+                bool ok = false;
+                uint32_t key = 0, pos_t = 0;
+                float curvature = 0.f, impact = 0.f, rT = 0.f;
+                if (valid) {
+                    const uint32_t tt = lor + (p - er);
+                    const float4 ba = __ldg(&LB[row0 + r].a);
+                    const float4 bb = __ldg(&LB[row0 + r].b);
+                    const float4 ta = __ldg(&LT[tt].a);
+                    const float4 tb = __ldg(&LT[tt].b);
+                    LinCircle lb, lt;
+                    lb.cotTheta = ba.x, lb.iDeltaR = ba.y, lb.Er = ba.z, lb.U = ba.w;
+                    lb.V = bb.x, lb.Zo = bb.y;
+                    lt.cotTheta = ta.x, lt.iDeltaR = ta.y, lt.Er = ta.z, lt.U = ta.w;
+                    lt.V = tb.x, lt.Zo = 0.f;
+                    float is2, s2;
+                    triplet_row_constants(cfg, lb.cotTheta, is2, s2);
+                    ok = triplet_is_compatible(cfg, rM, varRM, varZM, lb, lt, is2, s2, curvature,
+                                               impact);
+                    key = (r << 27) | __float_as_uint(tb.y);
+                    rT = tb.z;
+                    pos_t = __float_as_uint(tb.w);
+                }
+                const uint32_t mk = __ballot_sync(0xffffffffu, ok);
+                const uint32_t k = nlist + __popc(mk & ltmask);
+                if (ok && k < a.list_cap) {
+                    BlockTriplet e;
+                    e.key = key;
+                    e.curvature = curvature;
+                    e.weight = -impact * cfg.impactWeightFactor;
+                    e.rT = rT;
+                    list[k] = e;
+                    lpos[k] = pos_t;
+                }
+                nlist += __popc(mk);
+            }
+            __syncwarp();
+            if (nlist > a.list_cap) {
                 if (rows > 1) {
                     rows >>= 1;  // redo this block with fewer rows
                     continue;
@@ -582,20 +711,35 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
             }
             acc_trip += nlist;
 
-            // ---- compatible-seed bonus (triplet_finding.hpp:107-179), lane per triplet ----
+            // ---- compatible-seed bonus (triplet_finding.hpp:107-179), lane per triplet. The
+            //      list is row-major; inside a row the partners are visited in ascending
+            //      canonical mid-top index, which is the reference's iteration order. ----
             for (uint32_t i0 = 0; i0 < nlist; i0 += 32) {
                 const uint32_t i = i0 + lane;
                 if (i < nlist) {
                     const BlockTriplet cur = list[i];
                     const uint32_t row = cur.key >> 27;
+                    uint32_t sgm = i, egm = i + 1;
+                    while (sgm > 0 && (list[sgm - 1].key >> 27) == row) --sgm;
+                    while (egm < nlist && (list[egm].key >> 27) == row) ++egm;
                     const float lower = cur.curvature - cfg.deltaInvHelixDiameter;
                     const float upper = cur.curvature + cfg.deltaInvHelixDiameter;
                     float compat[MAX_COMPAT];
                     uint32_t ncompat = 0;
-                    for (uint32_t j = 0; j < nlist; ++j) {
-                        if (j == i) continue;
-                        const BlockTriplet o = list[j];
-                        if ((o.key >> 27) != row) continue;
+                    uint32_t next_min = row << 27;
+                    while (true) {
+                        uint32_t best = 0xFFFFFFFFu, bj = 0;
+                        for (uint32_t j = sgm; j < egm; ++j) {
+                            const uint32_t kj = list[j].key;
+                            if (kj >= next_min && kj < best) {
+                                best = kj;
+                                bj = j;
+                            }
+                        }
+                        if (best == 0xFFFFFFFFu) break;
+                        next_min = best + 1u;
+                        if (bj == i) continue;
+                        const BlockTriplet o = list[bj];
                         const float deltaR = cur.rT - o.rT;
                         if (absf(deltaR) < cfg.filterDeltaRMin) continue;
                         if (o.curvature < lower) continue;
@@ -628,8 +772,7 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
                     float w = cur.weight;
                     for (uint32_t q = bonus[i]; q > 0; --q) w += cfg.compatSeedWeight;
                     const float4 bb = __ldg(&LB[row0 + row].b);
-                    const float4 tb = __ldg(&LT[tt].b);
-                    const uint32_t pos_b = __float_as_uint(bb.w), pos_t = __float_as_uint(tb.w);
+                    const uint32_t pos_b = __float_as_uint(bb.w), pos_t = lpos[i];
                     if (a.dump) {
                         const uint32_t d = atomicAdd(&a.ctrl->dump_cursor, 1u);
                         if (d < a.max_dump) {
@@ -642,7 +785,7 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
                             atomicOr(&a.ctrl->overflow, B200SEED_OVF_DUMP);
                         }
                     }
-                    const float rB = bb.z, rT = tb.z;
+                    const float rB = bb.z, rT = cur.rT;
                     w += seed_weight_increase(cfg, rB, rT);
                     const bool keep = single_seed_cut(cfg, rB, w);
                     const float4 PB = __ldg(a.sp4 + pos_b);
@@ -650,7 +793,7 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
                     cur.weight = w;
                     cur.rT = sorter_sum(PB.y, PB.z, PT.y, PT.z);
                     cur.curvature = rB;
-                    cur.key = keep ? cur.key : 0xFFFFFFFFu;
+                    cur.key = keep ? pos_b : 0xFFFFFFFFu;  // pos_b < 2^32 - 1 always
                     list[i] = cur;
                 }
             }
@@ -672,12 +815,11 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
                         top_b[q] = top_b[q - 1];
                         top_t[q] = top_t[q - 1];
                     }
-                    const uint32_t row = c.key >> 27, tt = c.key & 0x07ffffffu;
                     top_w[p] = c.weight;
                     top_s[p] = c.rT;
                     top_rb[p] = c.curvature;
-                    top_b[p] = __float_as_uint(__ldg(&LB[row0 + row].b).w);
-                    top_t[p] = __float_as_uint(__ldg(&LT[tt].b).w);
+                    top_b[p] = c.key;
+                    top_t[p] = lpos[i];
                     if (ntop < K) ++ntop;
                 }
             }

@@ -238,8 +238,20 @@ class triplet_seeding_algorithm:
             a = np.frombuffer(ws, dtype=rec, count=used, offset=L.doublets + d * _align(md * 32))
             # gather the per-middle lists in sorted-position (canonical) order
             idx = np.concatenate([np.arange(o, o + c) for o, c in zip(off, cnt) if c]) if used else np.zeros(0, np.int64)
-            res[f"doublets_{name}"] = a[idx].copy()
-            res[f"doublets_{name}_mid"] = np.repeat(np.arange(nv), cnt)
+            lst = a[idx].copy()
+            mid = np.repeat(np.arange(nv), cnt)
+            if d == 1 and len(lst):
+                # mid-top lists are stored sorted by cotTheta; the "Zo" slot carries the
+                # canonical index -> restore the reference's order inside each middle
+                canon = lst["Zo"].view(np.uint32).astype(np.int64)
+                order = np.lexsort((canon, mid))
+                assert np.array_equal(mid[order], mid)
+                cot = lst["cotTheta"]
+                same = mid[1:] == mid[:-1]
+                assert (cot[1:][same] >= cot[:-1][same]).all(), "mid-top lists must be cot-sorted"
+                lst = lst[order]
+            res[f"doublets_{name}"] = lst
+            res[f"doublets_{name}_mid"] = mid
         if L.max_triplet_dump:
             ndump = int(arr(L.triplet_dump_count, np.uint32, 1)[0])
             trec = np.dtype([("pos_b", "<u4"), ("pos_m", "<u4"), ("pos_t", "<u4"), ("mb_idx", "<u4"),
