@@ -232,7 +232,7 @@ def run_b200(args):
         return seeding.seed_collection(
             torch.empty(cap, dtype=torch.int32, device=dev), torch.empty(cap, dtype=torch.int32, device=dev),
             torch.empty(cap, dtype=torch.int32, device=dev), torch.empty(cap, dtype=torch.float32, device=dev),
-            torch.zeros(1, dtype=torch.int32, device=dev), torch.zeros(48, dtype=torch.uint8, device=dev))
+            torch.zeros(1, dtype=torch.int32, device=dev), torch.zeros(C.sizeof(_lib.Counters), dtype=torch.uint8, device=dev))
 
     d_out = [new_out(e.n_spacepoints) for e in events]
     d_par = [torch.empty(o.capacity * 176, dtype=torch.uint8, device=dev) for o in d_out]

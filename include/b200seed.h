@@ -139,8 +139,11 @@ typedef struct b200seed_counters {
     uint32_t n_triplets;         /* triplets passing triplet_finding_helper::isCompatible */
     uint32_t n_seeds;            /* seeds written (== *d_n_seeds) */
     uint32_t overflow;           /* bit mask of B200SEED_OVF_* ; 0 == results complete */
-    uint64_t pair_tests;         /* sum over valid middles of candidate spacepoints scanned */
+    uint64_t pair_tests;         /* sum over valid middles of the spacepoints in their neighbour
+                                    bins == candidate pairs the reference tests */
     uint64_t triplet_tests;      /* sum over active middles of nMidBot * nMidTop */
+    uint64_t pair_visited;       /* candidate pairs this library actually evaluated (after the
+                                    conservative (r, z) cell pruning) */
 } b200seed_counters;
 
 #define B200SEED_OVF_DOUBLETS 1u /* doublet arena too small: raise max_doublets */

@@ -5,6 +5,8 @@ Bars (BASELINE.json north_star): binning and doublet/triplet index sets bit-exac
 disagreement is a full tie of the reference's unstable std::sort); track parameters within
 1e-5 relative (the reference comparator's formula).
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -231,7 +233,7 @@ def test_overflow_flags():
     small = seeding.seed_collection(*[torch.empty(10, dtype=torch.int32, device="cuda") for _ in range(3)],
                                     torch.empty(10, dtype=torch.float32, device="cuda"),
                                     torch.zeros(1, dtype=torch.int32, device="cuda"),
-                                    torch.zeros(48, dtype=torch.uint8, device="cuda"))
+                                    torch.zeros(C.sizeof(Counters), dtype=torch.uint8, device="cuda"))
     out = sa2(sps, out=small)
     torch.cuda.synchronize()
     c = out.host_counters()

@@ -108,3 +108,48 @@ def test_bins_doublets_triplets_bit_exact(n_particles, seed, kw):
     for i in acc:
         k = (int(rm[i]), int(ref.mb["other"][rb[i]]), int(ref.mt["other"][rt[i]]))
         assert ref_curv[k] == int(out[i, 0].view(np.uint32)), k
+
+
+@pytest.mark.parametrize("n_particles,seed,kw,cfg", [
+    (300, 1, {}, "default"), (2000, 2, dict(shuffle=True), "default"),
+    (1500, 3, dict(eta_max=1.0), "default"), (1500, 4, {}, "many_z_bins"),
+    (800, 5, {}, "loose"), (40000, 6, {}, "default")])
+def test_cell_window_is_conservative(n_particles, seed, kw, cfg):
+    """The (r, z) cell pruning of k_doublets never drops a pair that passes the first block of
+    doublet cuts (csrc/seed_math.cuh, cell_row_window), and it prunes most of the others."""
+    L = _lib.lib()
+    finder = seedfinder_config()
+    if cfg == "many_z_bins":
+        finder.cotThetaMax = 7.0
+    elif cfg == "loose":
+        finder.deltaRMin = 0.5
+        finder.deltaRMax = 150.0
+        finder.collisionRegionMin = -600.0
+        finder.collisionRegionMax = 400.0
+        finder.beamPos[0] = 3.0
+    grid = spacepoint_grid_config(finder)
+    filt = seedfilter_config()
+    dc = _devcfg(finder, grid, filt)
+    ev = toy_detector.generate_event(n_particles, seed, **kw)
+    n = ev.n_spacepoints
+    bins = np.zeros(n, np.uint32)
+    L.b200seed_host_probe_bins(dc, n, _p(ev.xyz), _p(bins))
+    valid = np.flatnonzero(bins != 0xFFFFFFFF)
+    sp5 = np.concatenate([ev.xyz, ev.var_z[:, None], ev.var_r[:, None]], axis=1).astype(np.float32)
+    rng = np.random.default_rng(seed)
+    mids = rng.choice(valid, size=min(300, len(valid)), replace=False)
+    cand = valid if len(valid) <= 6000 else rng.choice(valid, size=6000, replace=False)
+    mm = np.repeat(mids, len(cand))
+    oo = np.tile(cand, len(mids))
+    kind = np.zeros(len(mm), np.int32)
+    lc = np.zeros((len(mm), 6), np.float32)
+    m5, o5 = np.ascontiguousarray(sp5[mm]), np.ascontiguousarray(sp5[oo])
+    L.b200seed_host_probe_doublets(dc, len(mm), _p(m5), _p(o5), _p(kind), _p(lc))
+    vis = np.zeros(len(mm), np.int32)
+    gr = np.zeros(2, np.uint32)
+    L.b200seed_host_probe_cell_window(dc, C.byref(finder), n, len(mm), _p(m5), _p(o5),
+                                      _p(np.ascontiguousarray(bins[oo])), _p(vis), _p(gr))
+    assert kind.any()
+    assert vis[kind != 0].all(), "a compatible pair lies outside the visited cells"
+    if cfg == "default" and n_particles >= 2000:
+        assert vis.mean() < 0.5, (vis.mean(), gr)

@@ -83,7 +83,8 @@ class Counters(C.Structure):
     _fields_ = [("n_spacepoints", C.c_uint32), ("n_valid", C.c_uint32),
                 ("n_active_middles", C.c_uint32), ("n_mid_bot", C.c_uint32),
                 ("n_mid_top", C.c_uint32), ("n_triplets", C.c_uint32), ("n_seeds", C.c_uint32),
-                ("overflow", C.c_uint32), ("pair_tests", C.c_uint64), ("triplet_tests", C.c_uint64)]
+                ("overflow", C.c_uint32), ("pair_tests", C.c_uint64), ("triplet_tests", C.c_uint64),
+                ("pair_visited", C.c_uint64)]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -160,6 +161,9 @@ def lib() -> C.CDLL:
     L.b200seed_host_probe_bins.restype = None
     L.b200seed_host_probe_doublets.argtypes = [vp, u32, vp, vp, vp, vp]
     L.b200seed_host_probe_doublets.restype = None
+    L.b200seed_host_probe_cell_window.argtypes = [vp, C.POINTER(seedfinder_config), u32, u32, vp, vp,
+                                                  vp, vp, vp]
+    L.b200seed_host_probe_cell_window.restype = None
     L.b200seed_host_probe_triplets.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp]
     L.b200seed_host_probe_triplets.restype = None
     _lib = L

@@ -36,10 +36,13 @@ inline size_t align_up(size_t v, size_t a) {
 }
 
 struct Layout {
-    size_t control, bin_of, blk_hist, bin_off, sorted_index, sorted_bin, sp4, var2, cnt, off,
-        seed_cnt, seed_off, seed_b, seed_t, seed_w, arena_b, arena_t, dump, total;
+    size_t control, cell_cnt, bin_of, blk_hist, bin_off, cell_off, sorted_index, sorted_bin, sp4,
+        var2, csp4, ccanon, cnt, off, seed_cnt, seed_off, seed_b, seed_t, seed_w, arena_b, arena_t,
+        dump, total;
+    size_t zero_bytes;  // control block + cell populations: cleared at the start of an event
     uint32_t nblk;
     uint64_t max_doublets, max_dump;
+    CellGrid g;
 };
 
 struct TimingSlot {
@@ -96,9 +99,41 @@ uint64_t default_max_doublets(uint32_t max_sp) {
     return v;
 }
 
+// Fine (r, z) cells per reference bin (seed_math.cuh, CellGrid): about two cells per
+// spacepoint of an average bin, at most 32 x 128, and at most 2^21 cells in total.
+CellGrid make_cell_grid(const DevCfg& dev, const b200seed_finder_cfg& finder, uint32_t n_sp) {
+    const uint64_t nb64 = uint64_t(dev.nPhi) * dev.nZ;
+    const uint32_t nbins = nb64 ? uint32_t(nb64) : 1u;
+    const double per_bin = double(n_sp) / double(nbins);
+    uint32_t cpb = 1;
+    while (cpb < 4096u && double(cpb) < 2.0 * per_bin) cpb <<= 1;
+    if (cpb < 64u) cpb = 64u;
+    while (cpb > 1u && uint64_t(cpb) * nbins > (1ull << 21)) cpb >>= 1;
+    uint32_t nr = cpb >= 2048u ? 32u : (cpb >= 512u ? 16u : (cpb >= 64u ? 8u : 1u));
+    if (nr > cpb) nr = cpb;
+    CellGrid g{};
+    g.NR = nr;
+    g.NZc = cpb / nr;
+    g.CPB = cpb;
+    g.NZg = dev.nZ * g.NZc;
+    const float beam = std::sqrt(finder.beamPos[0] * finder.beamPos[0] +
+                                 finder.beamPos[1] * finder.beamPos[1]);
+    float rspan = finder.rMax + 2.f * beam + 1.f;
+    if (!(rspan > 1.f) || !(rspan < 1e30f)) rspan = 1.f;
+    g.rw = rspan / float(nr);
+    g.invRw = 1.f / g.rw;
+    g.zMin = dev.zAxisMin;
+    float zspan = dev.zAxisMax - dev.zAxisMin;
+    if (!(zspan > 0.f) || !(zspan < 1e30f)) zspan = 1.f;
+    g.invZw = float(g.NZg) / zspan;
+    return g;
+}
+
 Layout make_layout(const b200seed_handle* h, uint32_t max_sp) {
     Layout L{};
     const size_t n = max_sp ? max_sp : 1;
+    L.g = make_cell_grid(h->dev, h->finder, max_sp);
+    const size_t ncells = size_t(h->nbins) * L.g.CPB;
     L.nblk = uint32_t((n + BIN_THREADS - 1) / BIN_THREADS);
     L.max_doublets = h->max_doublets_user ? h->max_doublets_user : default_max_doublets(max_sp);
     L.max_dump = h->max_dump;
@@ -110,6 +145,11 @@ Layout make_layout(const b200seed_handle* h, uint32_t max_sp) {
         return at;
     };
     L.control = take(sizeof(Control));
+    L.cell_cnt = take(ncells * 4);
+    L.zero_bytes = o;
+    L.cell_off = take((ncells + 1) * 4);
+    L.csp4 = take(n * 16);
+    L.ccanon = take(n * 4);
     L.bin_of = take(n * 4);
     L.blk_hist = take(size_t(h->nbins) * L.nblk * 4);
     L.bin_off = take((size_t(h->nbins) + 1) * 4);
@@ -526,8 +566,9 @@ int b200seed_get_timings(b200seed_handle* h, const char** names, float* ms, int 
 }
 
 int b200seed_launches_per_event(const b200seed_handle*, int with_params) {
-    // k_bin_count, k_scan, k_bin_scatter, k_doublets, k_triplets, k_scan, k_seed_gather
-    return 7 + (with_params ? 1 : 0);
+    // k_bin_count, k_scan, k_cell_scan, k_bin_scatter, k_doublets, k_triplets, k_scan,
+    // k_seed_gather
+    return 8 + (with_params ? 1 : 0);
 }
 
 int b200seed_run(b200seed_handle* h, void* stream, uint32_t n_sp, const float* d_xyz,
@@ -575,11 +616,18 @@ int b200seed_run(b200seed_handle* h, void* stream, uint32_t n_sp, const float* d
     const uint32_t nblk = L.nblk;
     const uint32_t K = h->finder.maxSeedsPerSpM;
 
-    CUDA_TRY(h, cudaMemsetAsync(ctrl, 0, sizeof(Control), s));
+    uint32_t* cell_cnt = reinterpret_cast<uint32_t*>(at(L.cell_cnt));
+    uint32_t* cell_off = reinterpret_cast<uint32_t*>(at(L.cell_off));
+    float4* csp4 = reinterpret_cast<float4*>(at(L.csp4));
+    uint32_t* ccanon = reinterpret_cast<uint32_t*>(at(L.ccanon));
+    if (uint64_t(h->dev.scope0 + h->dev.scope1 + 1u) * n_sp > 0xFFFFFFFFull)
+        return fail(h, B200SEED_EINVAL, "b200seed_run: too many spacepoints for this neighbor_scope");
+
+    CUDA_TRY(h, cudaMemsetAsync(ws, 0, L.zero_bytes, s));
     {
         KernelTimer t(h, s, "bin_count");
         k_bin_count<<<nblk, BIN_THREADS, h->nbins * sizeof(uint32_t), s>>>(
-            h->dev, n_sp, d_xyz, bin_of, blk_hist, h->nbins, nblk);
+            h->dev, L.g, n_sp, d_xyz, bin_of, blk_hist, cell_cnt, h->nbins, nblk);
     }
     {
         KernelTimer t(h, s, "scan_bins");
@@ -587,9 +635,14 @@ int b200seed_run(b200seed_handle* h, void* stream, uint32_t n_sp, const float* d
                                           bin_off, h->nbins, nblk);
     }
     {
+        KernelTimer t(h, s, "cell_scan");
+        k_cell_scan<<<h->nbins, 256, 0, s>>>(cell_cnt, cell_off, bin_off, L.g.CPB, h->nbins);
+    }
+    {
         KernelTimer t(h, s, "bin_scatter");
-        k_bin_scatter<<<nblk, BIN_THREADS, 0, s>>>(n_sp, d_xyz, d_var_z, d_var_r, bin_of, blk_hist,
-                                                   nblk, sp4, var2, sorted_index, sorted_bin);
+        k_bin_scatter<<<nblk, BIN_THREADS, 0, s>>>(h->dev, L.g, n_sp, d_xyz, d_var_z, d_var_r, bin_of,
+                                                   blk_hist, nblk, sp4, var2, sorted_index,
+                                                   sorted_bin, cell_off, cell_cnt, csp4, ccanon);
     }
     {
         DoubletArgs a{};
@@ -597,6 +650,9 @@ int b200seed_run(b200seed_handle* h, void* stream, uint32_t n_sp, const float* d
         a.sp4 = sp4;
         a.var2 = var2;
         a.sorted_bin = sorted_bin;
+        a.cell_off = cell_off;
+        a.csp4 = csp4;
+        a.ccanon = ccanon;
         a.cnt_b = cnt;
         a.cnt_t = cnt + n_sp;
         a.off_b = off;
@@ -604,9 +660,11 @@ int b200seed_run(b200seed_handle* h, void* stream, uint32_t n_sp, const float* d
         a.arena_b = reinterpret_cast<DoubletRec*>(at(L.arena_b));
         a.arena_t = reinterpret_cast<DoubletRec*>(at(L.arena_t));
         a.ctrl = ctrl;
+        a.g = L.g;
         a.max_doublets = uint32_t(L.max_doublets);
-        a.stage_cap = doublet_stage_cap(n_sp);
-        const size_t smem = size_t(WARPS_PER_CTA) * (64 + 3 * a.stage_cap) * 4;
+        a.cap_b = doublet_stage_cap(n_sp);
+        a.cap_t = a.cap_b / 2;
+        const size_t smem = size_t(WARPS_PER_CTA) * doublet_smem_words(a.cap_b, a.cap_t) * 4;
         uint32_t grid = (n_sp + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
         const uint32_t max_grid = uint32_t(h->num_sms) * 8;
         if (grid > max_grid) grid = max_grid;
@@ -617,6 +675,7 @@ int b200seed_run(b200seed_handle* h, void* stream, uint32_t n_sp, const float* d
         TripletArgs a{};
         a.sp4 = sp4;
         a.var2 = var2;
+        a.sorted_bin = sorted_bin;
         a.cnt_b = cnt;
         a.cnt_t = cnt + n_sp;
         a.off_b = off;
@@ -851,6 +910,37 @@ void b200seed_host_probe_doublets(const void* devcfg, uint32_t n, const float* m
             float* q = lc + 6 * size_t(i);
             q[0] = l.Zo, q[1] = l.cotTheta, q[2] = l.iDeltaR, q[3] = l.Er, q[4] = l.U, q[5] = l.V;
         }
+    }
+}
+// Pruning index: for n (middle, other) pairs, whether the other spacepoint's cell lies inside
+// the cell window k_doublets visits for that middle (grid sized for n_sp spacepoints).
+// m/o = {x,y,z,varZ,varR}; bins = reference bin of each `other` (from ..._probe_bins).
+// grid_out (optional) receives {NR, NZc}.
+void b200seed_host_probe_cell_window(const void* devcfg, const b200seed_finder_cfg* finder,
+                                     uint32_t n_sp, uint32_t n, const float* m, const float* o,
+                                     const uint32_t* o_bin, int32_t* visited, uint32_t* grid_out) {
+    const DevCfg& d = *static_cast<const DevCfg*>(devcfg);
+    const CellGrid g = make_cell_grid(d, *finder, n_sp);
+    if (grid_out) {
+        grid_out[0] = g.NR;
+        grid_out[1] = g.NZc;
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* a = m + 5 * size_t(i);
+        const float* b = o + 5 * size_t(i);
+        const float rM = sp_radius(a[0], a[1]), r2 = sp_radius(b[0], b[1]);
+        const float er = 1e-2f + 1e-5f * (rM + absf(d.deltaRMax));
+        const uint32_t row_lo = cell_row(g, rM - d.deltaRMax - er);
+        const uint32_t row_hi = cell_row(g, rM + d.deltaRMax + er);
+        const uint32_t row = cell_row(g, r2);
+        const uint32_t zb = o_bin[i] / d.nPhi;
+        int v = 0;
+        float L, U;
+        if (row >= row_lo && row <= row_hi && cell_row_window(d, g, rM, a[2], row, L, U)) {
+            const uint32_t c = cell_z(g, zb, b[2]);
+            v = (c >= cell_z(g, zb, L) && c <= cell_z(g, zb, U)) ? 1 : 0;
+        }
+        visited[i] = v;
     }
 }
 // triplet decision for n (middle, lb, lt) combinations; out = {curvature, impact}

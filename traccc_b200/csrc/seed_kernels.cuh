@@ -3,11 +3,15 @@
 // Pipeline of one event (all on one stream, no host synchronisation, every intermediate
 // addressed through the workspace):
 //
-//   k_bin_count      is_valid_sp + bin index per spacepoint, per-block bin histogram
+//   k_bin_count      is_valid_sp + bin index per spacepoint, per-block bin histogram,
+//                    population of the fine (r, z) cells inside every bin
 //   k_scan           single-CTA exclusive scan of the [bin][block] histogram matrix
+//   k_cell_scan      CTA per bin: start of every (r row, z cell) inside the bin
 //   k_bin_scatter    stable scatter into bin-sorted float4 {x,y,z,r} / float2 {varZ,varR}
-//   k_doublets       warp per middle: stage-1 cuts on all neighbour-bin candidates,
-//                    ballot/popc compaction, stage-2 on survivors only, lin_circle, arena write
+//                    (the reference's grid order) + the cell-sorted copy used for pruning
+//   k_doublets       warp per middle (ticket queue): cell windows of the neighbour bins ->
+//                    flattened candidate list -> exact doublet cuts at full lane occupancy,
+//                    ballot/popc compaction, lin_circle, arena write
 //   k_triplets       warp per middle (atomic ticket queue): lane-owns-mid-bottom x loop over
 //                    mid-tops, cut-1 -> ballot compaction -> full cut, compatible-seed bonus,
 //                    per-middle top-N in shared memory
@@ -50,7 +54,9 @@ struct Control {
     uint32_t dump_cursor;
     uint32_t n_valid;         // written by the first scan
     uint32_t n_seeds_total;   // written by the second scan
-    uint32_t pad[3];
+    uint32_t ticket_d;        // k_doublets work queue
+    uint32_t pad[2];
+    unsigned long long pair_visited;  // candidates actually loaded by k_doublets
 };
 
 // One doublet record in the arena: two float4.
@@ -70,9 +76,9 @@ struct __align__(16) TripletDumpRec {
 // (1) binning: count
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(BIN_THREADS)
-k_bin_count(const DevCfg cfg, const uint32_t n_sp, const float* __restrict__ xyz,
-            uint32_t* __restrict__ bin_of, uint32_t* __restrict__ blk_hist, const uint32_t nbins,
-            const uint32_t nblk) {
+k_bin_count(const DevCfg cfg, const CellGrid g, const uint32_t n_sp, const float* __restrict__ xyz,
+            uint32_t* __restrict__ bin_of, uint32_t* __restrict__ blk_hist,
+            uint32_t* __restrict__ cell_cnt, const uint32_t nbins, const uint32_t nblk) {
     extern __shared__ uint32_t s_hist[];
     for (uint32_t b = threadIdx.x; b < nbins; b += BIN_THREADS) s_hist[b] = 0;
     __syncthreads();
@@ -83,7 +89,10 @@ k_bin_count(const DevCfg cfg, const uint32_t n_sp, const float* __restrict__ xyz
         const float z = __ldg(xyz + 3 * size_t(i) + 2);
         const uint32_t bin = sp_bin(cfg, x, y, z);
         bin_of[i] = bin;
-        if (bin != INVALID_BIN) atomicAdd(&s_hist[bin], 1u);
+        if (bin != INVALID_BIN) {
+            atomicAdd(&s_hist[bin], 1u);
+            atomicAdd(&cell_cnt[sp_cell(cfg, g, bin, sp_radius(x, y), z)], 1u);
+        }
     }
     __syncthreads();
     for (uint32_t b = threadIdx.x; b < nbins; b += BIN_THREADS)
@@ -156,11 +165,14 @@ k_scan(const uint32_t* in, uint32_t* data, uint32_t len, const uint32_t* __restr
 // (1) binning: stable scatter into the bin-sorted SoA
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(BIN_THREADS)
-k_bin_scatter(const uint32_t n_sp, const float* __restrict__ xyz, const float* __restrict__ var_z,
+k_bin_scatter(const DevCfg cfg, const CellGrid g, const uint32_t n_sp,
+              const float* __restrict__ xyz, const float* __restrict__ var_z,
               const float* __restrict__ var_r, const uint32_t* __restrict__ bin_of,
               const uint32_t* __restrict__ blk_scan, const uint32_t nblk,
               float4* __restrict__ sp4, float2* __restrict__ var2,
-              uint32_t* __restrict__ sorted_index, uint32_t* __restrict__ sorted_bin) {
+              uint32_t* __restrict__ sorted_index, uint32_t* __restrict__ sorted_bin,
+              const uint32_t* __restrict__ cell_off, uint32_t* __restrict__ cell_cur,
+              float4* __restrict__ csp4, uint32_t* __restrict__ ccanon) {
     __shared__ uint32_t s_bin[BIN_THREADS];
     const uint32_t i = blockIdx.x * BIN_THREADS + threadIdx.x;
     const uint32_t bin = (i < n_sp) ? bin_of[i] : INVALID_BIN;
@@ -176,10 +188,72 @@ k_bin_scatter(const uint32_t n_sp, const float* __restrict__ xyz, const float* _
     const float x = __ldg(xyz + 3 * size_t(i));
     const float y = __ldg(xyz + 3 * size_t(i) + 1);
     const float z = __ldg(xyz + 3 * size_t(i) + 2);
-    sp4[pos] = make_float4(x, y, z, sp_radius(x, y));
+    const float r = sp_radius(x, y);
+    const float4 P = make_float4(x, y, z, r);
+    sp4[pos] = P;
     var2[pos] = make_float2(var_z ? __ldg(var_z + i) : 0.f, var_r ? __ldg(var_r + i) : 0.f);
     sorted_index[pos] = i;
     sorted_bin[pos] = bin;
+    // cell-sorted copy (order inside a cell is arbitrary: nothing downstream depends on it)
+    const uint32_t cell = sp_cell(cfg, g, bin, r, z);
+    const uint32_t cpos = cell_off[cell] + atomicAdd(&cell_cur[cell], 1u);
+    csp4[cpos] = P;
+    ccanon[cpos] = pos;
+}
+
+// CTA per reference bin: cell_off[bin * CPB + c] = bin_off[bin] + exclusive scan of the
+// cell populations of this bin; the population array is zeroed again (k_bin_scatter uses
+// it as its cursor). cell_off[nbins * CPB] = n_valid.
+__global__ void __launch_bounds__(256)
+k_cell_scan(uint32_t* __restrict__ cell_cnt, uint32_t* __restrict__ cell_off,
+            const uint32_t* __restrict__ bin_off, const uint32_t CPB, const uint32_t nbins) {
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_total;
+    const uint32_t bin = blockIdx.x;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t carry = __ldg(bin_off + bin);
+    for (uint32_t base = 0; base < CPB; base += 256 * 4) {
+        const uint32_t idx = base + threadIdx.x * 4;
+        uint32_t v[4];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[k] = (idx + k < CPB) ? cell_cnt[size_t(bin) * CPB + idx + k] : 0u;
+            sum += v[k];
+        }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= uint32_t(off)) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t ws = (lane < 8) ? s_warp[lane] : 0u;
+            uint32_t wincl = ws;
+#pragma unroll
+            for (int off = 1; off < 8; off <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, wincl, off);
+                if (lane >= uint32_t(off)) wincl += t;
+            }
+            if (lane < 8) s_warp[lane] = wincl - ws;
+            if (lane == 7) s_total = wincl;
+        }
+        __syncthreads();
+        uint32_t run = carry + s_warp[warp] + incl - sum;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (idx + k < CPB) {
+                cell_off[size_t(bin) * CPB + idx + k] = run;
+                cell_cnt[size_t(bin) * CPB + idx + k] = 0u;
+            }
+            run += v[k];
+        }
+        carry += s_total;
+        __syncthreads();
+    }
+    if (bin == nbins - 1 && threadIdx.x == 0) cell_off[size_t(nbins) * CPB] = carry;
 }
 
 // ---------------------------------------------------------------------------
@@ -187,9 +261,12 @@ k_bin_scatter(const uint32_t n_sp, const float* __restrict__ xyz, const float* _
 // ---------------------------------------------------------------------------
 struct DoubletArgs {
     const uint32_t* bin_off;      // [nbins+1]
-    const float4* sp4;            // sorted {x,y,z,r}
+    const float4* sp4;            // sorted {x,y,z,r} (reference grid order)
     const float2* var2;           // sorted {varZ,varR}
     const uint32_t* sorted_bin;   // [n_valid]
+    const uint32_t* cell_off;     // [nbins*CPB+1] start of every cell in the cell-sorted arrays
+    const float4* csp4;           // cell-sorted {x,y,z,r}
+    const uint32_t* ccanon;       // cell-sorted -> sorted position
     uint32_t* cnt_b;              // [n_sp] doublets per middle (0 if inactive)
     uint32_t* cnt_t;
     uint32_t* off_b;              // [n_sp] arena offsets
@@ -197,8 +274,9 @@ struct DoubletArgs {
     DoubletRec* arena_b;
     DoubletRec* arena_t;
     Control* ctrl;
+    CellGrid g;
     uint32_t max_doublets;
-    uint32_t stage_cap;           // staged candidates per direction per warp (shared memory)
+    uint32_t cap_b, cap_t;        // staged doublets per warp (shared memory)
 };
 
 __device__ __forceinline__ uint32_t lanemask_lt() {
@@ -207,13 +285,33 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
     return m;
 }
 
-// Generator of the neighbour-bin candidate ranges of a middle, in the reference's order:
-// phi bins outer (circular zone, axis.hpp:336-362), z bins inner (regular zone,
-// axis.hpp:162-173), as in doublet_finding.hpp:67-80. Ranges that are adjacent in the
-// bin-sorted array are merged (with one z bin the three phi neighbours are contiguous
-// unless they wrap around).
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= uint32_t(o)) v += t;
+    }
+    return v;
+}
+
+// Lane that owns flattened element p, given the inclusive prefix sums `incl` of the lanes'
+// segment lengths (p < total): the number of lanes whose inclusive prefix is <= p.
+__device__ __forceinline__ uint32_t owner_lane(uint32_t incl, uint32_t p) {
+    uint32_t r = 0;
+#pragma unroll
+    for (uint32_t step = 16; step >= 1; step >>= 1) {
+        const uint32_t v = __shfl_sync(0xffffffffu, incl, (r + step - 1) & 31u);
+        if (v <= p) r += step;
+    }
+    return r & 31u;
+}
+
+// The neighbour bins of a middle in the reference's order: phi bins outer (circular zone,
+// axis.hpp:336-362), z bins inner (regular zone, axis.hpp:162-173), as in
+// doublet_finding.hpp:67-80. Neighbour q (0 <= q < nq) is bin(q); q / nz is the position of
+// its phi bin in the walk.
 struct NeighbourWalk {
-    uint32_t r0, n_phi_seq, z0, nz, q, nq;
+    uint32_t r0, n_phi_seq, z0, nz, nq;
     __device__ __forceinline__ void init(const DevCfg& cfg, uint32_t bin, float zM) {
         const uint32_t phi_bin = bin % cfg.nPhi;
         r0 = circular_remap(cfg.nPhi, phi_bin, -int(cfg.scope0));
@@ -225,163 +323,176 @@ struct NeighbourWalk {
         z0 = (ibinmin >= 0) ? uint32_t(ibinmin) : 0u;
         const uint32_t z1 = (ibinmax < int(cfg.nZ)) ? uint32_t(ibinmax) : cfg.nZ - 1u;
         nz = (z1 + 1u > z0) ? (z1 + 1u - z0) : 0u;
-        q = 0;
         nq = n_phi_seq * nz;
     }
-    __device__ __forceinline__ void rewind() { q = 0; }
-    // Next merged range [lo, hi); returns false when exhausted.
-    __device__ __forceinline__ bool next(const DevCfg& cfg, const uint32_t* __restrict__ bin_off,
-                                         uint32_t& lo, uint32_t& hi) {
-        lo = hi = 0;
-        while (q < nq) {
-            uint32_t pb = r0 + q / nz;
-            if (pb > cfg.nPhi - 1u) pb -= cfg.nPhi;
-            const uint32_t b = pb + (z0 + q % nz) * cfg.nPhi;
-            const uint32_t blo = __ldg(bin_off + b), bhi = __ldg(bin_off + b + 1);
-            if (blo == bhi) {
-                ++q;
-            } else if (lo == hi) {
-                lo = blo;
-                hi = bhi;
-                ++q;
-            } else if (blo == hi) {
-                hi = bhi;
-                ++q;
-            } else {
-                break;
-            }
-        }
-        return hi != lo;
+    __device__ __forceinline__ uint32_t zbin(uint32_t q) const { return z0 + q % nz; }
+    __device__ __forceinline__ uint32_t bin(const DevCfg& cfg, uint32_t q) const {
+        uint32_t pb = r0 + q / nz;
+        if (pb > cfg.nPhi - 1u) pb -= cfg.nPhi;
+        return pb + zbin(q) * cfg.nPhi;
     }
 };
 
-// Rank of element k in the ascending (value, index) order of v[0..n) — O(n) per element,
-// used for the short per-middle mid-top lists.
-template <typename LoadF>
-__device__ __forceinline__ uint32_t rank_by_value(LoadF load, uint32_t n, uint32_t k, float vk) {
-    uint32_t rank = 0;
-    for (uint32_t j = 0; j < n; ++j) {
-        const float vj = load(j);
-        rank += ((vj < vk) || (vj == vk && j < k)) ? 1u : 0u;
-    }
-    return rank;
+// Position of a spacepoint in the reference's candidate order of one middle: neighbour phi
+// bins in walk order, then the grid order (z bins ascending, position in bin).
+__device__ __forceinline__ uint32_t canon_key(uint32_t walk_phi, uint32_t n_valid, uint32_t pos) {
+    return walk_phi * n_valid + pos;
 }
 
-// Shared memory per warp of k_doublets: 64-entry compaction ring + 2 staging lists + the
-// cotTheta keys of the staged mid-top doublets.
-// Arena records: mid-bottom lists keep the reference's order (phi bins outer, z bins inner,
-// position in bin); mid-top lists are sorted by cotTheta so that k_triplets can binary-search
-// the scattering window of each mid-bottom doublet, and carry their canonical index.
+// Ranks of element k of the staged mid-top list: `kc` = position in the reference's order
+// (keys are unique), `ks` = position in the (cotTheta, reference order) sort.
+template <typename LoadCot, typename LoadKey>
+__device__ __forceinline__ void top_ranks(LoadCot cot, LoadKey key, uint32_t n, float ck, uint32_t kk,
+                                          uint32_t& kc, uint32_t& ks) {
+    kc = 0;
+    ks = 0;
+    for (uint32_t j = 0; j < n; ++j) {
+        const float cj = cot(j);
+        const uint32_t kj = key(j);
+        kc += (kj < kk) ? 1u : 0u;
+        ks += ((cj < ck) || (cj == ck && kj < kk)) ? 1u : 0u;
+    }
+}
+
+// Shared memory per warp of k_doublets (32-bit words).
+__host__ __device__ inline uint32_t doublet_smem_words(uint32_t cap_b, uint32_t cap_t) {
+    return cap_b + 3u * cap_t;
+}
+
+// Arena records. The order of a mid-bottom list is arbitrary (nothing downstream depends on
+// it; the parity tests sort it by canon_key). Mid-top lists are sorted by cotTheta so that
+// k_triplets can binary-search the scattering window of each mid-bottom doublet, and carry
+// their index in the reference's order:
 //   bottom: a = {cotTheta, iDeltaR, Er, U}  b = {V, Zo,               r_other, pos_other}
 //   top   : a = {cotTheta, iDeltaR, Er, U}  b = {V, bits(canonical k), r_other, pos_other}
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 k_doublets(const DevCfg cfg, const DoubletArgs a) {
     extern __shared__ uint32_t s_mem[];
-    __shared__ unsigned long long s_pairs;
+    __shared__ unsigned long long s_pairs[2];
     __shared__ uint32_t s_acc[3];  // active, nb, nt
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t ltmask = lanemask_lt();
-    uint32_t* ring = s_mem + size_t(warp) * (64 + 3 * a.stage_cap);
-    uint32_t* stage_b = ring + 64;
-    uint32_t* stage_t = stage_b + a.stage_cap;
-    float* cot_s = reinterpret_cast<float*>(stage_t + a.stage_cap);
+    uint32_t* stage_b = s_mem + size_t(warp) * doublet_smem_words(a.cap_b, a.cap_t);
+    uint32_t* stage_t = stage_b + a.cap_b;
+    uint32_t* key_s = stage_t + a.cap_t;
+    float* cot_s = reinterpret_cast<float*>(key_s + a.cap_t);
     if (threadIdx.x == 0) {
-        s_pairs = 0ull;
+        s_pairs[0] = s_pairs[1] = 0ull;
         s_acc[0] = s_acc[1] = s_acc[2] = 0u;
     }
     __syncthreads();
     const uint32_t n_valid = a.ctrl->n_valid;
-    const uint32_t total_warps = gridDim.x * WARPS_PER_CTA;
-    unsigned long long pairs = 0ull;
+    const CellGrid g = a.g;
+    unsigned long long pairs = 0ull, visited = 0ull;  // per lane
     uint32_t acc_active = 0, acc_nb = 0, acc_nt = 0;
 
-    for (uint32_t m = blockIdx.x * WARPS_PER_CTA + warp; m < n_valid; m += total_warps) {
+    while (true) {
+        uint32_t m = 0;
+        if (lane == 0) m = atomicAdd(&a.ctrl->ticket_d, 1u);
+        m = __shfl_sync(0xffffffffu, m, 0);
+        if (m >= n_valid) break;
         const float4 M = __ldg(a.sp4 + m);
         const float2 VM = __ldg(a.var2 + m);  // {varZ, varR}
         NeighbourWalk walk;
         walk.init(cfg, __ldg(a.sorted_bin + m), M.z);
+        // the reference tests every spacepoint of the neighbour bins: count them
+        for (uint32_t q = lane; q < walk.nq; q += 32) {
+            const uint32_t b = walk.bin(cfg, q);
+            pairs += __ldg(a.bin_off + b + 1) - __ldg(a.bin_off + b);
+        }
+        // rows that can hold a doublet partner: |r - rM| <= deltaRMax
+        const float er = 1e-2f + 1e-5f * (M.w + absf(cfg.deltaRMax));
+        const uint32_t row_lo = cell_row(g, M.w - cfg.deltaRMax - er);
+        const uint32_t row_hi = cell_row(g, M.w + cfg.deltaRMax + er);
+        const uint32_t nrows = row_hi - row_lo + 1u;
+        const uint32_t ncombo = walk.nq * nrows;
 
         uint32_t nB = 0, nT = 0;
         uint32_t offB = 0, offT = 0;
-        // pass 0: stage the survivors' positions in shared memory. pass 1 (only when a
-        // staging list overflowed): same scan, records written straight to the arena.
+        // pass 0: stage the doublets' cell-sorted positions in shared memory. pass 1 (only
+        // when a staging list overflowed): same scan, records written straight to the arena.
         for (int pass = 0; pass < 2; ++pass) {
             const bool direct = (pass == 1);
-            uint32_t qhead = 0, qn = 0;
-            uint32_t wB = 0, wT = 0;  // survivors so far in this pass
-            walk.rewind();
-            bool more = true;
-            while (more || qn > 0) {
-                uint32_t lo = 0, hi = 0;
-                if (more) more = walk.next(cfg, a.bin_off, lo, hi);
-                if (pass == 0 && lane == 0) pairs += (hi - lo);
-                uint32_t c0 = lo;
-                // scan this range; when it is the final flush (more == false) only drain
-                while (c0 < hi || (!more && qn > 0)) {
-                    if (c0 < hi) {
-                        const uint32_t c = c0 + lane;
-                        int st = 0;
-                        if (c < hi) {
-                            const float4 P = __ldg(a.sp4 + c);
-                            st = doublet_stage1(cfg, M.w, M.z, P.w, P.z);
-                        }
-                        const uint32_t mask = __ballot_sync(0xffffffffu, st != 0);
-                        if (st != 0)
-                            ring[(qhead + qn + __popc(mask & ltmask)) & 63u] =
-                                c | (st == 2 ? 0x80000000u : 0u);
-                        qn += __popc(mask);
-                        c0 += 32;
-                        __syncwarp();
-                        if (qn < 32) continue;
+            uint32_t wB = 0, wT = 0;  // doublets found so far in this pass
+            for (uint32_t j0 = 0; j0 < ncombo; j0 += 32) {
+                // lane j: one (neighbour bin, row) -> contiguous run of cells
+                const uint32_t j = j0 + lane;
+                uint32_t lo = 0, len = 0, wphi = 0;
+                if (j < ncombo) {
+                    const uint32_t q = j / nrows, row = row_lo + j % nrows;
+                    float L, U;
+                    if (cell_row_window(cfg, g, M.w, M.z, row, L, U)) {
+                        const uint32_t zb = walk.zbin(q);
+                        const uint32_t base = walk.bin(cfg, q) * g.CPB + row * g.NZc;
+                        lo = __ldg(a.cell_off + base + cell_z(g, zb, L));
+                        len = __ldg(a.cell_off + base + cell_z(g, zb, U) + 1u) - lo;
+                        wphi = q / walk.nz;
                     }
-                    // drain up to 32 stage-1 survivors: full-warp stage-2 evaluation
-                    const uint32_t take = qn < 32 ? qn : 32;
-                    bool ok = false, top = false;
-                    uint32_t c = 0;
+                }
+                const uint32_t incl = warp_incl_scan(len, lane);
+                const uint32_t excl = incl - len;
+                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                if (pass == 0 && lane == 0) visited += total;
+                for (uint32_t p0 = 0; p0 < total; p0 += 32) {
+                    const uint32_t p = p0 + lane;
+                    const uint32_t o = owner_lane(incl, p);
+                    const uint32_t c = __shfl_sync(0xffffffffu, lo, o) +
+                                       (p - __shfl_sync(0xffffffffu, excl, o));
+                    const uint32_t wp = __shfl_sync(0xffffffffu, wphi, o);
+                    int st = 0;
                     float4 P = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (lane < take) {
-                        const uint32_t e = ring[(qhead + lane) & 63u];
-                        c = e & 0x7fffffffu;
-                        top = (e >> 31) != 0u;
-                        P = __ldg(a.sp4 + c);
-                        ok = doublet_stage2(cfg, M.x, M.y, P.x, P.y);
+                    if (p < total) {
+                        P = __ldg(a.csp4 + c);
+                        st = doublet_stage1(cfg, M.w, M.z, P.w, P.z);
+                        if (st != 0 && !doublet_stage2(cfg, M.x, M.y, P.x, P.y)) st = 0;
                     }
-                    const uint32_t mB = __ballot_sync(0xffffffffu, ok && !top);
-                    const uint32_t mT = __ballot_sync(0xffffffffu, ok && top);
-                    if (ok) {
+                    const uint32_t mB = __ballot_sync(0xffffffffu, st == 1);
+                    const uint32_t mT = __ballot_sync(0xffffffffu, st == 2);
+                    if (st != 0) {
+                        const bool top = (st == 2);
                         const uint32_t k = top ? (wT + __popc(mT & ltmask))
                                                : (wB + __popc(mB & ltmask));
                         if (!direct) {
-                            if (k < a.stage_cap) (top ? stage_t : stage_b)[k] = c;
+                            if (top) {
+                                if (k < a.cap_t) {
+                                    stage_t[k] = c;
+                                    key_s[k] = wp;
+                                }
+                            } else if (k < a.cap_b) {
+                                stage_b[k] = c;
+                            }
                         } else {
-                            const float2 V = __ldg(a.var2 + c);
+                            const uint32_t pos = __ldg(a.ccanon + c);
+                            const float2 V = __ldg(a.var2 + pos);
                             const LinCircle l = transform_coordinates(
                                 !top, M.x, M.y, M.z, M.w, VM.x, VM.y, P.x, P.y, P.z, V.x, V.y);
                             DoubletRec r;
                             r.a = make_float4(l.cotTheta, l.iDeltaR, l.Er, l.U);
-                            r.b = make_float4(l.V, top ? __uint_as_float(k) : l.Zo, P.w,
-                                              __uint_as_float(c));
+                            r.b = make_float4(l.V,
+                                              top ? __uint_as_float(canon_key(wp, n_valid, pos))
+                                                  : l.Zo,
+                                              P.w, __uint_as_float(pos));
                             // unsorted tops go to the second half of a 2*nT allocation
                             (top ? a.arena_t + offT + nT : a.arena_b + offB)[k] = r;
                         }
                     }
                     wB += __popc(mB);
                     wT += __popc(mT);
-                    qhead = (qhead + take) & 63u;
-                    qn -= take;
-                    __syncwarp();
                 }
             }
             if (direct) {
-                // sort the mid-top records by cotTheta: second half -> first half
+                // sort the mid-top records: second half -> first half
                 const DoubletRec* src = a.arena_t + offT + nT;
                 DoubletRec* dst = a.arena_t + offT;
                 __syncwarp();
                 for (uint32_t k = lane; k < nT; k += 32) {
-                    const DoubletRec r = src[k];
-                    const uint32_t rank = rank_by_value(
-                        [&](uint32_t j) { return src[j].a.x; }, nT, k, r.a.x);
-                    dst[rank] = r;
+                    DoubletRec r = src[k];
+                    uint32_t kc, ks;
+                    top_ranks([&](uint32_t j) { return src[j].a.x; },
+                              [&](uint32_t j) { return __float_as_uint(src[j].b.y); }, nT, r.a.x,
+                              __float_as_uint(r.b.y), kc, ks);
+                    r.b.y = __uint_as_float(kc);
+                    dst[ks] = r;
                 }
                 break;
             }
@@ -392,7 +503,7 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
                 nB = nT = 0;
                 break;
             }
-            const bool spill = (nB > a.stage_cap || nT > a.stage_cap);
+            const bool spill = (nB > a.cap_b || nT > a.cap_t);
             const uint32_t allocT = spill ? 2u * nT : nT;  // room to sort in place
             if (lane == 0) {
                 offB = atomicAdd(&a.ctrl->cursor[0], nB);
@@ -407,39 +518,52 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
                 break;
             }
             if (spill) continue;  // rare: redo the scan in direct mode
-            // common path: lin_circle of every staged survivor, full lanes
+            __syncwarp();
+            // common path: lin_circle of every staged doublet, full lanes
             for (uint32_t k = lane; k < nB; k += 32) {
                 const uint32_t c = stage_b[k];
-                const float4 P = __ldg(a.sp4 + c);
-                const float2 V = __ldg(a.var2 + c);
+                const float4 P = __ldg(a.csp4 + c);
+                const uint32_t pos = __ldg(a.ccanon + c);
+                const float2 V = __ldg(a.var2 + pos);
                 const LinCircle l = transform_coordinates(true, M.x, M.y, M.z, M.w, VM.x, VM.y, P.x,
                                                           P.y, P.z, V.x, V.y);
                 DoubletRec r;
                 r.a = make_float4(l.cotTheta, l.iDeltaR, l.Er, l.U);
-                r.b = make_float4(l.V, l.Zo, P.w, __uint_as_float(c));
+                r.b = make_float4(l.V, l.Zo, P.w, __uint_as_float(pos));
                 a.arena_b[offB + k] = r;
             }
-            // mid-tops: cotTheta keys first, then each record goes to its sorted position
-            for (uint32_t k = lane; k < nT; k += 32) {
-                const uint32_t c = stage_t[k];
-                const float4 P = __ldg(a.sp4 + c);
-                const float2 V = __ldg(a.var2 + c);
-                cot_s[k] = transform_coordinates(false, M.x, M.y, M.z, M.w, VM.x, VM.y, P.x, P.y,
-                                                 P.z, V.x, V.y).cotTheta;
+            // mid-tops: lin_circle once, the sort keys go to shared memory, the record waits
+            // in registers (the first 32 per lane-slot) for its two ranks
+            for (uint32_t k0 = 0; k0 < nT; k0 += 32) {
+                const uint32_t k = k0 + lane;
+                if (k < nT) {
+                    const uint32_t c = stage_t[k];
+                    const float4 P = __ldg(a.csp4 + c);
+                    const uint32_t pos = __ldg(a.ccanon + c);
+                    const float2 V = __ldg(a.var2 + pos);
+                    cot_s[k] = transform_coordinates(false, M.x, M.y, M.z, M.w, VM.x, VM.y, P.x,
+                                                     P.y, P.z, V.x, V.y).cotTheta;
+                    key_s[k] = canon_key(key_s[k], n_valid, pos);
+                }
             }
             __syncwarp();
-            for (uint32_t k = lane; k < nT; k += 32) {
-                const uint32_t c = stage_t[k];
-                const float4 P = __ldg(a.sp4 + c);
-                const float2 V = __ldg(a.var2 + c);
-                const LinCircle l = transform_coordinates(false, M.x, M.y, M.z, M.w, VM.x, VM.y, P.x,
-                                                          P.y, P.z, V.x, V.y);
-                const uint32_t rank =
-                    rank_by_value([&](uint32_t j) { return cot_s[j]; }, nT, k, cot_s[k]);
-                DoubletRec r;
-                r.a = make_float4(cot_s[k], l.iDeltaR, l.Er, l.U);
-                r.b = make_float4(l.V, __uint_as_float(k), P.w, __uint_as_float(c));
-                a.arena_t[offT + rank] = r;
+            for (uint32_t k0 = 0; k0 < nT; k0 += 32) {
+                const uint32_t k = k0 + lane;
+                if (k < nT) {
+                    const uint32_t c = stage_t[k];
+                    const float4 P = __ldg(a.csp4 + c);
+                    const uint32_t pos = __ldg(a.ccanon + c);
+                    const float2 V = __ldg(a.var2 + pos);
+                    const LinCircle l = transform_coordinates(false, M.x, M.y, M.z, M.w, VM.x, VM.y,
+                                                              P.x, P.y, P.z, V.x, V.y);
+                    uint32_t kc, ks;
+                    top_ranks([&](uint32_t j) { return cot_s[j]; },
+                              [&](uint32_t j) { return key_s[j]; }, nT, cot_s[k], key_s[k], kc, ks);
+                    DoubletRec r;
+                    r.a = make_float4(cot_s[k], l.iDeltaR, l.Er, l.U);
+                    r.b = make_float4(l.V, __uint_as_float(kc), P.w, __uint_as_float(pos));
+                    a.arena_t[offT + ks] = r;
+                }
             }
             break;
         }
@@ -456,15 +580,19 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
             acc_nt += nT;
         }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pairs += __shfl_xor_sync(0xffffffffu, pairs, o);
     if (lane == 0) {
-        atomicAdd(&s_pairs, pairs);
+        atomicAdd(&s_pairs[0], pairs);
+        atomicAdd(&s_pairs[1], visited);
         atomicAdd(&s_acc[0], acc_active);
         atomicAdd(&s_acc[1], acc_nb);
         atomicAdd(&s_acc[2], acc_nt);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (s_pairs) atomicAdd(&a.ctrl->pair_tests, s_pairs);
+        if (s_pairs[0]) atomicAdd(&a.ctrl->pair_tests, s_pairs[0]);
+        if (s_pairs[1]) atomicAdd(&a.ctrl->pair_visited, s_pairs[1]);
         if (s_acc[0]) {
             atomicAdd(&a.ctrl->n_active, s_acc[0]);
             atomicAdd(&a.ctrl->n_mid_bot, s_acc[1]);
@@ -479,6 +607,7 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
 struct TripletArgs {
     const float4* sp4;
     const float2* var2;
+    const uint32_t* sorted_bin;
     const uint32_t* cnt_b;
     const uint32_t* cnt_t;
     const uint32_t* off_b;
@@ -595,6 +724,15 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
         const float4 M = __ldg(a.sp4 + m);
         const float2 VM = __ldg(a.var2 + m);  // {varZ, varR}
         const float rM = M.w, varZM = VM.x, varRM = VM.y;
+        // order of a spacepoint among the doublet partners of this middle in the reference
+        // (canon_key of k_doublets); only evaluated for full ties in the seed ranking
+        const uint32_t walk_r0 =
+            circular_remap(cfg.nPhi, __ldg(a.sorted_bin + m) % cfg.nPhi, -int(cfg.scope0));
+        auto tie_key = [&](uint32_t pos) -> unsigned long long {
+            const uint32_t pb = __ldg(a.sorted_bin + pos) % cfg.nPhi;
+            const uint32_t w = (pb + cfg.nPhi - walk_r0) % cfg.nPhi;
+            return (unsigned long long)w * n_valid + pos;
+        };
 
         // bounds over the mid-tops for the conservative window
         float maxEr = 0.f, minEr = 0.f, maxIDR = 0.f, maxAbsCot = 0.f;
@@ -805,7 +943,20 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
                     const BlockTriplet c = list[i];
                     if (c.key == 0xFFFFFFFFu) continue;
                     uint32_t p = ntop;
-                    while (p > 0 && seed_before(c.weight, c.rT, top_w[p - 1], top_s[p - 1])) --p;
+                    while (p > 0) {
+                        const uint32_t q = p - 1;
+                        bool before;
+                        if (c.weight != top_w[q] || c.rT != top_s[q]) {
+                            before = seed_before(c.weight, c.rT, top_w[q], top_s[q]);
+                        } else {
+                            // full tie of triplet_sorter: the reference's order of discovery
+                            // (mid-bottom doublets outer, mid-top doublets inner) decides
+                            const unsigned long long cb = tie_key(c.key), eb = tie_key(top_b[q]);
+                            before = (cb != eb) ? (cb < eb) : (tie_key(lpos[i]) < tie_key(top_t[q]));
+                        }
+                        if (!before) break;
+                        --p;
+                    }
                     if (p >= K) continue;
                     const uint32_t last = (ntop < K) ? ntop : (K - 1);
                     for (uint32_t q = last; q > p; --q) {
@@ -898,6 +1049,7 @@ k_seed_gather(const uint32_t n_sp, const uint32_t K, const Control* __restrict__
             c.overflow = ctrl->overflow | (total > seed_capacity ? B200SEED_OVF_SEEDS : 0u);
             c.pair_tests = ctrl->pair_tests;
             c.triplet_tests = ctrl->triplet_tests;
+            c.pair_visited = ctrl->pair_visited;
             *counters = c;
         }
     }

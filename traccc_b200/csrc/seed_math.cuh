@@ -289,6 +289,116 @@ B200_HD bool doublet_stage2(const DevCfg& c, float x1, float y1, float x2, float
     return true;
 }
 
+// ---------------------------------------------------------------------------
+// Fine (r, z) cells inside every reference grid bin — a pruning index that is NOT part of
+// the reference: the reference tests every spacepoint of the (2*scope+1)^2 neighbour bins
+// against each middle (doublet_finding.hpp:74-104). Here each bin's content is additionally
+// stored sorted by (r row, z cell), and a middle only visits the cells that can hold a
+// spacepoint passing the first block of doublet cuts. The windows below are conservative
+// (margins far above the float rounding of the exact cuts), the exact cut still runs on
+// every visited candidate, so the accepted set is identical to the full scan.
+// ---------------------------------------------------------------------------
+struct CellGrid {
+    uint32_t NR;    // r rows per bin
+    uint32_t NZc;   // z cells per bin and row
+    uint32_t CPB;   // cells per bin = NR * NZc
+    uint32_t NZg;   // z cells over the whole z axis = nZ * NZc
+    float invRw;    // rows per mm
+    float rw;       // mm per row
+    float zMin;     // start of the z axis
+    float invZw;    // z cells per mm
+};
+
+// Row of a radius; monotone non-decreasing in r, last row open-ended.
+B200_HD uint32_t cell_row(const CellGrid& g, float r) {
+    const float t = r * g.invRw;
+    if (!(t >= 0.f)) return 0u;
+    if (t >= static_cast<float>(g.NR)) return g.NR - 1u;
+    return static_cast<uint32_t>(static_cast<int>(t));
+}
+// z cell inside reference z bin zb; monotone non-decreasing in z for a fixed zb, the first
+// and last cells of a bin are open-ended.
+B200_HD uint32_t cell_z(const CellGrid& g, uint32_t zb, float z) {
+    const float t = (z - g.zMin) * g.invZw;
+    long long zg;
+    if (!(t >= 0.f))
+        zg = 0;
+    else if (t >= static_cast<float>(g.NZg))
+        zg = static_cast<long long>(g.NZg) - 1;
+    else
+        zg = static_cast<long long>(static_cast<int>(t));
+    long long l = zg - static_cast<long long>(zb) * g.NZc;
+    if (l < 0) l = 0;
+    if (l > static_cast<long long>(g.NZc) - 1) l = static_cast<long long>(g.NZc) - 1;
+    return static_cast<uint32_t>(l);
+}
+
+// Serialised cell of a valid spacepoint: (reference bin, r row, z cell).
+B200_HD uint32_t sp_cell(const DevCfg& c, const CellGrid& g, uint32_t bin, float r, float z) {
+    const uint32_t zb = bin / c.nPhi;
+    return bin * g.CPB + cell_row(g, r) * g.NZc + cell_z(g, zb, z);
+}
+
+B200_HD float fmin_nan_lo(float a, float b) { return (b < a) ? b : a; }
+B200_HD float fmax_nan_hi(float a, float b) { return (b > a) ? b : a; }
+
+// z interval [L, U] outside of which no spacepoint of row `row` can pass doublet_stage1
+// against the middle (rM, zM); returns false if the whole row is excluded. NaN bounds mean
+// "unbounded" to the caller (cell_z_lo / cell_z_hi).
+B200_HD bool cell_row_window(const DevCfg& c, const CellGrid& g, float rM, float zM, uint32_t row,
+                             float& L, float& U) {
+    const float inf = u2f(0x7f800000u);
+    const float er = 1e-3f + 1e-5f * (absf(rM) + static_cast<float>(row + 1u) * g.rw);
+    const float rlo = static_cast<float>(row) * g.rw - er;
+    const float rhi = (row + 1u >= g.NR) ? inf : static_cast<float>(row + 1u) * g.rw + er;
+    const bool zo_ok = rM > 1e-3f;
+    const float inv = zo_ok ? 1.f / rM : 0.f;
+    const float a = (zM - c.collisionRegionMin) * inv;
+    const float b = (zM - c.collisionRegionMax) * inv;
+    const float cmag = (absf(zM) + absf(c.collisionRegionMin) + absf(c.collisionRegionMax)) * inv;
+    bool any = false;
+    L = inf;
+    U = -inf;
+    for (int dir = 0; dir < 2; ++dir) {
+        // dir 0: bottom, deltaR = rM - r2; dir 1: top, deltaR = r2 - rM
+        float dlo = (dir == 0) ? (rM - rhi) : (rlo - rM);
+        float dhi = (dir == 0) ? (rM - rlo) : (rhi - rM);
+        if (dlo < c.deltaRMin - er) dlo = c.deltaRMin - er;
+        if (dhi > c.deltaRMax + er) dhi = c.deltaRMax + er;
+        if (dlo > dhi) continue;
+        if (dlo < 0.f) dlo = 0.f;
+        float l = -inf, u = inf;
+        if (zo_ok) {
+            // bottom: z2 in (zM - a dR, zM - b dR); top: z2 in (zM + b dR, zM + a dR); the
+            // bounds are linear in dR, so their extremes sit at dlo / dhi.
+            const float sg = (dir == 0) ? -1.f : 1.f;
+            const float v0 = zM + sg * (a * dlo), v1 = zM + sg * (a * dhi);
+            const float v2 = zM + sg * (b * dlo), v3 = zM + sg * (b * dhi);
+            const float m = 0.05f + 1e-4f * (absf(zM) + cmag * dhi);
+            if ((v0 == v0) && (v1 == v1) && (v2 == v2) && (v3 == v3) && (m == m)) {
+                l = fmin_nan_lo(fmin_nan_lo(v0, v1), fmin_nan_lo(v2, v3)) - m;
+                u = fmax_nan_hi(fmax_nan_hi(v0, v1), fmax_nan_hi(v2, v3)) + m;
+                if (!(l == l)) l = -inf;
+                if (!(u == u)) u = inf;
+            }
+        }
+        // |deltaZ| < cotThetaMax * deltaR and |deltaZ| < deltaZMax
+        const float m2 = 0.05f + 1e-4f * absf(zM);
+        float w = c.cotThetaMax * dhi;
+        w = fmin_nan_lo(w, c.deltaZMax);
+        w = w + m2 + 1e-4f * absf(w);
+        if (w == w) {
+            l = fmax_nan_hi(l, zM - w);
+            u = fmin_nan_lo(u, zM + w);
+        }
+        if (l > u) continue;
+        any = true;
+        L = fmin_nan_lo(L, l);
+        U = fmax_nan_hi(U, u);
+    }
+    return any;
+}
+
 // lin_circle (core/include/traccc/seeding/detail/lin_circle.hpp)
 struct LinCircle {
     float Zo, cotTheta, iDeltaR, Er, U, V;

@@ -229,6 +229,13 @@ class triplet_seeding_algorithm:
                "mid_counts": arr(L.mid_counts, np.uint32, 2 * n).reshape(2, n)[:, :nv],
                "mid_offsets": arr(L.mid_offsets, np.uint32, 2 * n).reshape(2, n)[:, :nv]}
         md = int(L.max_doublets)
+        # reference candidate order of a middle: neighbour phi bins in walk order (starting at
+        # phi_bin - scope[0], wrapping), then grid order — the canon_key of k_doublets
+        n_phi = self.axes()[0][0]
+        scope0 = int(self.finder_config.neighbor_scope[0])
+        bin_of_pos = np.searchsorted(bin_offsets, np.arange(nv), side="right") - 1
+        phi_of_pos = bin_of_pos % n_phi
+        mb_canon_rank = None
         rec = np.dtype([("cotTheta", "<f4"), ("iDeltaR", "<f4"), ("Er", "<f4"), ("U", "<f4"),
                         ("V", "<f4"), ("Zo", "<f4"), ("r", "<f4"), ("pos", "<u4")])
         for d, name in ((0, "bottom"), (1, "top")):
@@ -240,6 +247,18 @@ class triplet_seeding_algorithm:
             idx = np.concatenate([np.arange(o, o + c) for o, c in zip(off, cnt) if c]) if used else np.zeros(0, np.int64)
             lst = a[idx].copy()
             mid = np.repeat(np.arange(nv), cnt)
+            if d == 0 and len(lst):
+                # mid-bottom lists are stored in order of discovery: sort by canon_key
+                pos = lst["pos"].astype(np.int64)
+                walk = (phi_of_pos[pos] - (phi_of_pos[mid] - scope0)) % n_phi
+                order = np.lexsort((pos, walk, mid))
+                assert np.array_equal(mid[order], mid)
+                # canonical index of every stored record inside its middle's list
+                start = np.concatenate([[0], np.cumsum(cnt)])[:-1]
+                mb_canon_rank = np.empty(len(lst), np.int64)
+                mb_canon_rank[order] = np.arange(len(lst)) - np.repeat(start, cnt)
+                mb_first = start
+                lst = lst[order]
             if d == 1 and len(lst):
                 # mid-top lists are stored sorted by cotTheta; the "Zo" slot carries the
                 # canonical index -> restore the reference's order inside each middle
@@ -259,6 +278,9 @@ class triplet_seeding_algorithm:
                              ("z_vertex", "<f4")])
             t = np.frombuffer(ws, dtype=trec, count=min(ndump, int(L.max_triplet_dump)),
                               offset=L.triplet_dump).copy()
+            if len(t) and mb_canon_rank is not None:
+                # mb_idx is the index in the stored (discovery-order) list -> canonical index
+                t["mb_idx"] = mb_canon_rank[mb_first[t["pos_m"]] + t["mb_idx"]]
             order = np.lexsort((t["mt_idx"], t["mb_idx"], t["pos_m"]))
             res["triplets"] = t[order]
         return res
