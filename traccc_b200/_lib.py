@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200seed.so")
+# B200SEED_LIB selects another build of the same library (kernel A/B experiments, tools/kbench.py)
+LIB_PATH = os.environ.get("B200SEED_LIB") or os.path.join(_HERE, "libb200seed.so")
 
 
 class seedfinder_config(C.Structure):

@@ -18,15 +18,22 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-shared", "-cudart", "static"]
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and os.path.exists(OUT) and all(
-            os.path.getmtime(OUT) >= os.path.getmtime(d) for d in DEPS):
-        return OUT
+def build(force: bool = False, verbose: bool = False, out: str = OUT, defines=()) -> str:
+    """out / defines: experiment builds (e.g. out=build/variant.so, defines=["B200_X=1"])."""
+    if not force and os.path.exists(out) and all(
+            os.path.getmtime(out) >= os.path.getmtime(d) for d in DEPS):
+        return out
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = ([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) +
+           [f"-D{d}" for d in defines] + ["-o", out, SRC])
     subprocess.check_call(cmd)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force=True, verbose=True))
+    import sys
+    if len(sys.argv) > 1:   # python build.py out.so DEFINE[=v] ...
+        print(build(force=True, verbose=True, out=os.path.abspath(sys.argv[1]), defines=sys.argv[2:]))
+    else:
+        print(build(force=True, verbose=True))

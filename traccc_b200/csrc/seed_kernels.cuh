@@ -310,8 +310,15 @@ __device__ __forceinline__ uint32_t owner_lane(uint32_t incl, uint32_t p) {
 // axis.hpp:336-362), z bins inner (regular zone, axis.hpp:162-173), as in
 // doublet_finding.hpp:67-80. Neighbour q (0 <= q < nq) is bin(q); q / nz is the position of
 // its phi bin in the walk.
+// a / b for small operands (a < 2^21) with a precomputed 1.0f / b: exact, because
+// (a + 0.5) / b is at least 0.5 / b away from the next integer.
+__device__ __forceinline__ uint32_t div_small(uint32_t a, float inv_b) {
+    return uint32_t((float(a) + 0.5f) * inv_b);
+}
+
 struct NeighbourWalk {
     uint32_t r0, n_phi_seq, z0, nz, nq;
+    float inv_nz;
     __device__ __forceinline__ void init(const DevCfg& cfg, uint32_t bin, float zM) {
         const uint32_t phi_bin = bin % cfg.nPhi;
         r0 = circular_remap(cfg.nPhi, phi_bin, -int(cfg.scope0));
@@ -324,10 +331,13 @@ struct NeighbourWalk {
         const uint32_t z1 = (ibinmax < int(cfg.nZ)) ? uint32_t(ibinmax) : cfg.nZ - 1u;
         nz = (z1 + 1u > z0) ? (z1 + 1u - z0) : 0u;
         nq = n_phi_seq * nz;
+        inv_nz = 1.f / float(nz ? nz : 1u);
     }
-    __device__ __forceinline__ uint32_t zbin(uint32_t q) const { return z0 + q % nz; }
+    // position of neighbour q's phi bin in the walk
+    __device__ __forceinline__ uint32_t wphi(uint32_t q) const { return div_small(q, inv_nz); }
+    __device__ __forceinline__ uint32_t zbin(uint32_t q) const { return z0 + (q - wphi(q) * nz); }
     __device__ __forceinline__ uint32_t bin(const DevCfg& cfg, uint32_t q) const {
-        uint32_t pb = r0 + q / nz;
+        uint32_t pb = r0 + wphi(q);
         if (pb > cfg.nPhi - 1u) pb -= cfg.nPhi;
         return pb + zbin(q) * cfg.nPhi;
     }
@@ -339,19 +349,17 @@ __device__ __forceinline__ uint32_t canon_key(uint32_t walk_phi, uint32_t n_vali
     return walk_phi * n_valid + pos;
 }
 
-// Ranks of element k of the staged mid-top list: `kc` = position in the reference's order
-// (keys are unique), `ks` = position in the (cotTheta, reference order) sort.
+// Position of element (ck, kk) of a mid-top list in the (cotTheta, reference order) sort;
+// the keys are unique.
 template <typename LoadCot, typename LoadKey>
-__device__ __forceinline__ void top_ranks(LoadCot cot, LoadKey key, uint32_t n, float ck, uint32_t kk,
-                                          uint32_t& kc, uint32_t& ks) {
-    kc = 0;
-    ks = 0;
+__device__ __forceinline__ uint32_t top_rank(LoadCot cot, LoadKey key, uint32_t n, float ck,
+                                             uint32_t kk) {
+    uint32_t ks = 0;
     for (uint32_t j = 0; j < n; ++j) {
         const float cj = cot(j);
-        const uint32_t kj = key(j);
-        kc += (kj < kk) ? 1u : 0u;
-        ks += ((cj < ck) || (cj == ck && kj < kk)) ? 1u : 0u;
+        ks += ((cj < ck) || (cj == ck && key(j) < kk)) ? 1u : 0u;
     }
+    return ks;
 }
 
 // Shared memory per warp of k_doublets (32-bit words).
@@ -364,10 +372,13 @@ __host__ __device__ inline uint32_t doublet_smem_words(uint32_t cap_b, uint32_t 
 // k_triplets can binary-search the scattering window of each mid-bottom doublet, and carry
 // their index in the reference's order:
 //   bottom: a = {cotTheta, iDeltaR, Er, U}  b = {V, Zo,               r_other, pos_other}
-//   top   : a = {cotTheta, iDeltaR, Er, U}  b = {V, bits(canonical k), r_other, pos_other}
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+//   top   : a = {cotTheta, iDeltaR, Er, U}  b = {V, bits(canon_key),  r_other, pos_other}
+#ifndef B200_DOUBLET_MIN_CTAS
+#define B200_DOUBLET_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, B200_DOUBLET_MIN_CTAS)
 k_doublets(const DevCfg cfg, const DoubletArgs a) {
-    extern __shared__ uint32_t s_mem[];
+    extern __shared__ __align__(16) uint32_t s_mem[];
     __shared__ unsigned long long s_pairs[2];
     __shared__ uint32_t s_acc[3];  // active, nb, nt
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -404,8 +415,14 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
         const float er = 1e-2f + 1e-5f * (M.w + absf(cfg.deltaRMax));
         const uint32_t row_lo = cell_row(g, M.w - cfg.deltaRMax - er);
         const uint32_t row_hi = cell_row(g, M.w + cfg.deltaRMax + er);
-        const uint32_t nrows = row_hi - row_lo + 1u;
+        const uint32_t nrows = row_hi - row_lo + 1u;  // <= NR <= 32
         const uint32_t ncombo = walk.nq * nrows;
+        const float inv_nrows = 1.f / float(nrows);
+        // z window of every row (lane = row); the same for all neighbour bins
+        float winL = 0.f, winU = 0.f;
+        bool win_ok = false;
+        if (lane < nrows) win_ok = cell_row_window(cfg, g, M.w, M.z, row_lo + lane, winL, winU);
+        const uint32_t win_mask = __ballot_sync(0xffffffffu, win_ok);
 
         uint32_t nB = 0, nT = 0;
         uint32_t offB = 0, offT = 0;
@@ -418,16 +435,16 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
                 // lane j: one (neighbour bin, row) -> contiguous run of cells
                 const uint32_t j = j0 + lane;
                 uint32_t lo = 0, len = 0, wphi = 0;
-                if (j < ncombo) {
-                    const uint32_t q = j / nrows, row = row_lo + j % nrows;
-                    float L, U;
-                    if (cell_row_window(cfg, g, M.w, M.z, row, L, U)) {
-                        const uint32_t zb = walk.zbin(q);
-                        const uint32_t base = walk.bin(cfg, q) * g.CPB + row * g.NZc;
-                        lo = __ldg(a.cell_off + base + cell_z(g, zb, L));
-                        len = __ldg(a.cell_off + base + cell_z(g, zb, U) + 1u) - lo;
-                        wphi = q / walk.nz;
-                    }
+                const uint32_t jj = (j < ncombo) ? j : 0u;
+                const uint32_t q = div_small(jj, inv_nrows), ri = jj - q * nrows;
+                const float L = __shfl_sync(0xffffffffu, winL, ri);
+                const float U = __shfl_sync(0xffffffffu, winU, ri);
+                if (j < ncombo && ((win_mask >> ri) & 1u)) {
+                    const uint32_t zb = walk.zbin(q);
+                    const uint32_t base = walk.bin(cfg, q) * g.CPB + (row_lo + ri) * g.NZc;
+                    lo = __ldg(a.cell_off + base + cell_z(g, zb, L));
+                    len = __ldg(a.cell_off + base + cell_z(g, zb, U) + 1u) - lo;
+                    wphi = walk.wphi(q);
                 }
                 const uint32_t incl = warp_incl_scan(len, lane);
                 const uint32_t excl = incl - len;
@@ -486,12 +503,11 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
                 DoubletRec* dst = a.arena_t + offT;
                 __syncwarp();
                 for (uint32_t k = lane; k < nT; k += 32) {
-                    DoubletRec r = src[k];
-                    uint32_t kc, ks;
-                    top_ranks([&](uint32_t j) { return src[j].a.x; },
-                              [&](uint32_t j) { return __float_as_uint(src[j].b.y); }, nT, r.a.x,
-                              __float_as_uint(r.b.y), kc, ks);
-                    r.b.y = __uint_as_float(kc);
+                    const DoubletRec r = src[k];
+                    const uint32_t ks =
+                        top_rank([&](uint32_t j) { return src[j].a.x; },
+                                 [&](uint32_t j) { return __float_as_uint(src[j].b.y); }, nT, r.a.x,
+                                 __float_as_uint(r.b.y));
                     dst[ks] = r;
                 }
                 break;
@@ -546,6 +562,44 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
                     key_s[k] = canon_key(key_s[k], n_valid, pos);
                 }
             }
+            // pad to a multiple of four for the vectorised rank loop
+            if (lane < 4u && nT + lane < a.cap_t) cot_s[nT + lane] = __uint_as_float(0x7f800000u);
+            __syncwarp();
+            // sorted position of every mid-top = number of smaller cotTheta values; equal values
+            // (which would share a position) are detected through the sum of the positions and
+            // resolved by the reference order. stage_b is free again: it holds the positions.
+            uint32_t* rank_s = stage_b;
+            uint32_t rank_sum = 0;
+            const uint32_t n4 = (nT + 3u) & ~3u;
+            const bool vec_ok = n4 <= a.cap_t;
+            for (uint32_t k0 = 0; k0 < nT; k0 += 32) {
+                const uint32_t k = k0 + lane;
+                if (k < nT) {
+                    const float ck = cot_s[k];
+                    uint32_t lt = 0;
+                    if (vec_ok) {
+                        const float4* c4 = reinterpret_cast<const float4*>(cot_s);
+                        for (uint32_t j = 0; j < n4 / 4u; ++j) {
+                            const float4 v = c4[j];
+                            lt += (v.x < ck) ? 1u : 0u;
+                            lt += (v.y < ck) ? 1u : 0u;
+                            lt += (v.z < ck) ? 1u : 0u;
+                            lt += (v.w < ck) ? 1u : 0u;
+                        }
+                    } else {
+                        for (uint32_t j = 0; j < nT; ++j) lt += (cot_s[j] < ck) ? 1u : 0u;
+                    }
+                    rank_s[k] = lt;
+                    rank_sum += lt;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) rank_sum += __shfl_xor_sync(0xffffffffu, rank_sum, o);
+            if (rank_sum != (nT * (nT - 1u)) / 2u) {  // equal cotTheta values (or NaN): full order
+                for (uint32_t k = lane; k < nT; k += 32)
+                    rank_s[k] = top_rank([&](uint32_t j) { return cot_s[j]; },
+                                         [&](uint32_t j) { return key_s[j]; }, nT, cot_s[k], key_s[k]);
+            }
             __syncwarp();
             for (uint32_t k0 = 0; k0 < nT; k0 += 32) {
                 const uint32_t k = k0 + lane;
@@ -556,12 +610,10 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
                     const float2 V = __ldg(a.var2 + pos);
                     const LinCircle l = transform_coordinates(false, M.x, M.y, M.z, M.w, VM.x, VM.y,
                                                               P.x, P.y, P.z, V.x, V.y);
-                    uint32_t kc, ks;
-                    top_ranks([&](uint32_t j) { return cot_s[j]; },
-                              [&](uint32_t j) { return key_s[j]; }, nT, cot_s[k], key_s[k], kc, ks);
+                    const uint32_t ks = rank_s[k];
                     DoubletRec r;
                     r.a = make_float4(cot_s[k], l.iDeltaR, l.Er, l.U);
-                    r.b = make_float4(l.V, __uint_as_float(kc), P.w, __uint_as_float(pos));
+                    r.b = make_float4(l.V, __uint_as_float(key_s[k]), P.w, __uint_as_float(pos));
                     a.arena_t[offT + ks] = r;
                 }
             }
@@ -632,13 +684,22 @@ struct __align__(16) BlockTriplet {
     float rT;         // radius of the top spacepoint, later the sorter sum
 };
 
+constexpr uint32_t TCOT_CAP = 256;  // cotTheta of the first mid-tops of a middle kept in smem
+
+// cotTheta of mid-top t: shared-memory copy for the first TCOT_CAP, the arena otherwise
+struct TopCot {
+    const float* sm;
+    const DoubletRec* LT;
+    __device__ __forceinline__ float operator()(uint32_t t) const {
+        return (t < TCOT_CAP) ? sm[t] : __ldg(&LT[t].a.x);
+    }
+};
 // first t in [0, n) with cot(t) >= v  (mid-top records are sorted by cotTheta)
-__device__ __forceinline__ uint32_t cot_lower_bound(const DoubletRec* __restrict__ LT, uint32_t n,
-                                                    float v) {
+__device__ __forceinline__ uint32_t cot_lower_bound(const TopCot& cot, uint32_t n, float v) {
     uint32_t lo = 0, hi = n;
     while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(&LT[mid].a.x) < v)
+        if (cot(mid) < v)
             lo = mid + 1;
         else
             hi = mid;
@@ -646,12 +707,11 @@ __device__ __forceinline__ uint32_t cot_lower_bound(const DoubletRec* __restrict
     return lo;
 }
 // first t in [0, n) with cot(t) > v
-__device__ __forceinline__ uint32_t cot_upper_bound(const DoubletRec* __restrict__ LT, uint32_t n,
-                                                    float v) {
+__device__ __forceinline__ uint32_t cot_upper_bound(const TopCot& cot, uint32_t n, float v) {
     uint32_t lo = 0, hi = n;
     while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(&LT[mid].a.x) <= v)
+        if (cot(mid) <= v)
             lo = mid + 1;
         else
             hi = mid;
@@ -672,7 +732,7 @@ __device__ __forceinline__ float warp_min(float v) {
 
 // Per-warp shared memory of k_triplets.
 __host__ __device__ inline size_t triplet_smem_per_warp(uint32_t list_cap) {
-    return size_t(list_cap) * (16 + 4 + 4) + MAX_TOPK * 5 * 4;
+    return size_t(list_cap) * (16 + 4 + 4) + MAX_TOPK * 5 * 4 + TCOT_CAP * 4;
 }
 
 // Warp per middle spacepoint (atomic ticket queue). For every block of 32 mid-bottom doublets
@@ -698,6 +758,7 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
     float* top_rb = top_s + MAX_TOPK;
     uint32_t* top_b = reinterpret_cast<uint32_t*>(top_rb + MAX_TOPK);
     uint32_t* top_t = top_b + MAX_TOPK;
+    float* cot_sm = reinterpret_cast<float*>(top_t + MAX_TOPK);
     if (threadIdx.x == 0) {
         s_ntrip = 0;
         s_tests = 0ull;
@@ -738,6 +799,7 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
         float maxEr = 0.f, minEr = 0.f, maxIDR = 0.f, maxAbsCot = 0.f;
         for (uint32_t t = lane; t < nt; t += 32) {
             const float4 ta = __ldg(&LT[t].a);
+            if (t < TCOT_CAP) cot_sm[t] = ta.x;
             maxEr = fmaxf(maxEr, ta.z);
             minEr = fminf(minEr, ta.z);
             maxIDR = fmaxf(maxIDR, ta.y);
@@ -747,6 +809,8 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
         minEr = warp_min(minEr);
         maxIDR = warp_max(maxIDR);
         maxAbsCot = warp_max(maxAbsCot);
+        __syncwarp();
+        const TopCot top_cot{cot_sm, LT};
         // with negative or non-finite error terms the reference's sqrt() yields NaN and the
         // cut passes everything: no pruning then
         const bool sane = (varRM >= 0.f) && (varZM >= 0.f) && (minEr >= 0.f) && (maxEr < 1e30f) &&
@@ -773,8 +837,8 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
                 const float W = 1.004f * sqrt_rn(e2max) + 1.002f * sqrt_rn(sir2) +
                                 4e-6f * (absf(la.x) + maxAbsCot) + 1e-30f;
                 const bool prune = sane && (la.z >= 0.f) && (W < 1e30f) && (sir2 >= 0.f);
-                lo = prune ? cot_lower_bound(LT, nt, la.x - W) : 0u;
-                hi = prune ? cot_upper_bound(LT, nt, la.x + W) : nt;
+                lo = prune ? cot_lower_bound(top_cot, nt, la.x - W) : 0u;
+                hi = prune ? cot_upper_bound(top_cot, nt, la.x + W) : nt;
                 if (hi < lo) hi = lo;
             }
             const uint32_t wdt = hi - lo;
