@@ -620,8 +620,8 @@ int b200seed_run(b200seed_handle* h, void* stream, uint32_t n_sp, const float* d
     uint32_t* cell_off = reinterpret_cast<uint32_t*>(at(L.cell_off));
     float4* csp4 = reinterpret_cast<float4*>(at(L.csp4));
     uint32_t* ccanon = reinterpret_cast<uint32_t*>(at(L.ccanon));
-    // canon_key (seed_kernels.cuh) shares a 32-bit word with a 5-bit row index in k_triplets
-    if (uint64_t(h->dev.scope0 + h->dev.scope1 + 1u) * n_sp > (1ull << 27))
+    // canon_key (seed_kernels.cuh) is a 32-bit word
+    if (uint64_t(h->dev.scope0 + h->dev.scope1 + 1u) * n_sp > 0xFFFFFFFFull)
         return fail(h, B200SEED_EINVAL, "b200seed_run: too many spacepoints for this neighbor_scope");
 
     CUDA_TRY(h, cudaMemsetAsync(ws, 0, L.zero_bytes, s));

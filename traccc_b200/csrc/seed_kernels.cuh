@@ -678,7 +678,7 @@ struct TripletArgs {
 
 // One triplet of the current row block (shared memory, 16 bytes).
 struct __align__(16) BlockTriplet {
-    uint32_t key;     // (row in block) << 27 | canonical mid-top index
+    uint32_t key;     // canon_key of the top spacepoint, later the position of the bottom one
     float curvature;  // later: radius of the bottom spacepoint
     float weight;     // -impact * impactWeightFactor, later the final weight
     float rT;         // radius of the top spacepoint, later the sorter sum
@@ -706,9 +706,18 @@ __device__ __forceinline__ uint32_t cot_lower_bound(const TopCot& cot, uint32_t 
     }
     return lo;
 }
-// first t in [0, n) with cot(t) > v
-__device__ __forceinline__ uint32_t cot_upper_bound(const TopCot& cot, uint32_t n, float v) {
-    uint32_t lo = 0, hi = n;
+// first t in [from, n) with cot(t) > v; gallops from `from` (the windows are short)
+__device__ __forceinline__ uint32_t cot_upper_bound(const TopCot& cot, uint32_t from, uint32_t n,
+                                                    float v) {
+    uint32_t lo = from, hi = n, step = 2;
+    while (lo + step < n) {
+        if (cot(lo + step) > v) {
+            hi = lo + step;
+            break;
+        }
+        lo += step + 1;
+        step <<= 1;
+    }
     while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
         if (cot(mid) <= v)
@@ -732,7 +741,8 @@ __device__ __forceinline__ float warp_min(float v) {
 
 // Per-warp shared memory of k_triplets.
 __host__ __device__ inline size_t triplet_smem_per_warp(uint32_t list_cap) {
-    return size_t(list_cap) * (16 + 4 + 4) + MAX_TOPK * 5 * 4 + TCOT_CAP * 4;
+    // list (16) + pos of top (4) + mid-bottom index (4) + order (2) + bonus / rank (1) per entry
+    return size_t(list_cap) * (16 + 4 + 4 + 2 + 1) + MAX_TOPK * 5 * 4 + TCOT_CAP * 4;
 }
 
 // Warp per middle spacepoint (atomic ticket queue). For every block of 32 mid-bottom doublets
@@ -742,7 +752,10 @@ __host__ __device__ inline size_t triplet_smem_per_warp(uint32_t list_cap) {
 // evaluated 32 at a time at full lane occupancy with the exact reference arithmetic.
 // The window is conservative (see the margin below), so the accepted set is identical to
 // testing all nMidBot x nMidTop combinations.
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+#ifndef B200_TRIPLET_MIN_CTAS
+#define B200_TRIPLET_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, B200_TRIPLET_MIN_CTAS)
 k_triplets(const DevCfg cfg, const TripletArgs a) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ uint32_t s_ntrip;
@@ -752,13 +765,15 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
     unsigned char* base = s_raw + triplet_smem_per_warp(a.list_cap) * warp;
     BlockTriplet* list = reinterpret_cast<BlockTriplet*>(base);
     uint32_t* lpos = reinterpret_cast<uint32_t*>(base + size_t(a.list_cap) * 16);  // pos of top
-    uint32_t* bonus = lpos + a.list_cap;  // compatible seeds found per triplet
-    float* top_w = reinterpret_cast<float*>(bonus + a.list_cap);
+    uint32_t* lrow = lpos + a.list_cap;  // index of the mid-bottom doublet
+    float* top_w = reinterpret_cast<float*>(lrow + a.list_cap);
     float* top_s = top_w + MAX_TOPK;
     float* top_rb = top_s + MAX_TOPK;
     uint32_t* top_b = reinterpret_cast<uint32_t*>(top_rb + MAX_TOPK);
     uint32_t* top_t = top_b + MAX_TOPK;
     float* cot_sm = reinterpret_cast<float*>(top_t + MAX_TOPK);
+    uint16_t* ord = reinterpret_cast<uint16_t*>(cot_sm + TCOT_CAP);  // list order inside a row
+    uint8_t* aux = reinterpret_cast<uint8_t*>(ord + a.list_cap);     // bonus count, later rank
     if (threadIdx.x == 0) {
         s_ntrip = 0;
         s_tests = 0ull;
@@ -816,53 +831,213 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
         const bool sane = (varRM >= 0.f) && (varZM >= 0.f) && (minEr >= 0.f) && (maxEr < 1e30f) &&
                           (maxIDR < 1e30f) && (maxAbsCot < 1e30f);
 
-        uint32_t ntop = 0;  // entries in the per-middle top-K (warp-uniform)
+        uint32_t ntop = 0;   // entries in the per-middle top-K (warp-uniform)
+        uint32_t nlist = 0;  // triplets waiting in the shared-memory list (complete rows)
         uint32_t row0 = 0;
-        uint32_t rows = 32;  // rows of the current block (shrinks only on list overflow)
-        while (row0 < nb) {
-            const uint32_t nrows = (nb - row0 < rows) ? (nb - row0) : rows;
+        uint32_t rows = 32;  // rows of the next block (shrinks only on list overflow)
+        while (true) {
+            // ---- windows of the next block of mid-bottom doublets (one row per lane) ----
+            const bool have_block = row0 < nb;
+            const uint32_t nrows = have_block ? ((nb - row0 < rows) ? (nb - row0) : rows) : 0u;
             const bool has_row = lane < nrows;
-            float4 la = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (has_row) la = __ldg(&LB[row0 + lane].a);
-            float iSinTheta2, sir2;
-            triplet_row_constants(cfg, la.x, iSinTheta2, sir2);
-            // Window half-width. The cut rejects iff d2 - e2 > 0 and (|d| - e)^2 > sir2
-            // (d = cot_b - cot_t, e^2 = error2 <= e2max), i.e. surely when
-            // |d| > e + sqrt(sir2); the factors absorb float rounding including the
-            // cancellation in d2 + e2 - 2|d|e (relative error <= 1e-6 (d^2 + e^2)).
             uint32_t lo = 0, hi = 0;
             if (has_row) {
+                const float4 la = __ldg(&LB[row0 + lane].a);
+                float iSinTheta2, sir2;
+                triplet_row_constants(cfg, la.x, iSinTheta2, sir2);
+                // Window half-width. The cut rejects iff d2 - e2 > 0 and (|d| - e)^2 > sir2
+                // (d = cot_b - cot_t, e^2 = error2 <= e2max), i.e. surely when
+                // |d| > e + sqrt(sir2); the factors absorb float rounding including the
+                // cancellation in d2 + e2 - 2|d|e (relative error <= 1e-6 (d^2 + e^2)).
                 const float e2max = la.z + maxEr +
                                     2.f * (absf(la.x) * maxAbsCot * varRM + varZM) * la.y * maxIDR;
                 const float W = 1.004f * sqrt_rn(e2max) + 1.002f * sqrt_rn(sir2) +
                                 4e-6f * (absf(la.x) + maxAbsCot) + 1e-30f;
                 const bool prune = sane && (la.z >= 0.f) && (W < 1e30f) && (sir2 >= 0.f);
                 lo = prune ? cot_lower_bound(top_cot, nt, la.x - W) : 0u;
-                hi = prune ? cot_upper_bound(top_cot, nt, la.x + W) : nt;
+                hi = prune ? cot_upper_bound(top_cot, lo, nt, la.x + W) : nt;
                 if (hi < lo) hi = lo;
             }
             const uint32_t wdt = hi - lo;
-            uint32_t incl = wdt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= uint32_t(o)) incl += v;
-            }
+            const uint32_t incl = warp_incl_scan(wdt, lane);
             const uint32_t excl = incl - wdt;
             const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
 
-            uint32_t nlist = 0;
+            // ---- flush the list when the middle is finished or the next block may not fit ----
+            if (nlist != 0 && (!have_block || nlist + total > a.list_cap)) {
+                __syncwarp();
+                // (1) reference order inside every row: ord[first of row + rank by canon_key]
+                for (uint32_t i0 = 0; i0 < nlist; i0 += 32) {
+                    const uint32_t i = i0 + lane;
+                    if (i < nlist) {
+                        const uint32_t row = lrow[i], key = list[i].key;
+                        uint32_t sgm = i, rank = 0;
+                        while (sgm > 0 && lrow[sgm - 1] == row) {
+                            --sgm;
+                            rank += (list[sgm].key < key) ? 1u : 0u;
+                        }
+                        for (uint32_t j = i + 1; j < nlist && lrow[j] == row; ++j)
+                            rank += (list[j].key < key) ? 1u : 0u;
+                        ord[sgm + rank] = uint16_t(i);
+                    }
+                }
+                __syncwarp();
+                // (2) compatible-seed bonus (triplet_finding.hpp:107-179), lane per triplet:
+                //     the other triplets of the same mid-bottom doublet in the reference order
+                for (uint32_t i0 = 0; i0 < nlist; i0 += 32) {
+                    const uint32_t i = i0 + lane;
+                    if (i < nlist) {
+                        const BlockTriplet cur = list[i];
+                        const uint32_t row = lrow[i];
+                        uint32_t sgm = i, egm = i + 1;
+                        while (sgm > 0 && lrow[sgm - 1] == row) --sgm;
+                        while (egm < nlist && lrow[egm] == row) ++egm;
+                        const float lower = cur.curvature - cfg.deltaInvHelixDiameter;
+                        const float upper = cur.curvature + cfg.deltaInvHelixDiameter;
+                        float compat[MAX_COMPAT];
+                        uint32_t ncompat = 0;
+                        for (uint32_t q = sgm; q < egm; ++q) {
+                            const uint32_t j = ord[q];
+                            if (j == i) continue;
+                            const BlockTriplet o = list[j];
+                            const float deltaR = cur.rT - o.rT;
+                            if (absf(deltaR) < cfg.filterDeltaRMin) continue;
+                            if (o.curvature < lower) continue;
+                            if (o.curvature > upper) continue;
+                            bool newCompSeed = true;
+#pragma unroll
+                            for (uint32_t c = 0; c < MAX_COMPAT; ++c) {
+                                if (c < ncompat && absf(compat[c] - o.rT) < cfg.filterDeltaRMin)
+                                    newCompSeed = false;
+                            }
+                            if (newCompSeed) {
+#pragma unroll
+                                for (uint32_t c = 0; c < MAX_COMPAT; ++c)
+                                    if (c == ncompat) compat[c] = o.rT;
+                                ++ncompat;
+                            }
+                            if (ncompat >= cfg.compatSeedLimit) break;
+                        }
+                        aux[i] = uint8_t(ncompat);
+                    }
+                }
+                __syncwarp();
+                // (3) final weight, single-seed cut, sorter sum; optional dump
+                for (uint32_t i0 = 0; i0 < nlist; i0 += 32) {
+                    const uint32_t i = i0 + lane;
+                    if (i < nlist) {
+                        BlockTriplet cur = list[i];
+                        const uint32_t row = lrow[i];
+                        // the reference adds compatSeedWeight one at a time (:171)
+                        float w = cur.weight;
+                        for (uint32_t q = aux[i]; q > 0; --q) w += cfg.compatSeedWeight;
+                        const float4 bb = __ldg(&LB[row].b);
+                        const uint32_t pos_b = __float_as_uint(bb.w), pos_t = lpos[i];
+                        if (a.dump) {
+                            const uint32_t d = atomicAdd(&a.ctrl->dump_cursor, 1u);
+                            if (d < a.max_dump) {
+                                TripletDumpRec r;
+                                r.pos_b = pos_b, r.pos_m = m, r.pos_t = pos_t, r.mb_idx = row;
+                                r.mt_idx = cur.key, r.curvature = cur.curvature, r.weight = w;
+                                r.z_vertex = bb.y;
+                                a.dump[d] = r;
+                            } else {
+                                atomicOr(&a.ctrl->overflow, B200SEED_OVF_DUMP);
+                            }
+                        }
+                        const float rB = bb.z, rT = cur.rT;
+                        w += seed_weight_increase(cfg, rB, rT);
+                        const bool keep = single_seed_cut(cfg, rB, w);
+                        const float4 PB = __ldg(a.sp4 + pos_b);
+                        const float4 PT = __ldg(a.sp4 + pos_t);
+                        cur.weight = w;
+                        cur.rT = sorter_sum(PB.y, PB.z, PT.y, PT.z);
+                        cur.curvature = rB;
+                        cur.key = keep ? pos_b : 0xFFFFFFFFu;  // pos_b < 2^32 - 1 always
+                        list[i] = cur;
+                    }
+                }
+                __syncwarp();
+                // (4) merge into the per-middle top-K: every kept triplet computes its position
+                //     in the union of the list and the current top-K under triplet_sorter's
+                //     order (full ties: the reference's order of discovery)
+                auto before = [&](float w1, float s1, uint32_t b1, uint32_t t1, float w2, float s2,
+                                  uint32_t b2, uint32_t t2) -> bool {
+                    if (w1 != w2 || s1 != s2) return seed_before(w1, s1, w2, s2);
+                    const unsigned long long k1 = tie_key(b1), k2 = tie_key(b2);
+                    return (k1 != k2) ? (k1 < k2) : (tie_key(t1) < tie_key(t2));
+                };
+                uint32_t nkept = 0;
+                for (uint32_t i0 = 0; i0 < nlist; i0 += 32) {
+                    const uint32_t i = i0 + lane;
+                    uint32_t rank = 0xFFu;
+                    if (i < nlist) {
+                        const BlockTriplet c = list[i];
+                        const uint32_t ct = lpos[i];
+                        bool in = (c.key != 0xFFFFFFFFu);
+                        if (in && ntop == K)  // cannot displace anything: skip the ranking
+                            in = before(c.weight, c.rT, c.key, ct, top_w[K - 1], top_s[K - 1],
+                                        top_b[K - 1], top_t[K - 1]);
+                        if (in) {
+                            rank = 0;
+                            for (uint32_t q = 0; q < ntop; ++q)
+                                rank += before(top_w[q], top_s[q], top_b[q], top_t[q], c.weight, c.rT,
+                                               c.key, ct) ? 1u : 0u;
+                            for (uint32_t j = 0; j < nlist && rank < K; ++j) {
+                                const BlockTriplet o = list[j];
+                                if (j != i && o.key != 0xFFFFFFFFu &&
+                                    before(o.weight, o.rT, o.key, lpos[j], c.weight, c.rT, c.key, ct))
+                                    ++rank;
+                            }
+                            if (rank >= K) rank = 0xFFu;
+                        }
+                        aux[i] = uint8_t(rank);
+                    }
+                    nkept += __popc(__ballot_sync(0xffffffffu, rank != 0xFFu));
+                }
+                __syncwarp();
+                if (nkept) {
+                    // current entries move down by the number of new entries sorted before them
+                    float ew = 0.f, es = 0.f, erb = 0.f;
+                    uint32_t eb = 0, et = 0, npos = 0xFFu;
+                    if (lane < ntop) {
+                        ew = top_w[lane], es = top_s[lane], erb = top_rb[lane];
+                        eb = top_b[lane], et = top_t[lane];
+                        npos = lane;
+                        for (uint32_t j = 0; j < nlist; ++j) {
+                            if (aux[j] == 0xFFu) continue;
+                            const BlockTriplet o = list[j];
+                            npos += before(o.weight, o.rT, o.key, lpos[j], ew, es, eb, et) ? 1u : 0u;
+                        }
+                    }
+                    __syncwarp();
+                    if (npos < K) {
+                        top_w[npos] = ew, top_s[npos] = es, top_rb[npos] = erb;
+                        top_b[npos] = eb, top_t[npos] = et;
+                    }
+                    for (uint32_t i0 = 0; i0 < nlist; i0 += 32) {
+                        const uint32_t i = i0 + lane;
+                        if (i < nlist && aux[i] != 0xFFu) {
+                            const BlockTriplet c = list[i];
+                            const uint32_t r = aux[i];
+                            top_w[r] = c.weight, top_s[r] = c.rT, top_rb[r] = c.curvature;
+                            top_b[r] = c.key, top_t[r] = lpos[i];
+                        }
+                    }
+                    ntop = (ntop + nkept < K) ? (ntop + nkept) : K;
+                }
+                __syncwarp();
+                acc_trip += nlist;
+                nlist = 0;
+            }
+            if (!have_block) break;
+
+            // ---- evaluate the (row, mid-top) pairs inside the windows, 32 at a time ----
+            const uint32_t base_n = nlist;
             for (uint32_t p0 = 0; p0 < total; p0 += 32) {
                 const uint32_t p = p0 + lane;
                 const bool valid = p < total;
-                // row of pair p: number of rows whose inclusive prefix is <= p
-                uint32_t r = 0;
-#pragma unroll
-                for (uint32_t step = 16; step >= 1; step >>= 1) {
-                    const uint32_t v = __shfl_sync(0xffffffffu, incl, (r + step - 1) & 31u);
-                    if (v <= p) r += step;
-                }
-                r &= 31u;
+                const uint32_t r = owner_lane(incl, p);
                 const uint32_t er = __shfl_sync(0xffffffffu, excl, r);
                 const uint32_t lor = __shfl_sync(0xffffffffu, lo, r);
                 bool ok = false;
@@ -883,7 +1058,7 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
                     triplet_row_constants(cfg, lb.cotTheta, is2, s2);
                     ok = triplet_is_compatible(cfg, rM, varRM, varZM, lb, lt, is2, s2, curvature,
                                                impact);
-                    key = (r << 27) | __float_as_uint(tb.y);
+                    key = __float_as_uint(tb.y);
                     rT = tb.z;
                     pos_t = __float_as_uint(tb.w);
                 }
@@ -897,13 +1072,15 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
                     e.rT = rT;
                     list[k] = e;
                     lpos[k] = pos_t;
+                    lrow[k] = row0 + r;
                 }
                 nlist += __popc(mk);
             }
             __syncwarp();
-            if (nlist > a.list_cap) {
+            if (nlist > a.list_cap) {  // only possible when the list was empty before the block
                 if (rows > 1) {
                     rows >>= 1;  // redo this block with fewer rows
+                    nlist = base_n;
                     continue;
                 }
                 // a single row with more triplets than the list holds: keep the first
@@ -911,135 +1088,6 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
                 if (lane == 0) atomicOr(&a.ctrl->overflow, B200SEED_OVF_TRIPLETS);
                 nlist = a.list_cap;
             }
-            acc_trip += nlist;
-
-            // ---- compatible-seed bonus (triplet_finding.hpp:107-179), lane per triplet. The
-            //      list is row-major; inside a row the partners are visited in ascending
-            //      canonical mid-top index, which is the reference's iteration order. ----
-            for (uint32_t i0 = 0; i0 < nlist; i0 += 32) {
-                const uint32_t i = i0 + lane;
-                if (i < nlist) {
-                    const BlockTriplet cur = list[i];
-                    const uint32_t row = cur.key >> 27;
-                    uint32_t sgm = i, egm = i + 1;
-                    while (sgm > 0 && (list[sgm - 1].key >> 27) == row) --sgm;
-                    while (egm < nlist && (list[egm].key >> 27) == row) ++egm;
-                    const float lower = cur.curvature - cfg.deltaInvHelixDiameter;
-                    const float upper = cur.curvature + cfg.deltaInvHelixDiameter;
-                    float compat[MAX_COMPAT];
-                    uint32_t ncompat = 0;
-                    uint32_t next_min = row << 27;
-                    while (true) {
-                        uint32_t best = 0xFFFFFFFFu, bj = 0;
-                        for (uint32_t j = sgm; j < egm; ++j) {
-                            const uint32_t kj = list[j].key;
-                            if (kj >= next_min && kj < best) {
-                                best = kj;
-                                bj = j;
-                            }
-                        }
-                        if (best == 0xFFFFFFFFu) break;
-                        next_min = best + 1u;
-                        if (bj == i) continue;
-                        const BlockTriplet o = list[bj];
-                        const float deltaR = cur.rT - o.rT;
-                        if (absf(deltaR) < cfg.filterDeltaRMin) continue;
-                        if (o.curvature < lower) continue;
-                        if (o.curvature > upper) continue;
-                        bool newCompSeed = true;
-#pragma unroll
-                        for (uint32_t q = 0; q < MAX_COMPAT; ++q) {
-                            if (q < ncompat && absf(compat[q] - o.rT) < cfg.filterDeltaRMin)
-                                newCompSeed = false;
-                        }
-                        if (newCompSeed) {
-#pragma unroll
-                            for (uint32_t q = 0; q < MAX_COMPAT; ++q)
-                                if (q == ncompat) compat[q] = o.rT;
-                            ++ncompat;
-                        }
-                        if (ncompat >= cfg.compatSeedLimit) break;
-                    }
-                    bonus[i] = ncompat;
-                }
-            }
-            __syncwarp();
-            // ---- final weight, single-seed cut, sorter sum; optional dump ----
-            for (uint32_t i0 = 0; i0 < nlist; i0 += 32) {
-                const uint32_t i = i0 + lane;
-                if (i < nlist) {
-                    BlockTriplet cur = list[i];
-                    const uint32_t row = cur.key >> 27, tt = cur.key & 0x07ffffffu;
-                    // the reference adds compatSeedWeight one at a time (:171)
-                    float w = cur.weight;
-                    for (uint32_t q = bonus[i]; q > 0; --q) w += cfg.compatSeedWeight;
-                    const float4 bb = __ldg(&LB[row0 + row].b);
-                    const uint32_t pos_b = __float_as_uint(bb.w), pos_t = lpos[i];
-                    if (a.dump) {
-                        const uint32_t d = atomicAdd(&a.ctrl->dump_cursor, 1u);
-                        if (d < a.max_dump) {
-                            TripletDumpRec r;
-                            r.pos_b = pos_b, r.pos_m = m, r.pos_t = pos_t, r.mb_idx = row0 + row;
-                            r.mt_idx = tt, r.curvature = cur.curvature, r.weight = w;
-                            r.z_vertex = bb.y;
-                            a.dump[d] = r;
-                        } else {
-                            atomicOr(&a.ctrl->overflow, B200SEED_OVF_DUMP);
-                        }
-                    }
-                    const float rB = bb.z, rT = cur.rT;
-                    w += seed_weight_increase(cfg, rB, rT);
-                    const bool keep = single_seed_cut(cfg, rB, w);
-                    const float4 PB = __ldg(a.sp4 + pos_b);
-                    const float4 PT = __ldg(a.sp4 + pos_t);
-                    cur.weight = w;
-                    cur.rT = sorter_sum(PB.y, PB.z, PT.y, PT.z);
-                    cur.curvature = rB;
-                    cur.key = keep ? pos_b : 0xFFFFFFFFu;  // pos_b < 2^32 - 1 always
-                    list[i] = cur;
-                }
-            }
-            __syncwarp();
-            // ---- merge into the per-middle top-K (triplet_sorter order, earlier first on
-            //      full ties); sequential on lane 0, the lists are short ----
-            if (lane == 0) {
-                for (uint32_t i = 0; i < nlist; ++i) {
-                    const BlockTriplet c = list[i];
-                    if (c.key == 0xFFFFFFFFu) continue;
-                    uint32_t p = ntop;
-                    while (p > 0) {
-                        const uint32_t q = p - 1;
-                        bool before;
-                        if (c.weight != top_w[q] || c.rT != top_s[q]) {
-                            before = seed_before(c.weight, c.rT, top_w[q], top_s[q]);
-                        } else {
-                            // full tie of triplet_sorter: the reference's order of discovery
-                            // (mid-bottom doublets outer, mid-top doublets inner) decides
-                            const unsigned long long cb = tie_key(c.key), eb = tie_key(top_b[q]);
-                            before = (cb != eb) ? (cb < eb) : (tie_key(lpos[i]) < tie_key(top_t[q]));
-                        }
-                        if (!before) break;
-                        --p;
-                    }
-                    if (p >= K) continue;
-                    const uint32_t last = (ntop < K) ? ntop : (K - 1);
-                    for (uint32_t q = last; q > p; --q) {
-                        top_w[q] = top_w[q - 1];
-                        top_s[q] = top_s[q - 1];
-                        top_rb[q] = top_rb[q - 1];
-                        top_b[q] = top_b[q - 1];
-                        top_t[q] = top_t[q - 1];
-                    }
-                    top_w[p] = c.weight;
-                    top_s[p] = c.rT;
-                    top_rb[p] = c.curvature;
-                    top_b[p] = c.key;
-                    top_t[p] = lpos[i];
-                    if (ntop < K) ++ntop;
-                }
-            }
-            ntop = __shfl_sync(0xffffffffu, ntop, 0);
-            __syncwarp();
             row0 += nrows;
             rows = 32;
         }
