@@ -114,6 +114,77 @@ def test_parity_small(n_particles, seed, kw):
     _check_event(toy_detector.generate_event(n_particles, seed, **kw))
 
 
+def _check_event_bins(ev, bins, dump_cap):
+    """Large events: full GPU run, oracle restricted to the middles of phi bins [lo, hi)
+    (default config: one z bin, so global bin == phi bin). Binning is compared for the whole
+    event; doublets, triplets, seeds and parameters for those middles, bit for bit."""
+    import torch
+    from traccc_b200 import (seedfilter_config, seedfinder_config, seeding, spacepoint_grid_config)
+    lo, hi = bins
+    finder = seedfinder_config()
+    grid = spacepoint_grid_config(finder)
+    filt = seedfilter_config()
+    sa = seeding.triplet_seeding_algorithm(finder, grid, filt, triplet_dump=dump_cap)
+    tp = seeding.seed_parameter_estimation_algorithm()
+    sps = seeding.spacepoint_collection.from_event(ev)
+    meas = seeding.measurement_collection.from_event(ev)
+    seeds = sa(sps)
+    params = tp(ev.bfield, meas, sps, seeds)
+    torch.cuda.synchronize()
+    c = seeds.host_counters()
+    assert c["overflow"] == 0, c
+    ref = oracle.run(ev.xyz, ev.var_z, ev.var_r, dump=True, bins=bins, sp_meas_index=ev.meas_index,
+                     meas_local=ev.meas_local, meas_surface=ev.meas_surface, bfield=ev.bfield)
+    assert c["n_valid"] == ref.counters["n_valid"]
+    L = sa.layout(ev.n_spacepoints)
+    bo = np.frombuffer(sa._ws[L.bin_offsets:L.bin_offsets + 4 * (L.n_bins + 1)].cpu().numpy().tobytes(),
+                       np.uint32)
+    ws = sa.read_workspace(ev.n_spacepoints, middles=np.arange(bo[lo], bo[hi]))
+    assert np.array_equal(ws["bin_offsets"], ref.bin_offsets)
+    assert np.array_equal(ws["sorted_index"], ref.bin_entries)
+    for which, r in (("bottom", ref.mb), ("top", ref.mt)):
+        mid, other, lc = canonical_doublets(ws, which)
+        assert len(mid) == len(r["mid"]) and len(mid) > 0, which
+        assert np.array_equal(mid, r["mid"]), which
+        assert np.array_equal(other, r["other"]), which
+        cols = slice(0, 6) if which == "bottom" else slice(1, 6)
+        assert np.array_equal(lc[:, cols].view(np.uint32), r["lc"][:, cols].view(np.uint32)), which
+    t, si = ws["triplets"], ws["sorted_index"]
+    assert len(t) == len(ref.triplets["b"]) and len(t) > 0
+    assert np.array_equal(si[t["pos_b"]], ref.triplets["b"])
+    assert np.array_equal(si[t["pos_m"]], ref.triplets["m"])
+    assert np.array_equal(si[t["pos_t"]], ref.triplets["t"])
+    for k in ("curvature", "weight", "z_vertex"):
+        assert np.array_equal(t[k].view(np.uint32), ref.triplets[k].view(np.uint32)), k
+    # seeds of those middles, in order
+    s = seeds.to_host()
+    is_sel = np.zeros(ev.n_spacepoints, bool)
+    is_sel[si[bo[lo]:bo[hi]]] = True
+    pick = np.flatnonzero(is_sel[s["middle"]])
+    r = ref.seeds
+    assert len(pick) == len(r["bottom"]) and len(pick) > 0
+    for k in ("bottom", "middle", "top"):
+        assert np.array_equal(s[k][pick], r[k]), k
+    assert np.array_equal(s["quality"][pick].view(np.uint32), r["quality"].view(np.uint32))
+    p = tp.to_host(params, len(s["bottom"]))[pick]
+    assert np.array_equal(p["surface_link"], ref.params["surface_link"])
+    assert rel_close(p["vec"], ref.params["vec"]).all()
+    return c
+
+
+@pytest.mark.parametrize("n_particles,seed,bins,kw", [
+    (5000, 71, (0, 78), {}),                  # occupancy sweep (BASELINE.json configs[2]) ...
+    (20000, 72, (30, 34), {}),
+    (50000, 73, (77, 78), {}),                # ... the wrap-around bin at the highest occupancy
+    (30000, 74, (0, 2), dict(eta_max=1.0)),   # heavy-ion-like shape (configs[4]), reduced size
+])
+def test_parity_occupancy_sweep(n_particles, seed, bins, kw):
+    from traccc_b200 import toy_detector
+    ev = toy_detector.generate_event(n_particles, seed, **kw)
+    cap = {5000: 2_000_000, 20000: 6_000_000, 50000: 45_000_000, 30000: 60_000_000}[n_particles]
+    _check_event_bins(ev, bins, cap)
+
+
 def test_parity_10k_headline():
     """configs[1]: 10k particles/event."""
     from traccc_b200 import toy_detector

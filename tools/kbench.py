@@ -45,6 +45,9 @@ res = {k: round(float(np.median(v)) * 1e3, 1) for k, v in kt.items()}
 res["total_us"] = round(sum(res.values()), 1)
 alg.set_timing(False)
 
+if os.environ.get("KBENCH_NO_THROUGHPUT"):
+    print(os.environ.get("B200SEED_LIB", "default"), json.dumps(res), json.dumps(cnt))
+    sys.exit(0)
 # throughput mode: E events over S streams / algorithm instances, like bench.py
 E, S = 32, 8
 evs = [events[i % n_events] for i in range(E)]

@@ -211,14 +211,18 @@ class triplet_seeding_algorithm:
         _lib.check(rc, self.h)
         return out
 
-    def read_workspace(self, n: int) -> dict:
-        """Intermediate arrays of the last event of n spacepoints (parity tests)."""
+    def read_workspace(self, n: int, middles=None) -> dict:
+        """Intermediate arrays of the last event of n spacepoints (parity tests).
+
+        middles: optional array of sorted positions; when given, only the doublet lists and
+        dumped triplets of those middles are copied to the host (large events)."""
         L = self.layout(n)
         torch.cuda.synchronize()
-        ws = self._ws.cpu().numpy()
+        ws = self._ws
 
         def arr(off, dtype, count):
-            return np.frombuffer(ws, dtype=dtype, count=count, offset=off).copy()
+            nbytes = int(count) * np.dtype(dtype).itemsize
+            return np.frombuffer(ws[off:off + nbytes].cpu().numpy().tobytes(), dtype=dtype, count=count)
 
         nb = L.n_bins
         bin_offsets = arr(L.bin_offsets, np.uint32, nb + 1)
@@ -228,6 +232,8 @@ class triplet_seeding_algorithm:
                "sp_xyzr": arr(L.sp_xyzr, np.float32, 4 * nv).reshape(nv, 4),
                "mid_counts": arr(L.mid_counts, np.uint32, 2 * n).reshape(2, n)[:, :nv],
                "mid_offsets": arr(L.mid_offsets, np.uint32, 2 * n).reshape(2, n)[:, :nv]}
+        sel = np.arange(nv) if middles is None else np.sort(np.asarray(middles, dtype=np.int64))
+        res["middles"] = sel
         md = int(L.max_doublets)
         # reference candidate order of a middle: neighbour phi bins in walk order (starting at
         # phi_bin - scope[0], wrapping), then grid order — the canon_key of k_doublets
@@ -236,17 +242,20 @@ class triplet_seeding_algorithm:
         bin_of_pos = np.searchsorted(bin_offsets, np.arange(nv), side="right") - 1
         phi_of_pos = bin_of_pos % n_phi
         mb_canon_rank = None
+        mb_first = None
         rec = np.dtype([("cotTheta", "<f4"), ("iDeltaR", "<f4"), ("Er", "<f4"), ("U", "<f4"),
                         ("V", "<f4"), ("Zo", "<f4"), ("r", "<f4"), ("pos", "<u4")])
         for d, name in ((0, "bottom"), (1, "top")):
-            cnt = res["mid_counts"][d].astype(np.int64)
-            off = res["mid_offsets"][d].astype(np.int64)
-            used = int((off + cnt).max()) if nv and cnt.sum() else 0
-            a = np.frombuffer(ws, dtype=rec, count=used, offset=L.doublets + d * _align(md * 32))
-            # gather the per-middle lists in sorted-position (canonical) order
-            idx = np.concatenate([np.arange(o, o + c) for o, c in zip(off, cnt) if c]) if used else np.zeros(0, np.int64)
-            lst = a[idx].copy()
-            mid = np.repeat(np.arange(nv), cnt)
+            cnt = res["mid_counts"][d].astype(np.int64)[sel]
+            off = res["mid_offsets"][d].astype(np.int64)[sel]
+            # gather the per-middle lists in sorted-position (canonical) order, on the device
+            idx = (np.concatenate([np.arange(o, o + c) for o, c in zip(off, cnt) if c])
+                   if cnt.sum() else np.zeros(0, np.int64))
+            base = L.doublets + d * _align(md * 32)
+            arena = ws[base:base + md * 32].view(torch.float32).view(md, 8)
+            got = arena[torch.from_numpy(idx).to(ws.device)].cpu().numpy() if len(idx) else np.zeros((0, 8), np.float32)
+            lst = np.frombuffer(np.ascontiguousarray(got).tobytes(), dtype=rec).copy()
+            mid = np.repeat(sel, cnt)
             if d == 0 and len(lst):
                 # mid-bottom lists are stored in order of discovery: sort by canon_key
                 pos = lst["pos"].astype(np.int64)
@@ -257,11 +266,12 @@ class triplet_seeding_algorithm:
                 start = np.concatenate([[0], np.cumsum(cnt)])[:-1]
                 mb_canon_rank = np.empty(len(lst), np.int64)
                 mb_canon_rank[order] = np.arange(len(lst)) - np.repeat(start, cnt)
-                mb_first = start
+                mb_first = np.full(nv, -1, np.int64)
+                mb_first[sel] = start
                 lst = lst[order]
             if d == 1 and len(lst):
                 # mid-top lists are stored sorted by cotTheta; the "Zo" slot carries the
-                # canonical index -> restore the reference's order inside each middle
+                # canon_key -> restore the reference's order inside each middle
                 canon = lst["Zo"].view(np.uint32).astype(np.int64)
                 order = np.lexsort((canon, mid))
                 assert np.array_equal(mid[order], mid)
@@ -273,11 +283,16 @@ class triplet_seeding_algorithm:
             res[f"doublets_{name}_mid"] = mid
         if L.max_triplet_dump:
             ndump = int(arr(L.triplet_dump_count, np.uint32, 1)[0])
+            ndump = min(ndump, int(L.max_triplet_dump))
             trec = np.dtype([("pos_b", "<u4"), ("pos_m", "<u4"), ("pos_t", "<u4"), ("mb_idx", "<u4"),
                              ("mt_idx", "<u4"), ("curvature", "<f4"), ("weight", "<f4"),
                              ("z_vertex", "<f4")])
-            t = np.frombuffer(ws, dtype=trec, count=min(ndump, int(L.max_triplet_dump)),
-                              offset=L.triplet_dump).copy()
+            dump = ws[L.triplet_dump:L.triplet_dump + ndump * 32].view(torch.int32).view(ndump, 8)
+            if middles is not None and ndump:
+                is_sel = torch.zeros(nv, dtype=torch.bool, device=ws.device)
+                is_sel[torch.from_numpy(sel).to(ws.device)] = True
+                dump = dump[is_sel[dump[:, 1].long()]]
+            t = np.frombuffer(np.ascontiguousarray(dump.cpu().numpy()).tobytes(), dtype=trec).copy()
             if len(t) and mb_canon_rank is not None:
                 # mb_idx is the index in the stored (discovery-order) list -> canonical index
                 t["mb_idx"] = mb_canon_rank[mb_first[t["pos_m"]] + t["mb_idx"]]
