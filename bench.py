@@ -392,6 +392,14 @@ def run_b200(args):
             roof = {"bound": "hbm", "kernel": "k_" + dom, "achieved": ach, "peak": hbm_peak,
                     "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": hbm_src,
                     "ms_per_launch": kt[dom]}
+        # DRAM traffic of the dominant kernel from the committed ncu --set full capture
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            roof["traffic"] = tr["dram_bytes_per_launch"].get("k_" + dom)
+            roof["traffic_source"] = f"profiles/{tr['source']} (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+        except (OSError, KeyError, ValueError):
+            pass
+        roof["executed_pair_tests_per_event"] = c_mean.get("pair_visited")
         ev_bytes = sum(byts.values()) + (c_mean["n_mid_bot"] + c_mean["n_mid_top"]) * 32 * 2
         ev_ms = sum(kt.values())
         roof["per_kernel_ms"] = kt
