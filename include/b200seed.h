@@ -185,6 +185,12 @@ int b200seed_get_axes(const b200seed_handle* h, uint32_t* n_phi, float* phi_min,
  * max(2^20, 4e-3 * max_spacepoints^2). */
 int b200seed_set_max_doublets(b200seed_handle* h, uint64_t max_doublets);
 
+/* Tuning knob: mid-bottom doublets of one middle staged in shared memory by the doublet
+ * kernel (mid-tops: half of it) before its list is allocated in the arena; longer lists
+ * take a second scan that writes straight to the arena. 0 = automatic (512 ... 2048 by
+ * event size). Results do not depend on it. */
+int b200seed_set_stage_cap(b200seed_handle* h, uint32_t cap);
+
 /* Bytes of device scratch b200seed_run needs for events of up to max_spacepoints. */
 size_t b200seed_workspace_bytes(const b200seed_handle* h, uint32_t max_spacepoints);
 

@@ -16,7 +16,7 @@ from tests.helpers import canonical_doublets, oracle_cfgs, rel_close
 pytestmark = pytest.mark.gpu
 
 
-def _run_gpu(ev, finder=None, filt=None, grid=None, dump=True, max_doublets=0):
+def _run_gpu(ev, finder=None, filt=None, grid=None, dump=True, max_doublets=0, stage_cap=0):
     import torch
     from traccc_b200 import (seedfilter_config, seedfinder_config, seeding,
                              spacepoint_grid_config)
@@ -24,7 +24,7 @@ def _run_gpu(ev, finder=None, filt=None, grid=None, dump=True, max_doublets=0):
     grid = grid or spacepoint_grid_config(finder)
     filt = filt or seedfilter_config()
     sa = seeding.triplet_seeding_algorithm(finder, grid, filt, triplet_dump=(4_000_000 if dump else 0),
-                                           max_doublets=max_doublets)
+                                           max_doublets=max_doublets, stage_cap=stage_cap)
     tp = seeding.seed_parameter_estimation_algorithm()
     sps = seeding.spacepoint_collection.from_event(ev)
     meas = seeding.measurement_collection.from_event(ev)
@@ -39,8 +39,8 @@ def _run_gpu(ev, finder=None, filt=None, grid=None, dump=True, max_doublets=0):
     return res, (finder, grid, filt)
 
 
-def _check_event(ev, finder=None, filt=None, grid=None, dump=True):
-    got, (finder, grid, filt) = _run_gpu(ev, finder, filt, grid, dump)
+def _check_event(ev, finder=None, filt=None, grid=None, dump=True, stage_cap=0):
+    got, (finder, grid, filt) = _run_gpu(ev, finder, filt, grid, dump, stage_cap=stage_cap)
     of, og, ofl = oracle_cfgs(finder, grid, filt)
     ref = oracle.run(ev.xyz, ev.var_z, ev.var_r, finder=of, grid=og, filt=ofl, dump=dump,
                      sp_meas_index=ev.meas_index, meas_local=ev.meas_local,
@@ -183,6 +183,18 @@ def test_parity_occupancy_sweep(n_particles, seed, bins, kw):
     ev = toy_detector.generate_event(n_particles, seed, **kw)
     cap = {5000: 2_000_000, 20000: 6_000_000, 50000: 45_000_000, 30000: 60_000_000}[n_particles]
     _check_event_bins(ev, bins, cap)
+
+
+@pytest.mark.parametrize("n_particles,seed,kw,cap", [
+    (2000, 81, dict(shuffle=True, variances=0.03), 16),   # nearly every middle spills
+    (4000, 82, dict(eta_max=1.0), 32),
+    (3000, 83, {}, 64),                                   # a mix of staged and spilled middles
+])
+def test_parity_spilled_doublet_lists(n_particles, seed, kw, cap):
+    """Middles whose doublet lists do not fit the shared-memory staging area take the
+    two-pass path (second scan straight into the arena + bucket sort of the mid-tops)."""
+    from traccc_b200 import toy_detector
+    _check_event(toy_detector.generate_event(n_particles, seed, **kw), stage_cap=cap)
 
 
 def test_parity_10k_headline():

@@ -104,6 +104,7 @@ EXPORTS = (
     "b200seed_finder_cfg_defaults", "b200seed_finder_cfg_setup", "b200seed_grid_cfg_from_finder",
     "b200seed_filter_cfg_defaults", "b200seed_tpe_cfg_defaults", "b200seed_create",
     "b200seed_destroy", "b200seed_last_error", "b200seed_get_axes", "b200seed_set_max_doublets",
+    "b200seed_set_stage_cap",
     "b200seed_workspace_bytes", "b200seed_run", "b200seed_estimate_params", "b200seed_run_host",
     "b200seed_workspace_layout", "b200seed_set_triplet_dump", "b200seed_set_timing",
     "b200seed_get_timings", "b200seed_launches_per_event", "b200seed_measure_fp32_peak",
@@ -139,6 +140,7 @@ def lib() -> C.CDLL:
     L.b200seed_axes_for.argtypes = [C.POINTER(spacepoint_grid_config), vp, vp]
     L.b200seed_set_max_doublets.argtypes = [vp, u64]
     L.b200seed_set_triplet_dump.argtypes = [vp, u64]
+    L.b200seed_set_stage_cap.argtypes = [vp, u32]
     L.b200seed_workspace_bytes.argtypes = [vp, u32]
     L.b200seed_workspace_bytes.restype = sz
     L.b200seed_workspace_layout.argtypes = [vp, u32, C.POINTER(WsLayout)]

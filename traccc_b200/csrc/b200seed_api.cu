@@ -62,6 +62,7 @@ struct b200seed_handle {
     uint32_t nbins = 0;
     uint64_t max_doublets_user = 0;
     uint64_t max_dump = 0;
+    uint32_t stage_cap_user = 0;
     int num_sms = 148;
     int smem_optin = 0;
     bool timing = false;
@@ -511,6 +512,14 @@ int b200seed_set_max_doublets(b200seed_handle* h, uint64_t max_doublets) {
     return B200SEED_OK;
 }
 
+int b200seed_set_stage_cap(b200seed_handle* h, uint32_t cap) {
+    if (!h) return B200SEED_EINVAL;
+    if (cap != 0 && (cap < 16 || cap > 4096 || (cap & 15u)))
+        return fail(h, B200SEED_EINVAL, "stage cap must be 0 or a multiple of 16 in [16, 4096]");
+    h->stage_cap_user = cap;
+    return B200SEED_OK;
+}
+
 int b200seed_set_triplet_dump(b200seed_handle* h, uint64_t max_triplets) {
     if (!h) return B200SEED_EINVAL;
     if (max_triplets > 0xFFFF0000ull) return fail(h, B200SEED_EINVAL, "max_triplets too large");
@@ -663,7 +672,7 @@ int b200seed_run(b200seed_handle* h, void* stream, uint32_t n_sp, const float* d
         a.ctrl = ctrl;
         a.g = L.g;
         a.max_doublets = uint32_t(L.max_doublets);
-        a.cap_b = doublet_stage_cap(n_sp);
+        a.cap_b = h->stage_cap_user ? h->stage_cap_user : doublet_stage_cap(n_sp);
         a.cap_t = a.cap_b / 2;
         const size_t smem = size_t(WARPS_PER_CTA) * doublet_smem_words(a.cap_b, a.cap_t) * 4;
         uint32_t grid = (n_sp + WARPS_PER_CTA - 1) / WARPS_PER_CTA;

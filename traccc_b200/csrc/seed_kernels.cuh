@@ -498,17 +498,72 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
                 }
             }
             if (direct) {
-                // sort the mid-top records: second half -> first half
-                const DoubletRec* src = a.arena_t + offT + nT;
-                DoubletRec* dst = a.arena_t + offT;
+                // Sort the mid-top records by (cotTheta, reference order): bucket sort between
+                // the two halves of the allocation. U = unsorted records (second half);
+                // T = first half = final place.
+                DoubletRec* U = a.arena_t + offT + nT;
+                DoubletRec* T = a.arena_t + offT;
+                uint32_t* bcnt = key_s;                                  // [nbk] count -> cursor
+                uint32_t* bstart = reinterpret_cast<uint32_t*>(cot_s);   // [nbk]
+                __syncwarp();
+                float cmin = __uint_as_float(0x7f800000u), cmax = __uint_as_float(0xff800000u);
+                for (uint32_t k = lane; k < nT; k += 32) {
+                    const float c = U[k].a.x;
+                    cmin = fminf(cmin, c);
+                    cmax = fmaxf(cmax, c);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    cmin = fminf(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
+                    cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+                }
+                uint32_t nbk = nT / 16u + 1u;  // about 16 records per bucket
+                if (nbk > a.cap_t) nbk = a.cap_t;
+                float scale = float(nbk) / (cmax - cmin);
+                if (!(scale > 0.f) || !(scale < 1e30f)) {  // all equal / non-finite: one bucket
+                    nbk = 1;
+                    scale = 0.f;
+                }
+                auto bucket_of = [&](float c) -> uint32_t {
+                    const float t = (c - cmin) * scale;  // monotone in c
+                    if (!(t > 0.f)) return 0u;
+                    return (t >= float(nbk)) ? nbk - 1u : uint32_t(t);
+                };
+                for (uint32_t b = lane; b < nbk; b += 32) bcnt[b] = 0u;
+                __syncwarp();
+                for (uint32_t k = lane; k < nT; k += 32) atomicAdd(&bcnt[bucket_of(U[k].a.x)], 1u);
+                __syncwarp();
+                uint32_t carry = 0;
+                for (uint32_t b0 = 0; b0 < nbk; b0 += 32) {
+                    const uint32_t b = b0 + lane;
+                    const uint32_t v = (b < nbk) ? bcnt[b] : 0u;
+                    const uint32_t incl = warp_incl_scan(v, lane);
+                    if (b < nbk) {
+                        bstart[b] = carry + incl - v;
+                        bcnt[b] = carry + incl - v;  // cursor
+                    }
+                    carry += __shfl_sync(0xffffffffu, incl, 31);
+                }
                 __syncwarp();
                 for (uint32_t k = lane; k < nT; k += 32) {
-                    const DoubletRec r = src[k];
-                    const uint32_t ks =
-                        top_rank([&](uint32_t j) { return src[j].a.x; },
-                                 [&](uint32_t j) { return __float_as_uint(src[j].b.y); }, nT, r.a.x,
-                                 __float_as_uint(r.b.y));
-                    dst[ks] = r;
+                    const DoubletRec r = U[k];
+                    T[atomicAdd(&bcnt[bucket_of(r.a.x)], 1u)] = r;
+                }
+                __syncwarp();
+                for (uint32_t k = lane; k < nT; k += 32) U[k] = T[k];  // bucketed copy
+                __syncwarp();
+                // rank inside the bucket (after the scatter bcnt[b] is the end of bucket b)
+                for (uint32_t k = lane; k < nT; k += 32) {
+                    const DoubletRec r = U[k];
+                    const uint32_t b = bucket_of(r.a.x);
+                    const uint32_t s0 = bstart[b], s1 = bcnt[b];
+                    const uint32_t kk = __float_as_uint(r.b.y);
+                    uint32_t rank = 0;
+                    for (uint32_t j = s0; j < s1; ++j) {
+                        const float cj = U[j].a.x;
+                        rank += ((cj < r.a.x) || (cj == r.a.x && __float_as_uint(U[j].b.y) < kk)) ? 1u : 0u;
+                    }
+                    T[s0 + rank] = r;
                 }
                 break;
             }
