@@ -44,8 +44,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--events", type=int, default=32, help="events per step per GPU")
+    ap.add_argument("--events", type=int, default=64, help="events per step per GPU")
     ap.add_argument("--streams", type=int, default=8, help="algorithm instances / streams per GPU")
+    ap.add_argument("--pool-workers", type=int, default=6,
+                    help="host worker threads of the end-to-end leg (2 events in flight each)")
     ap.add_argument("--particles", type=int, default=N_PARTICLES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-one", action="store_true",
@@ -293,36 +295,19 @@ def run_b200(args):
     assert all(c["overflow"] == 0 for c in counters), "overflow flag set: results incomplete"
     mean_sp = float(np.mean([e.n_spacepoints for e in events]))
 
-    # ---- end to end through the host-buffer C-ABI call, one host thread per stream ----
-    pipes = [seeding.HostPipeline(finder, grid, filt, device=local, max_seeds=max_n * K5) for _ in range(S)]
-    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-    h_in = [(pin(e.xyz), pin(e.var_z), pin(e.var_r), pin(e.meas_index.view(np.int32)),
-             pin(e.meas_local), pin(e.meas_surface.view(np.int64))) for e in events]
-    h2d = sum(sum(t.numel() * t.element_size() for t in x) for x in h_in)
+    # ---- end to end through the host-buffer C-ABI (b200seed_pool_process): pinned HOST
+    #      buffers in, seeds + parameters back in pinned HOST buffers; H->D and D->H copies
+    #      inside the timed region; S native worker threads with two events in flight each ----
+    PW = max(1, args.pool_workers)
+    pool = seeding.EventPool(finder, grid, filt, device=local, n_workers=PW)
+    ios, outs = pool.make_batch(events)
+    h2d = sum(e.xyz.nbytes + e.var_z.nbytes + e.var_r.nbytes + e.meas_index.nbytes + e.meas_local.nbytes
+              + e.meas_surface.nbytes for e in events)
     d2h_box = [0]
-    errs = []
-
-    def e2e_worker(k, acc):
-        try:
-            torch.cuda.set_device(local)
-            n = 0
-            for i in range(k, E, S):
-                r = pipes[k].run(*h_in[i], events[i].bfield, stream=streams[k])
-                n += 48 + r["n_seeds"] * (16 + 176)
-            acc[k] = n
-        except Exception as ex:   # surface errors from worker threads
-            errs.append(ex)
 
     def step_e2e():
-        acc = [0] * S
-        ts = [threading.Thread(target=e2e_worker, args=(k, acc)) for k in range(S)]
-        for t in ts:
-            t.start()
-        for t in ts:
-            t.join()
-        if errs:
-            raise errs[0]
-        d2h_box[0] = sum(acc)
+        pool.process(ios)
+        d2h_box[0] = sum(C.sizeof(_lib.Counters) + int(io.n_seeds) * (16 + 176) for io in ios)
 
     def timed_wall(step_fn, k, w):
         for _ in range(w):
@@ -341,6 +326,10 @@ def run_b200(args):
 
     e2e_s = timed_wall(step_e2e, args.steps, args.warmup)
     e2e_ev_per_s = world * E * args.steps / e2e_s
+    # the pool's results are the device path's results
+    chk = seeding.EventPool.result(ios[0], outs[0])
+    ref0 = d_out[0].to_host()
+    assert chk["n_seeds"] == len(ref0["bottom"]) and np.array_equal(chk["top"], ref0["top"])
 
     # ---- per-kernel device times (CUDA events on the launching stream) for the roofline ----
     algs[0].set_timing(True)
@@ -418,7 +407,8 @@ def run_b200(args):
                 "gpu_launches": E * args.steps * algs[0].launches_per_event(True),
                 "e2e": {"value": e2e_ev_per_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h_box[0],
-                        "how": f"b200seed_run_host from pinned host buffers, {S} host threads/streams"},
+                        "how": f"b200seed_pool_process from pinned host buffers: {PW} native worker threads, "
+                               f"2 algorithm instances/streams each"},
                 "roofline": roof, "clocks": clocks,
                 "event_counters_mean": c_mean}
 

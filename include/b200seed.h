@@ -241,6 +241,52 @@ int b200seed_run_host(b200seed_handle* h, void* stream, uint32_t n_sp, const flo
                       b200seed_counters* h_counters);
 
 /* ------------------------------------------------------------------------ */
+/* Throughput: many events through one device                               */
+/* ------------------------------------------------------------------------ */
+
+/* One event of b200seed_pool_process: the arguments of b200seed_run_host as a record.
+ * All pointers are HOST pointers (pinned memory for asynchronous copies); n_seeds,
+ * counters and status are written by the pool. */
+typedef struct b200seed_event_io {
+    uint32_t n_spacepoints;
+    uint32_t n_measurements;
+    const float* xyz;
+    const float* var_z;
+    const float* var_r;
+    const uint32_t* sp_meas_index_1;
+    const float* meas_local;
+    const uint64_t* meas_surface;
+    float bfield[3];
+    uint32_t seed_capacity;
+    uint32_t* bottom;
+    uint32_t* middle;
+    uint32_t* top;
+    float* quality;
+    b200seed_bound_params* params; /* may be NULL: seeding only */
+    uint32_t n_seeds;
+    int32_t status;
+    b200seed_counters counters;
+} b200seed_event_io;
+
+typedef struct b200seed_pool b200seed_pool;
+
+/* The host side of a throughput job on one device, replacing what the reference's
+ * multi-threaded throughput application does around the two algorithms
+ * (examples/run/common/include/traccc/examples/impl/throughput_mt.ipp:170-298: one
+ * algorithm instance + stream per host thread, events handed out dynamically).
+ * n_workers host threads are created; each owns two algorithm instances / CUDA streams, so
+ * it always has one event in flight on the device while it collects the previous one.
+ * For several GPUs create one pool per device (events are independent: no exchange). */
+int b200seed_pool_create(const b200seed_finder_cfg* finder, const b200seed_grid_cfg* grid,
+                         const b200seed_filter_cfg* filter, const b200seed_tpe_cfg* tpe,
+                         int device, int n_workers, b200seed_pool** out);
+/* Process events[0..n_events): H->D, seeding, parameter estimation, D->H for each; returns
+ * when all are done (0, or the first failing event's status; see events[i].status). */
+int b200seed_pool_process(b200seed_pool* pool, b200seed_event_io* events, uint32_t n_events);
+const char* b200seed_pool_last_error(const b200seed_pool* pool);
+void b200seed_pool_destroy(b200seed_pool* pool);
+
+/* ------------------------------------------------------------------------ */
 /* Introspection for the parity tests and the bench                          */
 /* ------------------------------------------------------------------------ */
 

@@ -298,6 +298,33 @@ def test_run_host_matches_device_path():
     assert res["counters"] == got["counters"]
 
 
+def test_event_pool_matches_device_path():
+    """b200seed_pool (native worker threads, two events in flight each) returns, for every
+    event of a batch, what the single-event device path returns."""
+    from traccc_b200 import seeding, toy_detector
+    events = [toy_detector.generate_event(300 + 150 * i, 90 + i) for i in range(11)]
+    events.insert(4, toy_detector.ToyEvent(np.zeros((0, 3), np.float32), np.zeros(0, np.float32),
+                                           np.zeros(0, np.float32), np.zeros(0, np.uint32),
+                                           np.zeros((0, 2), np.float32), np.zeros(0, np.uint64),
+                                           np.zeros(0, np.uint32), 0, events[0].bfield))
+    pool = seeding.EventPool(n_workers=3)
+    ios, outs = pool.make_batch(events)
+    for _ in range(2):          # a pool is reusable
+        pool.process(ios)
+    for ev, io, out in zip(events, ios, outs):
+        res = seeding.EventPool.result(io, out)
+        assert io.status == 0
+        if ev.n_spacepoints == 0:
+            assert res["n_seeds"] == 0
+            continue
+        got, _ = _run_gpu(ev, dump=False)
+        assert res["n_seeds"] == got["counters"]["n_seeds"]
+        for k in ("bottom", "middle", "top", "quality"):
+            assert np.array_equal(res[k], got["seeds"][k])
+        assert np.array_equal(res["params"]["vec"].view(np.uint32), got["params"]["vec"].view(np.uint32))
+        assert res["counters"] == got["counters"]
+
+
 def test_overflow_flags():
     """A too-small doublet arena or seed buffer is reported, never silently truncated."""
     import torch

@@ -91,6 +91,18 @@ class Counters(C.Structure):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
+class EventIO(C.Structure):
+    """b200seed_event_io (include/b200seed.h)."""
+
+    _fields_ = [("n_spacepoints", C.c_uint32), ("n_measurements", C.c_uint32),
+                ("xyz", C.c_void_p), ("var_z", C.c_void_p), ("var_r", C.c_void_p),
+                ("sp_meas_index_1", C.c_void_p), ("meas_local", C.c_void_p),
+                ("meas_surface", C.c_void_p), ("bfield", C.c_float * 3),
+                ("seed_capacity", C.c_uint32), ("bottom", C.c_void_p), ("middle", C.c_void_p),
+                ("top", C.c_void_p), ("quality", C.c_void_p), ("params", C.c_void_p),
+                ("n_seeds", C.c_uint32), ("status", C.c_int32), ("counters", Counters)]
+
+
 class WsLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in (
         "bin_offsets", "sorted_index", "sp_xyzr", "mid_counts", "mid_offsets", "doublets",
@@ -104,7 +116,8 @@ EXPORTS = (
     "b200seed_finder_cfg_defaults", "b200seed_finder_cfg_setup", "b200seed_grid_cfg_from_finder",
     "b200seed_filter_cfg_defaults", "b200seed_tpe_cfg_defaults", "b200seed_create",
     "b200seed_destroy", "b200seed_last_error", "b200seed_get_axes", "b200seed_set_max_doublets",
-    "b200seed_set_stage_cap",
+    "b200seed_set_stage_cap", "b200seed_pool_create", "b200seed_pool_process",
+    "b200seed_pool_last_error", "b200seed_pool_destroy",
     "b200seed_workspace_bytes", "b200seed_run", "b200seed_estimate_params", "b200seed_run_host",
     "b200seed_workspace_layout", "b200seed_set_triplet_dump", "b200seed_set_timing",
     "b200seed_get_timings", "b200seed_launches_per_event", "b200seed_measure_fp32_peak",
@@ -150,6 +163,15 @@ def lib() -> C.CDLL:
     L.b200seed_run_host.argtypes = [vp, vp, u32, vp, vp, vp, vp, u32, vp, vp,
                                     C.POINTER(C.c_float * 3), u32, vp, vp, vp, vp, vp,
                                     C.POINTER(u32), C.POINTER(Counters)]
+    L.b200seed_pool_create.argtypes = [C.POINTER(seedfinder_config), C.POINTER(spacepoint_grid_config),
+                                       C.POINTER(seedfilter_config),
+                                       C.POINTER(track_params_estimation_config), C.c_int, C.c_int,
+                                       C.POINTER(vp)]
+    L.b200seed_pool_process.argtypes = [vp, C.POINTER(EventIO), u32]
+    L.b200seed_pool_last_error.argtypes = [vp]
+    L.b200seed_pool_last_error.restype = C.c_char_p
+    L.b200seed_pool_destroy.argtypes = [vp]
+    L.b200seed_pool_destroy.restype = None
     L.b200seed_set_timing.argtypes = [vp, C.c_int]
     L.b200seed_get_timings.argtypes = [vp, vp, vp, C.c_int]
     L.b200seed_launches_per_event.argtypes = [vp, C.c_int]

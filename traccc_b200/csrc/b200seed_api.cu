@@ -10,8 +10,11 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdio>
+#include <atomic>
+#include <condition_variable>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -746,24 +749,41 @@ int b200seed_estimate_params(b200seed_handle* h, void* stream, const uint32_t* d
     return B200SEED_OK;
 }
 
-int b200seed_run_host(b200seed_handle* h, void* stream, uint32_t n_sp, const float* h_xyz,
-                      const float* h_var_z, const float* h_var_r,
-                      const uint32_t* h_sp_meas_index_1, uint32_t n_meas,
-                      const float* h_meas_local, const uint64_t* h_meas_surface,
-                      const float bfield[3], uint32_t seed_capacity, uint32_t* h_bottom,
-                      uint32_t* h_middle, uint32_t* h_top, float* h_quality,
-                      b200seed_bound_params* h_params, uint32_t* h_n_seeds,
-                      b200seed_counters* h_counters) {
-    if (!h) return B200SEED_EINVAL;
-    if (!h_n_seeds) return fail(h, B200SEED_EINVAL, "b200seed_run_host: h_n_seeds is null");
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
+}  // extern "C"
+
+namespace {
+
+// One event of the host-buffer path, split in two so that callers can keep several events
+// in flight: submit = H->D + all kernels + read-back of the counters (asynchronous);
+// finish = wait for the counters, sized D->H copies of seeds and parameters, wait.
+struct HostEvent {
+    uint32_t n_sp = 0, n_meas = 0, seed_capacity = 0;
+    const float* h_xyz = nullptr;
+    const float* h_var_z = nullptr;
+    const float* h_var_r = nullptr;
+    const uint32_t* h_smi = nullptr;
+    const float* h_ml = nullptr;
+    const uint64_t* h_ms = nullptr;
+    float bfield[3] = {0.f, 0.f, 0.f};
+    uint32_t* h_bottom = nullptr;
+    uint32_t* h_middle = nullptr;
+    uint32_t* h_top = nullptr;
+    float* h_quality = nullptr;
+    b200seed_bound_params* h_params = nullptr;
+    // device staging of the outputs (set by submit)
+    uint32_t *d_b = nullptr, *d_m = nullptr, *d_t = nullptr;
+    float* d_q = nullptr;
+    b200seed_bound_params* d_p = nullptr;
+    bool submitted = false;
+};
+
+int host_submit(b200seed_handle* h, cudaStream_t s, HostEvent& e) {
     CUDA_TRY(h, cudaSetDevice(h->device));
-    *h_n_seeds = 0;
-    if (h_counters) std::memset(h_counters, 0, sizeof(*h_counters));
-    if (n_sp == 0) return B200SEED_OK;
-    if (!h_xyz) return fail(h, B200SEED_EINVAL, "b200seed_run_host: h_xyz is null");
-    const bool want_params = h_params != nullptr;
-    if (want_params && !bfield) return fail(h, B200SEED_EINVAL, "b200seed_run_host: bfield is null");
+    e.submitted = false;
+    if (e.n_sp == 0) return B200SEED_OK;
+    if (!e.h_xyz) return fail(h, B200SEED_EINVAL, "b200seed_run_host: h_xyz is null");
+    const bool want_params = e.h_params != nullptr;
+    const uint32_t n_sp = e.n_sp, n_meas = e.n_meas, seed_capacity = e.seed_capacity;
 
     // device staging: inputs | outputs | workspace
     size_t o = 0;
@@ -792,58 +812,243 @@ int b200seed_run_host(b200seed_handle* h, void* stream, uint32_t n_sp, const flo
     if (!h->h_pinned) CUDA_TRY(h, cudaMallocHost(&h->h_pinned, 256));
     unsigned char* d = static_cast<unsigned char*>(h->d_stage);
     float* d_xyz = reinterpret_cast<float*>(d + o_xyz);
-    float* d_vz = h_var_z ? reinterpret_cast<float*>(d + o_vz) : nullptr;
-    float* d_vr = h_var_r ? reinterpret_cast<float*>(d + o_vr) : nullptr;
-    uint32_t* d_smi = h_sp_meas_index_1 ? reinterpret_cast<uint32_t*>(d + o_smi) : nullptr;
-    float* d_ml = h_meas_local ? reinterpret_cast<float*>(d + o_ml) : nullptr;
-    uint64_t* d_ms = h_meas_surface ? reinterpret_cast<uint64_t*>(d + o_ms) : nullptr;
-    uint32_t* d_b = reinterpret_cast<uint32_t*>(d + o_b);
-    uint32_t* d_m = reinterpret_cast<uint32_t*>(d + o_m);
-    uint32_t* d_t = reinterpret_cast<uint32_t*>(d + o_t);
-    float* d_q = reinterpret_cast<float*>(d + o_q);
-    b200seed_bound_params* d_p = reinterpret_cast<b200seed_bound_params*>(d + o_p);
+    float* d_vz = e.h_var_z ? reinterpret_cast<float*>(d + o_vz) : nullptr;
+    float* d_vr = e.h_var_r ? reinterpret_cast<float*>(d + o_vr) : nullptr;
+    uint32_t* d_smi = e.h_smi ? reinterpret_cast<uint32_t*>(d + o_smi) : nullptr;
+    float* d_ml = e.h_ml ? reinterpret_cast<float*>(d + o_ml) : nullptr;
+    uint64_t* d_ms = e.h_ms ? reinterpret_cast<uint64_t*>(d + o_ms) : nullptr;
+    e.d_b = reinterpret_cast<uint32_t*>(d + o_b);
+    e.d_m = reinterpret_cast<uint32_t*>(d + o_m);
+    e.d_t = reinterpret_cast<uint32_t*>(d + o_t);
+    e.d_q = reinterpret_cast<float*>(d + o_q);
+    e.d_p = reinterpret_cast<b200seed_bound_params*>(d + o_p);
     uint32_t* d_n = reinterpret_cast<uint32_t*>(d + o_n);
     b200seed_counters* d_c = reinterpret_cast<b200seed_counters*>(d + o_c);
 
-    CUDA_TRY(h, cudaMemcpyAsync(d_xyz, h_xyz, size_t(n_sp) * 12, cudaMemcpyHostToDevice, s));
-    if (d_vz) CUDA_TRY(h, cudaMemcpyAsync(d_vz, h_var_z, size_t(n_sp) * 4, cudaMemcpyHostToDevice, s));
-    if (d_vr) CUDA_TRY(h, cudaMemcpyAsync(d_vr, h_var_r, size_t(n_sp) * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(d_xyz, e.h_xyz, size_t(n_sp) * 12, cudaMemcpyHostToDevice, s));
+    if (d_vz) CUDA_TRY(h, cudaMemcpyAsync(d_vz, e.h_var_z, size_t(n_sp) * 4, cudaMemcpyHostToDevice, s));
+    if (d_vr) CUDA_TRY(h, cudaMemcpyAsync(d_vr, e.h_var_r, size_t(n_sp) * 4, cudaMemcpyHostToDevice, s));
     if (want_params) {
         if (d_smi)
-            CUDA_TRY(h, cudaMemcpyAsync(d_smi, h_sp_meas_index_1, size_t(n_sp) * 4,
-                                        cudaMemcpyHostToDevice, s));
+            CUDA_TRY(h, cudaMemcpyAsync(d_smi, e.h_smi, size_t(n_sp) * 4, cudaMemcpyHostToDevice, s));
         if (d_ml)
-            CUDA_TRY(h, cudaMemcpyAsync(d_ml, h_meas_local, size_t(n_meas) * 8,
-                                        cudaMemcpyHostToDevice, s));
+            CUDA_TRY(h, cudaMemcpyAsync(d_ml, e.h_ml, size_t(n_meas) * 8, cudaMemcpyHostToDevice, s));
         if (d_ms)
-            CUDA_TRY(h, cudaMemcpyAsync(d_ms, h_meas_surface, size_t(n_meas) * 8,
-                                        cudaMemcpyHostToDevice, s));
+            CUDA_TRY(h, cudaMemcpyAsync(d_ms, e.h_ms, size_t(n_meas) * 8, cudaMemcpyHostToDevice, s));
     }
-    int rc = b200seed_run(h, s, n_sp, d_xyz, d_vz, d_vr, d + o_ws, ws_bytes, seed_capacity, d_b, d_m,
-                          d_t, d_q, d_n, d_c);
+    int rc = b200seed_run(h, s, n_sp, d_xyz, d_vz, d_vr, d + o_ws, ws_bytes, seed_capacity, e.d_b,
+                          e.d_m, e.d_t, e.d_q, d_n, d_c);
     if (rc != B200SEED_OK) return rc;
     if (want_params) {
-        rc = b200seed_estimate_params(h, s, d_n, seed_capacity, d_b, d_m, d_t, d_xyz, d_smi, d_ml,
-                                      d_ms, bfield, d_p);
+        rc = b200seed_estimate_params(h, s, d_n, seed_capacity, e.d_b, e.d_m, e.d_t, d_xyz, d_smi,
+                                      d_ml, d_ms, e.bfield, e.d_p);
         if (rc != B200SEED_OK) return rc;
     }
     // the counters struct carries n_seeds: one small read-back, then the sized copies
     CUDA_TRY(h, cudaMemcpyAsync(h->h_pinned, d_c, sizeof(b200seed_counters), cudaMemcpyDeviceToHost, s));
+    e.submitted = true;
+    return B200SEED_OK;
+}
+
+int host_finish(b200seed_handle* h, cudaStream_t s, HostEvent& e, uint32_t* h_n_seeds,
+                b200seed_counters* h_counters) {
+    *h_n_seeds = 0;
+    if (h_counters) std::memset(h_counters, 0, sizeof(*h_counters));
+    if (!e.submitted) return B200SEED_OK;
+    e.submitted = false;
+    CUDA_TRY(h, cudaSetDevice(h->device));
     CUDA_TRY(h, cudaStreamSynchronize(s));
     const uint32_t n = h->h_pinned->n_seeds;
     *h_n_seeds = n;
     if (h_counters) *h_counters = *h->h_pinned;
     if (n) {
-        if (h_bottom) CUDA_TRY(h, cudaMemcpyAsync(h_bottom, d_b, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
-        if (h_middle) CUDA_TRY(h, cudaMemcpyAsync(h_middle, d_m, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
-        if (h_top) CUDA_TRY(h, cudaMemcpyAsync(h_top, d_t, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
-        if (h_quality) CUDA_TRY(h, cudaMemcpyAsync(h_quality, d_q, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
-        if (want_params)
-            CUDA_TRY(h, cudaMemcpyAsync(h_params, d_p, size_t(n) * sizeof(b200seed_bound_params),
+        if (e.h_bottom) CUDA_TRY(h, cudaMemcpyAsync(e.h_bottom, e.d_b, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
+        if (e.h_middle) CUDA_TRY(h, cudaMemcpyAsync(e.h_middle, e.d_m, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
+        if (e.h_top) CUDA_TRY(h, cudaMemcpyAsync(e.h_top, e.d_t, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
+        if (e.h_quality) CUDA_TRY(h, cudaMemcpyAsync(e.h_quality, e.d_q, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
+        if (e.h_params)
+            CUDA_TRY(h, cudaMemcpyAsync(e.h_params, e.d_p, size_t(n) * sizeof(b200seed_bound_params),
                                         cudaMemcpyDeviceToHost, s));
         CUDA_TRY(h, cudaStreamSynchronize(s));
     }
     return B200SEED_OK;
+}
+
+HostEvent host_event_of(const b200seed_event_io& io) {
+    HostEvent e;
+    e.n_sp = io.n_spacepoints, e.n_meas = io.n_measurements, e.seed_capacity = io.seed_capacity;
+    e.h_xyz = io.xyz, e.h_var_z = io.var_z, e.h_var_r = io.var_r, e.h_smi = io.sp_meas_index_1;
+    e.h_ml = io.meas_local, e.h_ms = io.meas_surface;
+    e.bfield[0] = io.bfield[0], e.bfield[1] = io.bfield[1], e.bfield[2] = io.bfield[2];
+    e.h_bottom = io.bottom, e.h_middle = io.middle, e.h_top = io.top, e.h_quality = io.quality;
+    e.h_params = io.params;
+    return e;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// Event pool: the host side of a throughput job on one device — worker threads, each with
+// two algorithm instances + streams, so that a worker always has one event computing while
+// it collects the previous one (the reference's throughput_mt app runs one
+// full_chain_algorithm per TBB thread: examples/run/common/.../throughput_mt.ipp:170-298).
+// ---------------------------------------------------------------------------
+struct b200seed_pool {
+    struct Slot {
+        b200seed_handle* h = nullptr;
+        cudaStream_t s = nullptr;
+        HostEvent ev;
+        long pending = -1;
+    };
+    struct Worker {
+        Slot slot[2];
+        std::thread th;
+    };
+    int device = 0;
+    std::vector<Worker> workers;
+    std::mutex mu;
+    std::condition_variable cv_job, cv_done;
+    b200seed_event_io* events = nullptr;
+    uint32_t n_events = 0;
+    std::atomic<uint32_t> next{0};
+    uint64_t generation = 0;
+    int running = 0;
+    bool stop = false;
+    std::string error;
+
+    void work(Worker& w) {
+        uint64_t seen = 0;
+        while (true) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_job.wait(lk, [&] { return stop || generation != seen; });
+                if (stop) return;
+                seen = generation;
+            }
+            cudaSetDevice(device);
+            int k = 0;
+            while (true) {
+                Slot& cur = w.slot[k];
+                const uint32_t idx = next.fetch_add(1);
+                if (idx < n_events) {
+                    cur.ev = host_event_of(events[idx]);
+                    const int rc = host_submit(cur.h, cur.s, cur.ev);
+                    events[idx].status = rc;
+                    cur.pending = idx;
+                }
+                Slot& oth = w.slot[k ^ 1];
+                if (oth.pending >= 0) {
+                    b200seed_event_io& io = events[oth.pending];
+                    if (io.status == B200SEED_OK)
+                        io.status = host_finish(oth.h, oth.s, oth.ev, &io.n_seeds, &io.counters);
+                    oth.pending = -1;
+                }
+                if (idx >= n_events && cur.pending < 0) break;
+                k ^= 1;
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (--running == 0) cv_done.notify_all();
+            }
+        }
+    }
+};
+
+extern "C" {
+
+int b200seed_pool_create(const b200seed_finder_cfg* finder, const b200seed_grid_cfg* grid,
+                         const b200seed_filter_cfg* filter, const b200seed_tpe_cfg* tpe, int device,
+                         int n_workers, b200seed_pool** out) {
+    if (!out || n_workers < 1 || n_workers > 64)
+        return fail(nullptr, B200SEED_EINVAL, "b200seed_pool_create: bad argument");
+    *out = nullptr;
+    b200seed_pool* p = new b200seed_pool();
+    p->device = device;
+    p->workers = std::vector<b200seed_pool::Worker>(size_t(n_workers));
+    for (auto& w : p->workers) {
+        for (auto& sl : w.slot) {
+            int rc = b200seed_create(finder, grid, filter, tpe, device, &sl.h);
+            if (rc == B200SEED_OK && cudaStreamCreateWithFlags(&sl.s, cudaStreamNonBlocking) != cudaSuccess)
+                rc = fail(nullptr, B200SEED_ECUDA, "cudaStreamCreate failed");
+            if (rc != B200SEED_OK) {
+                b200seed_pool_destroy(p);
+                return rc;
+            }
+        }
+    }
+    for (auto& w : p->workers) w.th = std::thread([p, &w] { p->work(w); });
+    *out = p;
+    return B200SEED_OK;
+}
+
+int b200seed_pool_process(b200seed_pool* p, b200seed_event_io* events, uint32_t n_events) {
+    if (!p || (!events && n_events)) return B200SEED_EINVAL;
+    {
+        std::lock_guard<std::mutex> lk(p->mu);
+        p->events = events;
+        p->n_events = n_events;
+        p->next.store(0);
+        p->running = int(p->workers.size());
+        ++p->generation;
+    }
+    p->cv_job.notify_all();
+    {
+        std::unique_lock<std::mutex> lk(p->mu);
+        p->cv_done.wait(lk, [&] { return p->running == 0; });
+    }
+    for (uint32_t i = 0; i < n_events; ++i)
+        if (events[i].status != B200SEED_OK) {
+            p->error = "event " + std::to_string(i) + " failed with status " + std::to_string(events[i].status);
+            return events[i].status;
+        }
+    return B200SEED_OK;
+}
+
+const char* b200seed_pool_last_error(const b200seed_pool* p) {
+    return p ? p->error.c_str() : g_create_error.c_str();
+}
+
+void b200seed_pool_destroy(b200seed_pool* p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(p->mu);
+        p->stop = true;
+    }
+    p->cv_job.notify_all();
+    for (auto& w : p->workers) {
+        if (w.th.joinable()) w.th.join();
+        for (auto& sl : w.slot) {
+            if (sl.s) cudaStreamDestroy(sl.s);
+            if (sl.h) b200seed_destroy(sl.h);
+        }
+    }
+    delete p;
+}
+
+int b200seed_run_host(b200seed_handle* h, void* stream, uint32_t n_sp, const float* h_xyz,
+                      const float* h_var_z, const float* h_var_r,
+                      const uint32_t* h_sp_meas_index_1, uint32_t n_meas,
+                      const float* h_meas_local, const uint64_t* h_meas_surface,
+                      const float bfield[3], uint32_t seed_capacity, uint32_t* h_bottom,
+                      uint32_t* h_middle, uint32_t* h_top, float* h_quality,
+                      b200seed_bound_params* h_params, uint32_t* h_n_seeds,
+                      b200seed_counters* h_counters) {
+    if (!h) return B200SEED_EINVAL;
+    if (!h_n_seeds) return fail(h, B200SEED_EINVAL, "b200seed_run_host: h_n_seeds is null");
+    if (h_params && !bfield) return fail(h, B200SEED_EINVAL, "b200seed_run_host: bfield is null");
+    HostEvent e;
+    e.n_sp = n_sp, e.n_meas = n_meas, e.seed_capacity = seed_capacity;
+    e.h_xyz = h_xyz, e.h_var_z = h_var_z, e.h_var_r = h_var_r, e.h_smi = h_sp_meas_index_1;
+    e.h_ml = h_meas_local, e.h_ms = h_meas_surface;
+    if (bfield) e.bfield[0] = bfield[0], e.bfield[1] = bfield[1], e.bfield[2] = bfield[2];
+    e.h_bottom = h_bottom, e.h_middle = h_middle, e.h_top = h_top, e.h_quality = h_quality;
+    e.h_params = h_params;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    *h_n_seeds = 0;
+    if (h_counters) std::memset(h_counters, 0, sizeof(*h_counters));
+    int rc = host_submit(h, s, e);
+    if (rc != B200SEED_OK) return rc;
+    return host_finish(h, s, e, h_n_seeds, h_counters);
 }
 
 // Measured non-fused FP32 rate of the device (ops/s) — the denominator bench.py uses for the

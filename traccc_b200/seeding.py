@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (B200SeedError, Counters, WsLayout, seedfilter_config, seedfinder_config,
+from ._lib import (B200SeedError, Counters, EventIO, WsLayout, seedfilter_config, seedfinder_config,
                    spacepoint_grid_config, track_params_estimation_config)
 
 BOUND_PARAMS_DTYPE = np.dtype([("surface_link", "<u8"), ("vec", "<f4", (6,)),
@@ -407,5 +407,87 @@ class HostPipeline:
                "quality": self._out["quality"][:ns].numpy()}
         if with_params:   # zero-copy view of the pinned output buffer
             res["params"] = self._out["params"][: ns * BOUND_PARAMS_DTYPE.itemsize].numpy().view(
+                BOUND_PARAMS_DTYPE)
+        return res
+
+
+class EventPool:
+    """b200seed_pool: the native host side of a throughput job on one device (worker threads
+    with two algorithm instances / streams each) — what the reference's multi-threaded
+    throughput application does around the algorithms
+    (examples/run/common/include/traccc/examples/impl/throughput_mt.ipp:170-298)."""
+
+    def __init__(self, finder_config=None, grid_config=None, filter_config=None, tpe_config=None,
+                 device: int = 0, n_workers: int = 8):
+        self.finder = finder_config or seedfinder_config()
+        self.grid = grid_config or spacepoint_grid_config(self.finder)
+        self.filter = filter_config or seedfilter_config()
+        self.tpe = tpe_config or track_params_estimation_config()
+        self.lib = _lib.lib()
+        if not torch.cuda.is_available():
+            raise B200SeedError("no CUDA device: the seeding path has no CPU fallback")
+        p = C.c_void_p()
+        _lib.check(self.lib.b200seed_pool_create(C.byref(self.finder), C.byref(self.grid),
+                                                 C.byref(self.filter), C.byref(self.tpe), int(device),
+                                                 int(n_workers), C.byref(p)), None)
+        self.p = p
+        self._keep = []
+
+    def __del__(self):
+        p = getattr(self, "p", None)
+        if p:
+            self.lib.b200seed_pool_destroy(p)
+            self.p = None
+
+    def make_batch(self, events, with_params: bool = True):
+        """Pinned host buffers + the b200seed_event_io array for a list of ToyEvent-like
+        objects. Returns (io_array, outputs) where outputs[i] holds the pinned result tensors."""
+        K = max(int(self.finder.maxSeedsPerSpM), 1)
+        ios = (EventIO * len(events))()
+        outs = []
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        for i, e in enumerate(events):
+            n = e.n_spacepoints
+            cap = max(n * K, 1)
+            inp = (pin(e.xyz), pin(e.var_z), pin(e.var_r), pin(e.meas_index.view(np.int32)),
+                   pin(e.meas_local), pin(e.meas_surface.view(np.int64)))
+            out = {"bottom": torch.empty(cap, dtype=torch.int32, pin_memory=True),
+                   "middle": torch.empty(cap, dtype=torch.int32, pin_memory=True),
+                   "top": torch.empty(cap, dtype=torch.int32, pin_memory=True),
+                   "quality": torch.empty(cap, dtype=torch.float32, pin_memory=True),
+                   "params": torch.empty(cap * BOUND_PARAMS_DTYPE.itemsize, dtype=torch.uint8,
+                                         pin_memory=True) if with_params else None}
+            io = ios[i]
+            io.n_spacepoints, io.n_measurements = n, int(e.meas_local.shape[0])
+            io.xyz, io.var_z, io.var_r = inp[0].data_ptr(), inp[1].data_ptr(), inp[2].data_ptr()
+            io.sp_meas_index_1, io.meas_local, io.meas_surface = (inp[3].data_ptr(), inp[4].data_ptr(),
+                                                                  inp[5].data_ptr())
+            for k in range(3):
+                io.bfield[k] = float(e.bfield[k])
+            io.seed_capacity = cap
+            io.bottom, io.middle, io.top = (out["bottom"].data_ptr(), out["middle"].data_ptr(),
+                                            out["top"].data_ptr())
+            io.quality = out["quality"].data_ptr()
+            io.params = out["params"].data_ptr() if with_params else None
+            self._keep.append((inp, out))
+            outs.append(out)
+        return ios, outs
+
+    def process(self, ios):
+        rc = self.lib.b200seed_pool_process(self.p, ios, len(ios))
+        if rc < 0:
+            msg = self.lib.b200seed_pool_last_error(self.p)
+            raise B200SeedError(f"b200seed error {rc}: {msg.decode() if msg else ''}")
+
+    @staticmethod
+    def result(io, out) -> dict:
+        ns = int(io.n_seeds)
+        res = {"n_seeds": ns, "counters": io.counters.as_dict(),
+               "bottom": out["bottom"][:ns].numpy().view(np.uint32),
+               "middle": out["middle"][:ns].numpy().view(np.uint32),
+               "top": out["top"][:ns].numpy().view(np.uint32),
+               "quality": out["quality"][:ns].numpy()}
+        if out["params"] is not None:
+            res["params"] = out["params"][: ns * BOUND_PARAMS_DTYPE.itemsize].numpy().view(
                 BOUND_PARAMS_DTYPE)
         return res
