@@ -167,6 +167,57 @@ def ref_lib():
     return _ref
 
 
+REF_SEEDING_LIB_PATH = os.path.join(_HERE, "_ref", "libtraccc_ref_seeding.so")
+_ref_seeding = None
+
+
+def ref_seeding_lib():
+    """oracle/_ref/libtraccc_ref_seeding.so: the reference's host::seeding_algorithm sources
+    compiled verbatim (oracle/ref_seeding.cpp). None when it was never built."""
+    global _ref_seeding
+    if _ref_seeding is None:
+        if not os.path.exists(REF_SEEDING_LIB_PATH):
+            if os.path.isdir("/root/reference/core/include/traccc"):
+                subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+            else:
+                return None
+        R = C.CDLL(REF_SEEDING_LIB_PATH)
+        R.ref_seeding_run.restype = C.c_long
+        R.ref_seeding_run.argtypes = [C.POINTER(FinderCfg), C.POINTER(GridCfg), C.POINTER(FilterCfg),
+                                      C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _ref_seeding = R
+    return _ref_seeding
+
+
+def ref_run(xyz, var_z=None, var_r=None, finder=None, grid=None, filt=None) -> dict | None:
+    """traccc::host::seeding_algorithm — the reference's own code — on one event.
+    Returns the seed columns, or None when oracle/_ref is not available."""
+    R = ref_seeding_lib()
+    if R is None:
+        return None
+    d = default_configs()
+    finder = finder or d[0]
+    if grid is None:
+        grid = GridCfg()
+        lib().oracle_grid_cfg_from_finder(C.byref(finder), C.byref(grid))
+    filt = filt or d[2]
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+    n = xyz.shape[0]
+    vz = None if var_z is None else np.ascontiguousarray(var_z, dtype=np.float32)
+    vr = None if var_r is None else np.ascontiguousarray(var_r, dtype=np.float32)
+    cap = max(1, n * max(1, int(finder.maxSeedsPerSpM)))
+    out = {k: np.empty(cap, np.uint32) for k in ("bottom", "middle", "top")}
+    out["quality"] = np.empty(cap, np.float32)
+    ns = R.ref_seeding_run(C.byref(finder), C.byref(grid), C.byref(filt), n, _ptr(xyz), _ptr(vz), _ptr(vr),
+                           cap, _ptr(out["bottom"]), _ptr(out["middle"]), _ptr(out["top"]),
+                           _ptr(out["quality"]))
+    if ns < 0:
+        raise ValueError("get_axes: std::domain_error in the reference")
+    assert ns <= cap
+    return {k: v[:ns].copy() for k, v in out.items()}
+
+
 def default_configs():
     """(finder, grid, filter, tpe) with the reference's in-class defaults."""
     L = lib()

@@ -1,6 +1,8 @@
 #pragma once
-#include <vector>
+#include "vecmem/containers/vector.hpp"
 namespace detray {
 using dindex = unsigned int;
-using dindex_sequence = std::vector<dindex>;
+template <typename T>
+using dvector = vecmem::vector<T>;
+using dindex_sequence = dvector<dindex>;
 }

@@ -11,3 +11,4 @@ struct jagged_vector_view {
     jagged_vector_view(const O& o) : m_size(o.m_size), m_ptr(reinterpret_cast<vector_view<T>*>(o.m_ptr)) {}
 };
 }
+#include "vecmem/containers/data/jagged_vector_data.hpp"

@@ -88,6 +88,11 @@ def _check_event(ev, finder=None, filt=None, grid=None, dump=True, stage_cap=0):
         print(f"seed {i}: gpu=({s['bottom'][i]},{s['middle'][i]},{s['top'][i]},{s['quality'][i]}) "
               f"cpu=({r['bottom'][i]},{r['middle'][i]},{r['top'][i]},{r['quality'][i]})")
     assert len(bad) == 0, f"{len(bad)} of {n_ref} seeds differ"
+    # (4b) and against the reference's own host code (oracle/_ref, when it was built)
+    ref_code = oracle.ref_run(ev.xyz, ev.var_z, ev.var_r, finder=of, grid=og, filt=ofl)
+    if ref_code is not None:
+        for k in ("bottom", "middle", "top", "quality"):
+            assert np.array_equal(s[k].view(np.uint32), ref_code[k].view(np.uint32)), k
     # (5) track parameters within 1e-5 relative; surface link and local position exact
     if n_ref:
         p, q = got["params"], ref.params
