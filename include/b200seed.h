@@ -298,16 +298,19 @@ void b200seed_pool_destroy(b200seed_pool* pool);
  *   sp_xyzr     : float4[n_valid]      {x, y, z, radius} per sorted position
  *   mid_counts  : uint32[2][max_sp]    nMidBot / nMidTop per sorted position (0 if inactive)
  *   mid_offsets : uint32[2][max_sp]    start of each middle's list in the doublet arena
- *                                      (bump-allocated: list order is canonical, the placement
- *                                      of the lists relative to each other is not)
+ *                                      (bump-allocated: the placement of the lists relative
+ *                                      to each other is arbitrary)
  *   doublets    : 32-byte records [2][max_doublets]: {cotTheta, iDeltaR, Er, U, V, Zo,
  *                 radius of the other spacepoint, sorted position of the other spacepoint};
- *                 mid-bottom lists are in the reference's order; mid-top lists are sorted by
- *                 cotTheta and carry their canonical index (u32 bits) in the Zo slot
+ *                 mid-bottom lists are stored in order of discovery; mid-top lists are sorted
+ *                 by cotTheta and carry, in the Zo slot (u32 bits), the key that orders the
+ *                 partners of a middle like the reference's loops do:
+ *                 (position of the partner's phi bin in the neighbour walk) * n_valid +
+ *                 sorted position
  *   triplet_dump: 32-byte records {sorted pos bottom, middle, top (u32), index of the
- *                 mid-bottom doublet, index of the mid-top doublet (u32), curvature, weight
- *                 after the compatible-seed bonus, z_vertex (f32)} in no particular order;
- *                 filled only when dumping is enabled. */
+ *                 mid-bottom doublet in its stored list, key of the mid-top doublet (u32),
+ *                 curvature, weight after the compatible-seed bonus, z_vertex (f32)} in no
+ *                 particular order; filled only when dumping is enabled. */
 typedef struct b200seed_ws_layout {
     size_t bin_offsets;
     size_t sorted_index;
