@@ -50,6 +50,8 @@ def parse_args():
                     help="host worker threads of the end-to-end leg (2 events in flight each)")
     ap.add_argument("--particles", type=int, default=N_PARTICLES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true",
+                    help="skip timing the reference's own CUDA seeding code (oracle/_ref)")
     ap.add_argument("--profile-one", action="store_true",
                     help="run a single event once (for ncu) and exit")
     return ap.parse_args()
@@ -174,6 +176,48 @@ def run_reference(args):
                     "d2h_bytes_per_step": 0},
             "spacepoints_per_second": ev_per_s * float(np.mean([e.n_spacepoints for e in events]))}
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------
+# the reference's own CUDA seeding code (oracle/_ref/libtraccc_ref_cuda.so: the sources of
+# traccc::cuda::triplet_seeding_algorithm compiled verbatim, see oracle/ref_cuda_seeding.cu)
+# on the same events and the same GPU — a reported baseline ("reference CUDA seeding
+# throughput" of the north star), never part of the product path.
+# ----------------------------------------------------------------------------------
+def ref_cuda_baseline(events, reps=12, threads=8):
+    from oracle import oracle
+    if oracle.ref_cuda_lib() is None:
+        return {"unavailable": "oracle/_ref/libtraccc_ref_cuda.so not built (no /root/reference at build time)"}
+    out = {"what": "traccc::cuda::triplet_seeding_algorithm (seeding only, no parameter estimation), "
+                   "spacepoints resident on the device, timed as seeding_example_cuda.cpp:281-291 does "
+                   "(algorithm + stream synchronize, host clock); nvcc --use_fast_math -O2 -DNDEBUG "
+                   "sm_100a, vecmem replaced by oracle/shim_cuda", "unit": UNIT}
+    for key, caching in (("single_instance_cudaMalloc", False), ("single_instance_caching_mr", True)):
+        r = oracle.RefCudaSeeding(caching=caching)
+        r.upload(events[0].xyz, events[0].var_z, events[0].var_r)
+        r.run(3)
+        ms = r.run(reps)
+        out[key] = 1e3 / ms
+        out["n_seeds_event0"] = len(r.seeds()["bottom"])
+        r.close()
+    inst = []
+    for t in range(threads):
+        r = oracle.RefCudaSeeding(caching=True)
+        e = events[t % len(events)]
+        r.upload(e.xyz, e.var_z, e.var_r)
+        r.run(2)
+        inst.append(r)
+    th = [threading.Thread(target=r.run, args=(reps,)) for r in inst]
+    t0 = time.perf_counter()
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    out[f"{threads}_host_threads_caching_mr"] = threads * reps / (time.perf_counter() - t0)
+    for r in inst:
+        r.close()
+    out["value"] = max(v for k, v in out.items() if isinstance(v, float))
+    return out
 
 
 # ----------------------------------------------------------------------------------
@@ -464,6 +508,11 @@ def run_b200(args):
             sample = (f"{len(evs)} events x {nb}/78 phi-bins of middles, one event per thread "
                       f"({t:.1f} s), {cpu_what(kind)}")
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample}
+    if rank == 0 and world == 1 and not args.no_ref_cuda:
+        try:
+            line["reference_cuda"] = ref_cuda_baseline(events)
+        except Exception as exc:                      # a baseline must never break the bench line
+            line["reference_cuda"] = {"unavailable": f"{type(exc).__name__}: {exc}"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -218,6 +218,97 @@ def ref_run(xyz, var_z=None, var_r=None, finder=None, grid=None, filt=None) -> d
     return {k: v[:ns].copy() for k, v in out.items()}
 
 
+REF_CUDA_LIB_PATH = os.path.join(_HERE, "_ref", "libtraccc_ref_cuda.so")
+_ref_cuda = None
+
+
+def ref_cuda_lib():
+    """oracle/_ref/libtraccc_ref_cuda.so: the reference's own CUDA seeding algorithm
+    (traccc::cuda::triplet_seeding_algorithm, its nine kernels and host logic) compiled verbatim
+    with nvcc (oracle/ref_cuda_seeding.cu). None when it was never built. Needs a GPU to run."""
+    global _ref_cuda
+    if _ref_cuda is None:
+        if not os.path.exists(REF_CUDA_LIB_PATH):
+            if os.path.isdir("/root/reference/device/cuda/src/seeding"):
+                subprocess.check_call(["make", "-C", _HERE, "ref_cuda"], stdout=subprocess.DEVNULL)
+            else:
+                return None
+        R = C.CDLL(REF_CUDA_LIB_PATH)
+        R.refcuda_create.restype = C.c_void_p
+        R.refcuda_create.argtypes = [C.POINTER(FinderCfg), C.POINTER(GridCfg), C.POINTER(FilterCfg), C.c_int]
+        R.refcuda_destroy.argtypes = [C.c_void_p]
+        R.refcuda_upload.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        R.refcuda_run.restype = C.c_double
+        R.refcuda_run.argtypes = [C.c_void_p, C.c_int]
+        R.refcuda_seeds.restype = C.c_long
+        R.refcuda_seeds.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        R.refcuda_device_allocations.restype = C.c_ulong
+        R.refcuda_device_allocations.argtypes = [C.c_void_p]
+        _ref_cuda = R
+    return _ref_cuda
+
+
+class RefCudaSeeding:
+    """One traccc::cuda::triplet_seeding_algorithm instance (own stream, own memory resources)
+    of the reference's CUDA code. caching=False allocates like seeding_example_cuda
+    (cudaMalloc per buffer), caching=True like the throughput applications."""
+
+    def __init__(self, finder=None, grid=None, filt=None, caching=True):
+        self.R = ref_cuda_lib()
+        if self.R is None:
+            raise RuntimeError("oracle/_ref/libtraccc_ref_cuda.so not built")
+        d = default_configs()
+        self.finder = finder or d[0]
+        if grid is None:
+            grid = GridCfg()
+            lib().oracle_grid_cfg_from_finder(C.byref(self.finder), C.byref(grid))
+        self.grid, self.filt = grid, (filt or d[2])
+        self.h = self.R.refcuda_create(C.byref(self.finder), C.byref(self.grid), C.byref(self.filt),
+                                       1 if caching else 0)
+        if not self.h:
+            raise RuntimeError("refcuda_create failed")
+        self.n = 0
+
+    def upload(self, xyz, var_z=None, var_r=None):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        vz = None if var_z is None else np.ascontiguousarray(var_z, dtype=np.float32)
+        vr = None if var_r is None else np.ascontiguousarray(var_r, dtype=np.float32)
+        self.n = xyz.shape[0]
+        if self.R.refcuda_upload(self.h, self.n, _ptr(xyz), _ptr(vz), _ptr(vr)) != 0:
+            raise RuntimeError("refcuda_upload failed")
+
+    def run(self, reps=1) -> float:
+        """reps x (algorithm + stream synchronize); mean wall-clock ms per event."""
+        ms = self.R.refcuda_run(self.h, reps)
+        if ms < 0:
+            raise RuntimeError("refcuda_run failed")
+        return ms
+
+    def seeds(self) -> dict:
+        cap = max(1, self.n * max(1, int(self.finder.maxSeedsPerSpM) + 1))
+        out = {k: np.empty(cap, np.uint32) for k in ("bottom", "middle", "top")}
+        out["quality"] = np.empty(cap, np.float32)
+        ns = self.R.refcuda_seeds(self.h, cap, _ptr(out["bottom"]), _ptr(out["middle"]),
+                                  _ptr(out["top"]), _ptr(out["quality"]))
+        if ns < 0 or ns > cap:
+            raise RuntimeError(f"refcuda_seeds: {ns}")
+        return {k: v[:ns].copy() for k, v in out.items()}
+
+    def device_allocations(self) -> int:
+        return int(self.R.refcuda_device_allocations(self.h))
+
+    def close(self):
+        if self.h:
+            self.R.refcuda_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def default_configs():
     """(finder, grid, filter, tpe) with the reference's in-class defaults."""
     L = lib()
