@@ -679,7 +679,7 @@ int b200seed_run(b200seed_handle* h, void* stream, uint32_t n_sp, const float* d
         a.cap_t = a.cap_b / 2;
         const size_t smem = size_t(WARPS_PER_CTA) * doublet_smem_words(a.cap_b, a.cap_t) * 4;
         uint32_t grid = (n_sp + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-        const uint32_t max_grid = uint32_t(h->num_sms) * 8;
+        const uint32_t max_grid = uint32_t(h->num_sms) * (32 / WARPS_PER_CTA) * 2;
         if (grid > max_grid) grid = max_grid;
         KernelTimer t(h, s, "doublets");
         k_doublets<<<grid, WARPS_PER_CTA * 32, smem, s>>>(h->dev, a);
@@ -705,7 +705,7 @@ int b200seed_run(b200seed_handle* h, void* stream, uint32_t n_sp, const float* d
         a.list_cap = triplet_list_cap(n_sp);
         const size_t smem = triplet_smem_per_warp(a.list_cap) * WARPS_PER_CTA;
         uint32_t grid = (n_sp + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-        const uint32_t max_grid = uint32_t(h->num_sms) * 6;
+        const uint32_t max_grid = uint32_t(h->num_sms) * (32 / WARPS_PER_CTA) * 3 / 2;
         if (grid > max_grid) grid = max_grid;
         KernelTimer t(h, s, "triplets");
         k_triplets<<<grid, WARPS_PER_CTA * 32, smem, s>>>(h->dev, a);

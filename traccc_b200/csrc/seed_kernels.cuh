@@ -36,7 +36,10 @@ constexpr uint32_t INVALID_BIN = 0xFFFFFFFFu;
 constexpr int BIN_THREADS = 256;    // spacepoints per binning block
 constexpr int SCAN_THREADS = 1024;  // single-CTA scan
 constexpr int SCAN_ITEMS = 4;
-constexpr int WARPS_PER_CTA = 8;
+#ifndef B200_WARPS_PER_CTA
+#define B200_WARPS_PER_CTA 8
+#endif
+constexpr int WARPS_PER_CTA = B200_WARPS_PER_CTA;
 constexpr int MAX_TOPK = 16;        // upper bound on maxSeedsPerSpM
 constexpr int MAX_COMPAT = 8;       // upper bound on compatSeedLimit
 
@@ -374,7 +377,7 @@ __host__ __device__ inline uint32_t doublet_smem_words(uint32_t cap_b, uint32_t 
 //   bottom: a = {cotTheta, iDeltaR, Er, U}  b = {V, Zo,               r_other, pos_other}
 //   top   : a = {cotTheta, iDeltaR, Er, U}  b = {V, bits(canon_key),  r_other, pos_other}
 #ifndef B200_DOUBLET_MIN_CTAS
-#define B200_DOUBLET_MIN_CTAS 4
+#define B200_DOUBLET_MIN_CTAS (32 / B200_WARPS_PER_CTA)
 #endif
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B200_DOUBLET_MIN_CTAS)
 k_doublets(const DevCfg cfg, const DoubletArgs a) {
@@ -808,7 +811,7 @@ __host__ __device__ inline size_t triplet_smem_per_warp(uint32_t list_cap) {
 // The window is conservative (see the margin below), so the accepted set is identical to
 // testing all nMidBot x nMidTop combinations.
 #ifndef B200_TRIPLET_MIN_CTAS
-#define B200_TRIPLET_MIN_CTAS 4
+#define B200_TRIPLET_MIN_CTAS (32 / B200_WARPS_PER_CTA)
 #endif
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B200_TRIPLET_MIN_CTAS)
 k_triplets(const DevCfg cfg, const TripletArgs a) {
@@ -1248,11 +1251,25 @@ k_estimate_params(const b200seed_tpe_cfg cfg, const uint32_t* __restrict__ n_see
                   const float* __restrict__ meas_local, const uint64_t* __restrict__ meas_surface,
                   const float bx, const float by, const float bz,
                   b200seed_bound_params* __restrict__ out) {
+    // Records are 176 B: written one per lane they would cost 32 sectors per store
+    // instruction. Each warp builds its 32 records (5632 contiguous bytes) in shared memory
+    // and streams them out as float4 rows.
+    __shared__ __align__(16) float s_rec[4][32 * 44];
     uint32_t n = *n_seeds_dev;
     if (n > seed_capacity) n = seed_capacity;
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t ib = sd_b[i], im = sd_m[i], it = sd_t[i];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t i0 = blockIdx.x * blockDim.x + warp * 32;  // first seed of this warp
+    if (i0 >= n) return;
+    const uint32_t i = i0 + lane;
+    const bool live = i < n;
+    float* rec = s_rec[warp];
+    {
+        float4* z4 = reinterpret_cast<float4*>(rec);
+#pragma unroll
+        for (int k = 0; k < 11; ++k) z4[k * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+    const uint32_t ib = live ? sd_b[i] : 0u, im = live ? sd_m[i] : 0u, it = live ? sd_t[i] : 0u;
     const V3 p0{xyz[3 * size_t(ib)], xyz[3 * size_t(ib) + 1], xyz[3 * size_t(ib) + 2]};
     const V3 p1{xyz[3 * size_t(im)], xyz[3 * size_t(im) + 1], xyz[3 * size_t(im) + 2]};
     const V3 p2{xyz[3 * size_t(it)], xyz[3 * size_t(it) + 1], xyz[3 * size_t(it) + 2]};
@@ -1284,10 +1301,8 @@ k_estimate_params(const b200seed_tpe_cfg cfg, const uint32_t* __restrict__ n_see
     const float qop = qOverPt / perp2(1.f, invTanTheta);
     const uint32_t mi = sp_meas ? sp_meas[ib] : ib;
 
-    b200seed_bound_params* o = out + i;
-    float2* o2 = reinterpret_cast<float2*>(o);  // 176 bytes = 22 float2, 8-byte aligned
-#pragma unroll
-    for (int k = 0; k < 22; ++k) o2[k] = make_float2(0.f, 0.f);
+    // the record of this lane inside the warp's staging buffer (same layout as the output)
+    b200seed_bound_params* o = reinterpret_cast<b200seed_bound_params*>(rec + lane * 44);
     o->surface_link = meas_surface ? meas_surface[mi] : 0ull;
     o->vec[0] = meas_local ? meas_local[2 * size_t(mi)] : 0.f;
     o->vec[1] = meas_local ? meas_local[2 * size_t(mi) + 1] : 0.f;
@@ -1310,6 +1325,18 @@ k_estimate_params(const b200seed_tpe_cfg cfg, const uint32_t* __restrict__ n_see
         var *= cfg.initial_inflation[j];
         if (j == 3) var_theta = var;
         o->cov[j * 6 + j] = var;
+    }
+    __syncwarp();
+    const uint32_t nrec = (n - i0 < 32u) ? (n - i0) : 32u;
+    float* dst = reinterpret_cast<float*>(out + i0);
+    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(rec);
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (uint32_t k = lane; k < nrec * 11u; k += 32) d4[k] = s4[k];
+    } else {  // caller buffer only 8-byte aligned
+        const float2* s2 = reinterpret_cast<const float2*>(rec);
+        float2* d2 = reinterpret_cast<float2*>(dst);
+        for (uint32_t k = lane; k < nrec * 22u; k += 32) d2[k] = s2[k];
     }
 }
 
