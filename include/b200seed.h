@@ -227,6 +227,54 @@ int b200seed_estimate_params(b200seed_handle* h, void* stream, const uint32_t* d
                              const float* d_meas_local, const uint64_t* d_meas_surface,
                              const float bfield[3], b200seed_bound_params* d_params);
 
+/* ------------------------------------------------------------------------ */
+/* The step before the path: spacepoint formation       */
+/* ------------------------------------------------------------------------ */
+
+/* A placed planar surface: what detray::tracking_surface::local_to_global uses for a 2D
+ * measurement (core/include/traccc/seeding/impl/spacepoint_formation.ipp:34-40) — the
+ * translation and the columns of the rotation of the surface's transform3. The caller
+ * flattens the detector into a table of these, indexed by the surface index that the
+ * measurement's surface_link (detray::geometry::identifier) carries. */
+typedef struct b200seed_surface {
+    float translation[3];
+    float x_axis[3];
+    float y_axis[3];
+    float z_axis[3];
+} b200seed_surface;
+
+/* Replaces device::silicon_pixel_spacepoint_formation_algorithm::operator()
+ * (device/common/src/seeding/silicon_pixel_spacepoint_formation_algorithm.cpp:20-52, kernel
+ * device/common/include/traccc/seeding/device/impl/form_spacepoints.ipp:19-51).
+ * In : measurement columns local_position (stride 2 floats), dimensions (NULL = all 2D) and,
+ *      per measurement, the index of its surface in d_surfaces.
+ * Out: one spacepoint per 2D measurement — global (stride 3 floats), zero variances,
+ *      measurement_index_1 = measurement index, measurement_index_2 = 0xFFFFFFFF — and the
+ *      resizable buffer's size word *d_n_sp. The output columns need room for n_meas entries;
+ *      d_var_z / d_var_r / d_meas_index_1 / d_meas_index_2 may be NULL.
+ * Order: measurement order, i.e. the order of the reference's HOST algorithm
+ * (core/src/seeding/silicon_pixel_spacepoint_formation.hpp:47-59); the reference's device kernel
+ * appends atomically in arbitrary order. Measurements whose surface index is >= n_surfaces are
+ * skipped. Asynchronous on `stream`; n_meas == 0 writes *d_n_sp = 0. */
+int b200seed_form_spacepoints(b200seed_handle* h, void* stream, uint32_t n_meas,
+                              const float* d_meas_local, const uint32_t* d_meas_dim,
+                              const uint32_t* d_meas_surface_index,
+                              const b200seed_surface* d_surfaces, uint32_t n_surfaces, float* d_xyz,
+                              float* d_var_z, float* d_var_r, uint32_t* d_meas_index_1,
+                              uint32_t* d_meas_index_2, uint32_t* d_n_sp);
+
+/* b200seed_run for spacepoints whose number only exists on the device (the size word written
+ * by b200seed_form_spacepoints): max_sp is an upper bound (the capacity of the columns, the
+ * value the workspace is sized for), the kernels read min(*d_n_sp, max_sp). Chains formation
+ * and seeding on one stream without the D->H size read of the reference
+ * (triplet_seeding_algorithm.cpp:64-73). */
+int b200seed_run_n_on_device(b200seed_handle* h, void* stream, uint32_t max_sp,
+                             const uint32_t* d_n_sp, const float* d_xyz, const float* d_var_z,
+                             const float* d_var_r, void* d_workspace, size_t workspace_bytes,
+                             uint32_t seed_capacity, uint32_t* d_bottom, uint32_t* d_middle,
+                             uint32_t* d_top, float* d_quality, uint32_t* d_n_seeds,
+                             b200seed_counters* d_counters);
+
 /* End-to-end convenience with HOST buffers: H->D of the event, seeding, parameter
  * estimation, D->H of seeds + parameters, stream synchronised before returning. This is
  * what seeding_example_cuda.cpp:264-356 does around the two algorithms. Device staging

@@ -111,6 +111,9 @@ class device_allocation {
 // edm::spacepoint_collection::const_view — core/include/traccc/edm/spacepoint_collection.hpp:223-234
 struct spacepoint_const_view {
     std::uint32_t size = 0;
+    // resizable buffers (made on the device by the spacepoint formation): the number of filled
+    // entries is this device word and `size` is the capacity; nullptr for fixed-size views
+    const std::uint32_t* size_ptr = nullptr;
     const std::uint32_t* measurement_index_1 = nullptr;
     const float* global = nullptr;  // std::array<float,3> per spacepoint
     const float* z_variance = nullptr;
@@ -121,6 +124,33 @@ struct measurement_const_view {
     std::uint32_t size = 0;
     const float* local_position = nullptr;        // std::array<float,2>
     const std::uint64_t* surface_link = nullptr;  // detray::geometry::identifier
+    const std::uint32_t* dimensions = nullptr;    // nullptr: all measurements are 2D
+    // index of the measurement's surface in the detector's surface table (the index field of
+    // surface_link); only the spacepoint formation reads it
+    const std::uint32_t* surface_index = nullptr;
+};
+// the part of a detray detector view the spacepoint formation needs: the placed surfaces
+struct detector_view {
+    std::uint32_t n_surfaces = 0;
+    const b200seed_surface* surfaces = nullptr;  // device memory
+};
+// edm::spacepoint_collection::buffer (resizable) returned by the spacepoint formation
+struct spacepoint_buffer {
+    std::uint32_t capacity = 0;
+    std::uint32_t* size = nullptr;  // device: the buffer's size word
+    float* global = nullptr;
+    float* z_variance = nullptr;
+    float* radius_variance = nullptr;
+    std::uint32_t* measurement_index_1 = nullptr;
+    std::uint32_t* measurement_index_2 = nullptr;
+    device_allocation memory;
+    /// vecmem::get_data(buffer): the view the seeding algorithms take
+    operator spacepoint_const_view() const {
+        spacepoint_const_view v;
+        v.size = capacity, v.size_ptr = size, v.measurement_index_1 = measurement_index_1;
+        v.global = global, v.z_variance = z_variance, v.radius_variance = radius_variance;
+        return v;
+    }
 };
 // edm::seed_collection::buffer (resizable) — core/include/traccc/edm/seed_collection.hpp:142-146
 struct seed_buffer {
@@ -198,6 +228,18 @@ class triplet_seeding_algorithm {
         // scratch lives as long as this algorithm object (grown on demand, reused per event)
         const std::size_t need = b200seed_workspace_bytes(m_handle.get(), n);
         if (need > m_workspace.bytes()) m_workspace = device_allocation(*m_mr, need + need / 4);
+        if (spacepoints.size_ptr && n) {
+            // resizable input: its size stays on the device, no D->H read
+            detail::check(
+                b200seed_run_n_on_device(m_handle.get(), m_stream.cudaStream(), n,
+                                         spacepoints.size_ptr, spacepoints.global,
+                                         spacepoints.z_variance, spacepoints.radius_variance,
+                                         m_workspace.get(), m_workspace.bytes(), out.capacity,
+                                         out.bottom_index, out.middle_index, out.top_index,
+                                         out.quality, out.size, out.counters),
+                m_handle.get());
+            return out;
+        }
         detail::check(b200seed_run(m_handle.get(), m_stream.cudaStream(), n, spacepoints.global,
                                    spacepoints.z_variance, spacepoints.radius_variance,
                                    m_workspace.get(), m_workspace.bytes(), out.capacity,
@@ -213,6 +255,53 @@ class triplet_seeding_algorithm {
     memory_resource* m_mr;
     stream_wrapper m_stream;
     mutable device_allocation m_workspace;
+};
+
+/// Drop-in for traccc::cuda::silicon_pixel_spacepoint_formation_algorithm
+/// (device/cuda/include/traccc/cuda/seeding/silicon_pixel_spacepoint_formation_algorithm.hpp;
+/// common part device/common/src/seeding/silicon_pixel_spacepoint_formation_algorithm.cpp:20-52)
+/// = algorithm<edm::spacepoint_collection::buffer(const detector_buffer&,
+///                                               const edm::measurement_collection::const_view&)>.
+/// Spacepoints come out in measurement order (the reference's host algorithm's order).
+class silicon_pixel_spacepoint_formation_algorithm {
+    public:
+    using output_type = spacepoint_buffer;
+
+    silicon_pixel_spacepoint_formation_algorithm(memory_resource& mr, const stream_wrapper& str)
+        : m_mr(&mr), m_stream(str) {
+        const seedfinder_config f;
+        m_handle = detail::make_handle(f, spacepoint_grid_config(f), seedfilter_config(), nullptr);
+    }
+
+    output_type operator()(const detector_view& det,
+                           const measurement_const_view& measurements) const {
+        spacepoint_buffer out;
+        const std::uint32_t n = measurements.size;
+        if (n == 0) return out;  // "If there are no measurements, return right away" (:37-40)
+        out.capacity = n;
+        const std::size_t col = detail::up256(std::size_t(n) * 4);
+        out.memory = device_allocation(*m_mr, 256 + detail::up256(std::size_t(n) * 12) + 4 * col);
+        auto* base = static_cast<unsigned char*>(out.memory.get());
+        out.size = reinterpret_cast<std::uint32_t*>(base);
+        out.global = reinterpret_cast<float*>(base + 256);
+        unsigned char* c = base + 256 + detail::up256(std::size_t(n) * 12);
+        out.z_variance = reinterpret_cast<float*>(c);
+        out.radius_variance = reinterpret_cast<float*>(c + col);
+        out.measurement_index_1 = reinterpret_cast<std::uint32_t*>(c + 2 * col);
+        out.measurement_index_2 = reinterpret_cast<std::uint32_t*>(c + 3 * col);
+        detail::check(b200seed_form_spacepoints(
+                          m_handle.get(), m_stream.cudaStream(), n, measurements.local_position,
+                          measurements.dimensions, measurements.surface_index, det.surfaces,
+                          det.n_surfaces, out.global, out.z_variance, out.radius_variance,
+                          out.measurement_index_1, out.measurement_index_2, out.size),
+                      m_handle.get());
+        return out;
+    }
+
+    private:
+    std::unique_ptr<b200seed_handle, detail::handle_deleter> m_handle;
+    memory_resource* m_mr;
+    stream_wrapper m_stream;
 };
 
 /// Drop-in for traccc::cuda::seed_parameter_estimation_algorithm (homogeneous field).

@@ -101,6 +101,9 @@ def lib() -> C.CDLL:
         L.oracle_copy_params.argtypes = [C.c_void_p] * 2
         L.oracle_estimate_params.argtypes = [C.c_void_p, C.POINTER(TpeCfg)] + [C.c_void_p] * 5
         L.oracle_estimate_params_for.argtypes = [C.POINTER(TpeCfg), C.c_uint32] + [C.c_void_p] * 9
+        L.oracle_form_spacepoints.restype = C.c_uint32
+        L.oracle_form_spacepoints.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_uint32] + [C.c_void_p] * 5
         L.oracle_selftest_atan2f.restype = C.c_uint64
         L.oracle_selftest_atan2f.argtypes = [C.c_uint64, C.c_float, C.c_uint64]
         L.oracle_atan2f_fdlibm.restype = C.c_float
@@ -430,3 +433,21 @@ def estimate_params_for(bottom, middle, top, xyz, bfield, tpe=None, sp_meas_inde
     L.oracle_estimate_params_for(C.byref(tpe), len(b), _ptr(b), _ptr(m), _ptr(t), _ptr(xyz),
                                  _ptr(smi), _ptr(ml), _ptr(ms), _ptr(bf), _ptr(out))
     return out
+
+
+def form_spacepoints(meas_local, meas_dim, meas_surface_index, surfaces) -> dict:
+    """host silicon_pixel_spacepoint_formation (core/src/seeding/silicon_pixel_spacepoint_formation.hpp:33-62)
+    over a flat surface table (S,12) f32 = translation | x | y | z axes."""
+    local = np.ascontiguousarray(meas_local, np.float32)
+    m = local.shape[0]
+    dim = None if meas_dim is None else np.ascontiguousarray(meas_dim, np.uint32)
+    sidx = np.ascontiguousarray(meas_surface_index, np.uint32)
+    surf = np.ascontiguousarray(surfaces, np.float32)
+    xyz = np.zeros((max(m, 1), 3), np.float32)
+    vz, vr = np.ones(max(m, 1), np.float32), np.ones(max(m, 1), np.float32)
+    mi1, mi2 = np.zeros(max(m, 1), np.uint32), np.zeros(max(m, 1), np.uint32)
+    n = lib().oracle_form_spacepoints(m, _ptr(local), _ptr(dim) if dim is not None else None, _ptr(sidx),
+                                      _ptr(surf), surf.shape[0], _ptr(xyz), _ptr(vz), _ptr(vr),
+                                      _ptr(mi1), _ptr(mi2))
+    return {"xyz": xyz[:n].copy(), "z_variance": vz[:n].copy(), "radius_variance": vr[:n].copy(),
+            "measurement_index_1": mi1[:n].copy(), "measurement_index_2": mi2[:n].copy()}

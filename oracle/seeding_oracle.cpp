@@ -1190,4 +1190,36 @@ void oracle_copy_params(const oracle_result* r, b200seed_bound_params* p) {
     COPY(r->params, p);
 }
 
+// Spacepoint formation — the host loop of
+// core/src/seeding/silicon_pixel_spacepoint_formation.hpp:33-62 with
+// details::is_valid_measurement / fill_pixel_spacepoint
+// (core/include/traccc/seeding/impl/spacepoint_formation.ipp:17-47): one spacepoint per 2D
+// measurement, in measurement order, global = surface.local_to_global(local), zero variances,
+// measurement_index_1 = i, measurement_index_2 = INVALID. detray's local_to_global for a planar
+// surface is transform3::point_to_global({l0, l1, 0}) = rotation * p + translation (third-party
+// code, absent here: restated as (x_axis * l0 + y_axis * l1) + translation per component —
+// "parity unpinned" at the last ulp, see the file header). dim == NULL: all 2D. A surface index
+// outside the table skips the measurement (the reference would read out of bounds).
+// Returns the number of spacepoints.
+uint32_t oracle_form_spacepoints(uint32_t n_meas, const float* local, const uint32_t* dim,
+                                 const uint32_t* surface_index, const b200seed_surface* surfaces,
+                                 uint32_t n_surfaces, float* xyz, float* var_z, float* var_r,
+                                 uint32_t* mi1, uint32_t* mi2) {
+    uint32_t n = 0;
+    for (uint32_t i = 0; i < n_meas; ++i) {
+        if (dim && dim[i] != 2u) continue;
+        if (surface_index[i] >= n_surfaces) continue;
+        const b200seed_surface& S = surfaces[surface_index[i]];
+        const float l0 = local[2 * size_t(i)], l1 = local[2 * size_t(i) + 1];
+        for (int k = 0; k < 3; ++k)
+            xyz[3 * size_t(n) + k] = (S.x_axis[k] * l0 + S.y_axis[k] * l1) + S.translation[k];
+        if (var_z) var_z[n] = 0.f;
+        if (var_r) var_r[n] = 0.f;
+        if (mi1) mi1[n] = i;
+        if (mi2) mi2[n] = 0xFFFFFFFFu;
+        ++n;
+    }
+    return n;
+}
+
 }  // extern "C"

@@ -152,6 +152,66 @@ static int config_errors() {
     return 0;
 }
 
+// TEST(spacepoint_formation, cpu) — tests/cpu/test_spacepoint_formation.cpp:24-102: a telescope
+// of nine planes along x (normal = x, local x = global y, local y = global z), a measurement
+// (7, 2) on the first and (10, 15) on the last plane -> spacepoints (20, 7, 2), (180, 10, 15);
+// a 1D measurement in between must be skipped.
+static int formation_case() {
+    cudaStream_t s;
+    CHECK(cudaStreamCreate(&s) == cudaSuccess);
+    stream_wrapper stream(s);
+    cuda_device_memory_resource mr;
+    const float pos[9] = {20.f, 40.f, 60.f, 80.f, 100.f, 120.f, 140.f, 160.f, 180.f};
+    std::vector<b200seed_surface> planes(9);
+    for (int i = 0; i < 9; ++i) {
+        std::memset(&planes[i], 0, sizeof(b200seed_surface));
+        planes[i].translation[0] = pos[i];
+        planes[i].x_axis[1] = 1.f, planes[i].y_axis[2] = 1.f, planes[i].z_axis[0] = 1.f;
+    }
+    const float local[6] = {7.f, 2.f, 3.f, 0.f, 10.f, 15.f};
+    const std::uint32_t dims[3] = {2u, 1u, 2u}, sidx[3] = {0u, 4u, 8u};
+    device_allocation d_planes(mr, sizeof(b200seed_surface) * 9), d_local(mr, sizeof(local)),
+        d_dims(mr, sizeof(dims)), d_sidx(mr, sizeof(sidx));
+    cudaMemcpy(d_planes.get(), planes.data(), sizeof(b200seed_surface) * 9, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_local.get(), local, sizeof(local), cudaMemcpyHostToDevice);
+    cudaMemcpy(d_dims.get(), dims, sizeof(dims), cudaMemcpyHostToDevice);
+    cudaMemcpy(d_sidx.get(), sidx, sizeof(sidx), cudaMemcpyHostToDevice);
+    detector_view det;
+    det.n_surfaces = 9, det.surfaces = static_cast<const b200seed_surface*>(d_planes.get());
+    measurement_const_view meas;
+    meas.size = 3, meas.local_position = static_cast<const float*>(d_local.get());
+    meas.dimensions = static_cast<const std::uint32_t*>(d_dims.get());
+    meas.surface_index = static_cast<const std::uint32_t*>(d_sidx.get());
+    silicon_pixel_spacepoint_formation_algorithm sp_formation(mr, stream);
+    auto spacepoints = sp_formation(det, meas);
+    stream.synchronize();
+    std::uint32_t n = 0, mi[2] = {9, 9}, mi2[2] = {0, 0};
+    float g[6], vz[2] = {1.f, 1.f};
+    cudaMemcpy(&n, spacepoints.size, 4, cudaMemcpyDeviceToHost);
+    CHECK(n == 2u);  // EXPECT_EQ(spacepoints.size(), 2u)
+    cudaMemcpy(g, spacepoints.global, sizeof(g), cudaMemcpyDeviceToHost);
+    cudaMemcpy(mi, spacepoints.measurement_index_1, sizeof(mi), cudaMemcpyDeviceToHost);
+    cudaMemcpy(mi2, spacepoints.measurement_index_2, sizeof(mi2), cudaMemcpyDeviceToHost);
+    cudaMemcpy(vz, spacepoints.z_variance, sizeof(vz), cudaMemcpyDeviceToHost);
+    CHECK(g[0] == 20.f && g[1] == 7.f && g[2] == 2.f);
+    CHECK(g[3] == 180.f && g[4] == 10.f && g[5] == 15.f);
+    CHECK(mi[0] == 0u && mi[1] == 2u && mi2[0] == 0xFFFFFFFFu && vz[0] == 0.f && vz[1] == 0.f);
+    // the resizable buffer feeds the seeding algorithm without a size read-back
+    seedfinder_config f;
+    spacepoint_grid_config gcfg(f);
+    triplet_seeding_algorithm sa(f, gcfg, seedfilter_config(), mr, stream);
+    auto seeds = sa(spacepoints);
+    stream.synchronize();
+    std::uint32_t ns = 7;
+    cudaMemcpy(&ns, seeds.size, 4, cudaMemcpyDeviceToHost);
+    CHECK(ns == 0u);
+    // no measurements -> default-constructed buffer
+    auto none = sp_formation(det, measurement_const_view{});
+    CHECK(none.capacity == 0u && none.size == nullptr);
+    cudaStreamDestroy(s);
+    return 0;
+}
+
 int main() {
     const std::vector<float> case1 = {36.6706f, 10.6472f, 104.131f, 94.2191f, 29.6699f, 113.628f,
                                       149.805f, 47.9518f, 122.979f, 218.514f, 70.3049f, 134.029f,
@@ -169,5 +229,7 @@ int main() {
     std::printf("[ OK ] track_params_estimation.helix_positive_charge\n");
     if (config_errors()) return 1;
     std::printf("[ OK ] config errors / empty input\n");
+    if (formation_case()) return 1;
+    std::printf("[ OK ] spacepoint_formation.telescope\n");
     return 0;
 }

@@ -20,4 +20,4 @@ def test_reference_unit_tests_through_adapter():
                          text=True, timeout=120)
     print(out.stdout, out.stderr)
     assert out.returncode == 0
-    assert out.stdout.count("[ OK ]") == 5
+    assert out.stdout.count("[ OK ]") == 6

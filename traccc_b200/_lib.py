@@ -119,6 +119,7 @@ EXPORTS = (
     "b200seed_set_stage_cap", "b200seed_pool_create", "b200seed_pool_process",
     "b200seed_pool_last_error", "b200seed_pool_destroy",
     "b200seed_workspace_bytes", "b200seed_run", "b200seed_estimate_params", "b200seed_run_host",
+    "b200seed_form_spacepoints", "b200seed_run_n_on_device",
     "b200seed_workspace_layout", "b200seed_set_triplet_dump", "b200seed_set_timing",
     "b200seed_get_timings", "b200seed_launches_per_event", "b200seed_measure_fp32_peak",
     "b200seed_version")
@@ -158,6 +159,9 @@ def lib() -> C.CDLL:
     L.b200seed_workspace_bytes.restype = sz
     L.b200seed_workspace_layout.argtypes = [vp, u32, C.POINTER(WsLayout)]
     L.b200seed_run.argtypes = [vp, vp, u32, vp, vp, vp, vp, sz, u32, vp, vp, vp, vp, vp, vp]
+    L.b200seed_run_n_on_device.argtypes = [vp, vp, u32, vp, vp, vp, vp, vp, sz, u32, vp, vp, vp, vp,
+                                           vp, vp]
+    L.b200seed_form_spacepoints.argtypes = [vp, vp, u32, vp, vp, vp, vp, u32, vp, vp, vp, vp, vp, vp]
     L.b200seed_estimate_params.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp, vp, vp,
                                            C.POINTER(C.c_float * 3), vp]
     L.b200seed_run_host.argtypes = [vp, vp, u32, vp, vp, vp, vp, u32, vp, vp,

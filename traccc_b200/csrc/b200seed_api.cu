@@ -76,6 +76,11 @@ struct b200seed_handle {
     void* d_stage = nullptr;
     size_t d_stage_bytes = 0;
     b200seed_counters* h_pinned = nullptr;  // counters + n_seeds read-back
+    // look-back state of b200seed_form_spacepoints (status words + ticket counter)
+    unsigned long long* d_form = nullptr;
+    size_t form_tiles = 0;
+    unsigned long long form_ticket_base = 0;
+    uint32_t form_epoch = 0;
 };
 
 namespace {
@@ -478,6 +483,7 @@ void b200seed_destroy(b200seed_handle* h) {
         cudaEventDestroy(s.stop);
     }
     if (h->d_stage) cudaFree(h->d_stage);
+    if (h->d_form) cudaFree(h->d_form);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     delete h;
 }
@@ -583,11 +589,16 @@ int b200seed_launches_per_event(const b200seed_handle*, int with_params) {
     return 8 + (with_params ? 1 : 0);
 }
 
-int b200seed_run(b200seed_handle* h, void* stream, uint32_t n_sp, const float* d_xyz,
-                 const float* d_var_z, const float* d_var_r, void* d_workspace,
-                 size_t workspace_bytes, uint32_t seed_capacity, uint32_t* d_bottom,
-                 uint32_t* d_middle, uint32_t* d_top, float* d_quality, uint32_t* d_n_seeds,
-                 b200seed_counters* d_counters) {
+}  // extern "C"
+
+namespace {
+// b200seed_run / b200seed_run_n_on_device: n_sp is the number of spacepoints, or — when
+// d_n_sp != nullptr — an upper bound of the number stored in *d_n_sp on the device.
+int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_n_sp,
+             const float* d_xyz, const float* d_var_z, const float* d_var_r, void* d_workspace,
+             size_t workspace_bytes, uint32_t seed_capacity, uint32_t* d_bottom,
+             uint32_t* d_middle, uint32_t* d_top, float* d_quality, uint32_t* d_n_seeds,
+             b200seed_counters* d_counters) {
     if (!h) return B200SEED_EINVAL;
     if (!d_n_seeds) return fail(h, B200SEED_EINVAL, "b200seed_run: d_n_seeds is null");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -640,7 +651,7 @@ int b200seed_run(b200seed_handle* h, void* stream, uint32_t n_sp, const float* d
     {
         KernelTimer t(h, s, "bin_count");
         k_bin_count<<<nblk, BIN_THREADS, h->nbins * sizeof(uint32_t), s>>>(
-            h->dev, L.g, n_sp, d_xyz, bin_of, blk_hist, cell_cnt, h->nbins, nblk);
+            h->dev, L.g, n_sp, d_xyz, bin_of, blk_hist, cell_cnt, h->nbins, nblk, d_n_sp);
     }
     {
         KernelTimer t(h, s, "scan_bins");
@@ -655,7 +666,8 @@ int b200seed_run(b200seed_handle* h, void* stream, uint32_t n_sp, const float* d
         KernelTimer t(h, s, "bin_scatter");
         k_bin_scatter<<<nblk, BIN_THREADS, 0, s>>>(h->dev, L.g, n_sp, d_xyz, d_var_z, d_var_r, bin_of,
                                                    blk_hist, nblk, sp4, var2, sorted_index,
-                                                   sorted_bin, cell_off, cell_cnt, csp4, ccanon);
+                                                   sorted_bin, cell_off, cell_cnt, csp4, ccanon,
+                                                   d_n_sp);
     }
     {
         DoubletArgs a{};
@@ -720,8 +732,79 @@ int b200seed_run(b200seed_handle* h, void* stream, uint32_t n_sp, const float* d
         KernelTimer t(h, s, "seed_gather");
         k_seed_gather<<<(n_sp + 255) / 256, 256, 0, s>>>(
             n_sp, K, ctrl, seed_cnt, seed_off, seed_b, seed_t, seed_w, sorted_index, seed_capacity,
-            d_bottom, d_middle, d_top, d_quality, d_n_seeds, d_counters);
+            d_bottom, d_middle, d_top, d_quality, d_n_seeds, d_counters, d_n_sp);
     }
+    CUDA_TRY(h, cudaGetLastError());
+    return B200SEED_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int b200seed_run(b200seed_handle* h, void* stream, uint32_t n_sp, const float* d_xyz,
+                 const float* d_var_z, const float* d_var_r, void* d_workspace,
+                 size_t workspace_bytes, uint32_t seed_capacity, uint32_t* d_bottom,
+                 uint32_t* d_middle, uint32_t* d_top, float* d_quality, uint32_t* d_n_seeds,
+                 b200seed_counters* d_counters) {
+    return run_impl(h, stream, n_sp, nullptr, d_xyz, d_var_z, d_var_r, d_workspace, workspace_bytes,
+                    seed_capacity, d_bottom, d_middle, d_top, d_quality, d_n_seeds, d_counters);
+}
+
+int b200seed_run_n_on_device(b200seed_handle* h, void* stream, uint32_t max_sp,
+                             const uint32_t* d_n_sp, const float* d_xyz, const float* d_var_z,
+                             const float* d_var_r, void* d_workspace, size_t workspace_bytes,
+                             uint32_t seed_capacity, uint32_t* d_bottom, uint32_t* d_middle,
+                             uint32_t* d_top, float* d_quality, uint32_t* d_n_seeds,
+                             b200seed_counters* d_counters) {
+    if (h && !d_n_sp) return fail(h, B200SEED_EINVAL, "b200seed_run_n_on_device: d_n_sp is null");
+    return run_impl(h, stream, max_sp, d_n_sp, d_xyz, d_var_z, d_var_r, d_workspace, workspace_bytes,
+                    seed_capacity, d_bottom, d_middle, d_top, d_quality, d_n_seeds, d_counters);
+}
+
+int b200seed_form_spacepoints(b200seed_handle* h, void* stream, uint32_t n_meas,
+                              const float* d_meas_local, const uint32_t* d_meas_dim,
+                              const uint32_t* d_meas_surface_index,
+                              const b200seed_surface* d_surfaces, uint32_t n_surfaces, float* d_xyz,
+                              float* d_var_z, float* d_var_r, uint32_t* d_meas_index_1,
+                              uint32_t* d_meas_index_2, uint32_t* d_n_sp) {
+    if (!h) return B200SEED_EINVAL;
+    if (!d_n_sp) return fail(h, B200SEED_EINVAL, "b200seed_form_spacepoints: d_n_sp is null");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (n_meas == 0) {
+        // "If there are no measurements, return right away"
+        // (silicon_pixel_spacepoint_formation_algorithm.cpp:37-40)
+        CUDA_TRY(h, cudaMemsetAsync(d_n_sp, 0, sizeof(uint32_t), s));
+        return B200SEED_OK;
+    }
+    if (!d_meas_local || !d_meas_surface_index || !d_surfaces || !d_xyz)
+        return fail(h, B200SEED_EINVAL, "b200seed_form_spacepoints: null device pointer");
+    const size_t tiles = (size_t(n_meas) + FORM_THREADS - 1) / FORM_THREADS;
+    if (tiles > h->form_tiles) {
+        // grows rarely; a fresh buffer is zero == "epoch 0", which no call ever uses
+        CUDA_TRY(h, cudaStreamSynchronize(s));
+        if (h->d_form) CUDA_TRY(h, cudaFree(h->d_form));
+        h->d_form = nullptr;
+        h->form_tiles = 0;
+        const size_t want = tiles + tiles / 2 + 64;
+        CUDA_TRY(h, cudaMalloc(&h->d_form, (want + 1) * sizeof(unsigned long long)));
+        CUDA_TRY(h, cudaMemset(h->d_form, 0, (want + 1) * sizeof(unsigned long long)));
+        h->form_tiles = want;
+        h->form_ticket_base = 0;
+        h->form_epoch = 0;
+    }
+    if (++h->form_epoch >= (1u << 30)) {  // epoch field is 30 bits wide: start over
+        CUDA_TRY(h, cudaMemsetAsync(h->d_form + 1, 0, h->form_tiles * sizeof(unsigned long long), s));
+        h->form_epoch = 1;
+    }
+    {
+        KernelTimer t(h, s, "form_spacepoints");
+        k_form_spacepoints<<<uint32_t(tiles), FORM_THREADS, 0, s>>>(
+            n_meas, d_meas_local, d_meas_dim, d_meas_surface_index, d_surfaces, n_surfaces, d_xyz,
+            d_var_z, d_var_r, d_meas_index_1, d_meas_index_2, d_n_sp, h->d_form + 1, h->d_form,
+            h->form_ticket_base, h->form_epoch);
+    }
+    h->form_ticket_base += tiles;
     CUDA_TRY(h, cudaGetLastError());
     return B200SEED_OK;
 }

@@ -76,15 +76,129 @@ struct __align__(16) TripletDumpRec {
 };
 
 // ---------------------------------------------------------------------------
+// (0) spacepoint formation from 2D measurements — the step before seeding
+//     (core/include/traccc/seeding/impl/spacepoint_formation.ipp:21-47, host loop
+//     core/src/seeding/silicon_pixel_spacepoint_formation.hpp:33-62, device kernel
+//     device/common/.../impl/form_spacepoints.ipp:19-51).
+// One thread per measurement; global = translation + l0 * x_axis + l1 * y_axis of the placed
+// surface. The reference's device kernel appends with an atomic (random order); here the valid
+// measurements are compacted in measurement order — the HOST algorithm's order — by a
+// single-pass scan with decoupled look-back: every CTA publishes its count, then the
+// inclusive prefix, in one 64-bit status word {epoch:30, state:2, value:32}. The epoch and the
+// ticket base advance on the host with every call, so nothing has to be cleared between events.
+// ---------------------------------------------------------------------------
+constexpr int FORM_THREADS = 256;
+constexpr unsigned long long FORM_AGGREGATE = 1ull, FORM_PREFIX = 2ull;
+
+__device__ __forceinline__ unsigned long long form_pack(uint32_t epoch, unsigned long long state,
+                                                        uint32_t value) {
+    return ((unsigned long long)(epoch & 0x3FFFFFFFu) << 34) | (state << 32) | value;
+}
+
+__global__ void __launch_bounds__(FORM_THREADS)
+k_form_spacepoints(const uint32_t n_meas, const float* __restrict__ meas_local,
+                   const uint32_t* __restrict__ meas_dim, const uint32_t* __restrict__ meas_surface,
+                   const b200seed_surface* __restrict__ surfaces, const uint32_t n_surfaces,
+                   float* __restrict__ xyz, float* __restrict__ var_z, float* __restrict__ var_r,
+                   uint32_t* __restrict__ mi1, uint32_t* __restrict__ mi2,
+                   uint32_t* __restrict__ n_sp_out, unsigned long long* __restrict__ status,
+                   unsigned long long* __restrict__ ticket_ctr, const unsigned long long ticket_base,
+                   const uint32_t epoch) {
+    __shared__ uint32_t s_tile, s_warp[FORM_THREADS / 32], s_prefix;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // tiles are handed out in the order the CTAs start: a CTA only ever waits for tiles
+    // whose CTAs are already running
+    if (threadIdx.x == 0) s_tile = uint32_t(atomicAdd(ticket_ctr, 1ull) - ticket_base);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t i = tile * FORM_THREADS + threadIdx.x;
+    bool valid = false;
+    uint32_t sf = 0;
+    if (i < n_meas) {
+        sf = __ldg(meas_surface + i);
+        // "We use 2D (pixel) measurements only" (spacepoint_formation.ipp:19-23)
+        valid = (!meas_dim || __ldg(meas_dim + i) == 2u) && sf < n_surfaces;
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, valid);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < FORM_THREADS / 32; ++w) {
+        const uint32_t c = s_warp[w];
+        if (w < int(warp)) before += c;
+        total += c;
+    }
+    if (warp == 0) {
+        volatile unsigned long long* st = status;
+        uint32_t prefix = 0;
+        if (tile == 0) {
+            if (lane == 0) st[0] = form_pack(epoch, FORM_PREFIX, total);
+        } else {
+            if (lane == 0) st[tile] = form_pack(epoch, FORM_AGGREGATE, total);
+            // look back over the predecessors, 32 at a time, closest first
+            int base = int(tile) - 1;
+            while (true) {
+                const int j = base - int(lane);
+                unsigned long long w = form_pack(epoch, FORM_PREFIX, 0);  // before tile 0: prefix 0
+                if (j >= 0) {
+                    do {
+                        w = st[j];
+                    } while ((w >> 34) != (epoch & 0x3FFFFFFFu) || ((w >> 32) & 3ull) == 0ull);
+                }
+                const uint32_t is_pref = __ballot_sync(0xffffffffu, ((w >> 32) & 3ull) == FORM_PREFIX);
+                // lanes up to (and including) the first inclusive prefix contribute
+                const uint32_t first = is_pref ? uint32_t(__ffs(int(is_pref)) - 1) : 32u;
+                uint32_t v = (lane <= first) ? uint32_t(w) : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                prefix += v;
+                if (is_pref) break;
+                base -= 32;
+            }
+            if (lane == 0) st[tile] = form_pack(epoch, FORM_PREFIX, prefix + total);
+        }
+        if (lane == 0) {
+            s_prefix = prefix;
+            if (tile == (n_meas + FORM_THREADS - 1) / FORM_THREADS - 1) *n_sp_out = prefix + total;
+        }
+    }
+    __syncthreads();
+    if (!valid) return;
+    const uint32_t p = s_prefix + before + __popc(bal & ((1u << lane) - 1u));
+    const float l0 = __ldg(meas_local + 2 * size_t(i)), l1 = __ldg(meas_local + 2 * size_t(i) + 1);
+    const b200seed_surface S = surfaces[sf];
+    xyz[3 * size_t(p)] = (S.x_axis[0] * l0 + S.y_axis[0] * l1) + S.translation[0];
+    xyz[3 * size_t(p) + 1] = (S.x_axis[1] * l0 + S.y_axis[1] * l1) + S.translation[1];
+    xyz[3 * size_t(p) + 2] = (S.x_axis[2] * l0 + S.y_axis[2] * l1) + S.translation[2];
+    if (var_z) var_z[p] = 0.f;
+    if (var_r) var_r[p] = 0.f;
+    if (mi1) mi1[p] = i;
+    if (mi2) mi2[p] = 0xFFFFFFFFu;  // INVALID_MEASUREMENT_INDEX (spacepoint_collection.hpp:47-48)
+}
+
+// Number of spacepoints of the event: the host's value, or — when the spacepoints were made on
+// the device by k_form_spacepoints and their number never went to the host — the device word
+// clamped to the host's upper bound (the grid is sized for the bound).
+__device__ __forceinline__ uint32_t dev_count(uint32_t n_max, const uint32_t* n_dev) {
+    if (!n_dev) return n_max;
+    const uint32_t n = *n_dev;
+    return n < n_max ? n : n_max;
+}
+
+// ---------------------------------------------------------------------------
 // (1) binning: count
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(BIN_THREADS)
-k_bin_count(const DevCfg cfg, const CellGrid g, const uint32_t n_sp, const float* __restrict__ xyz,
+k_bin_count(const DevCfg cfg, const CellGrid g, const uint32_t n_sp_max,
+            const float* __restrict__ xyz,
             uint32_t* __restrict__ bin_of, uint32_t* __restrict__ blk_hist,
-            uint32_t* __restrict__ cell_cnt, const uint32_t nbins, const uint32_t nblk) {
+            uint32_t* __restrict__ cell_cnt, const uint32_t nbins, const uint32_t nblk,
+            const uint32_t* __restrict__ n_sp_dev) {
     extern __shared__ uint32_t s_hist[];
     for (uint32_t b = threadIdx.x; b < nbins; b += BIN_THREADS) s_hist[b] = 0;
     __syncthreads();
+    const uint32_t n_sp = dev_count(n_sp_max, n_sp_dev);
     const uint32_t i = blockIdx.x * BIN_THREADS + threadIdx.x;
     if (i < n_sp) {
         const float x = __ldg(xyz + 3 * size_t(i));
@@ -168,15 +282,17 @@ k_scan(const uint32_t* in, uint32_t* data, uint32_t len, const uint32_t* __restr
 // (1) binning: stable scatter into the bin-sorted SoA
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(BIN_THREADS)
-k_bin_scatter(const DevCfg cfg, const CellGrid g, const uint32_t n_sp,
+k_bin_scatter(const DevCfg cfg, const CellGrid g, const uint32_t n_sp_max,
               const float* __restrict__ xyz, const float* __restrict__ var_z,
               const float* __restrict__ var_r, const uint32_t* __restrict__ bin_of,
               const uint32_t* __restrict__ blk_scan, const uint32_t nblk,
               float4* __restrict__ sp4, float2* __restrict__ var2,
               uint32_t* __restrict__ sorted_index, uint32_t* __restrict__ sorted_bin,
               const uint32_t* __restrict__ cell_off, uint32_t* __restrict__ cell_cur,
-              float4* __restrict__ csp4, uint32_t* __restrict__ ccanon) {
+              float4* __restrict__ csp4, uint32_t* __restrict__ ccanon,
+              const uint32_t* __restrict__ n_sp_dev) {
     __shared__ uint32_t s_bin[BIN_THREADS];
+    const uint32_t n_sp = dev_count(n_sp_max, n_sp_dev);
     const uint32_t i = blockIdx.x * BIN_THREADS + threadIdx.x;
     const uint32_t bin = (i < n_sp) ? bin_of[i] : INVALID_BIN;
     s_bin[threadIdx.x] = bin;
@@ -1186,7 +1302,7 @@ k_seed_gather(const uint32_t n_sp, const uint32_t K, const Control* __restrict__
               const uint32_t seed_capacity, uint32_t* __restrict__ out_b,
               uint32_t* __restrict__ out_m, uint32_t* __restrict__ out_t,
               float* __restrict__ out_q, uint32_t* __restrict__ out_n,
-              b200seed_counters* __restrict__ counters) {
+              b200seed_counters* __restrict__ counters, const uint32_t* __restrict__ n_sp_dev) {
     const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_valid = ctrl->n_valid;
     if (m < n_valid) {
@@ -1209,7 +1325,7 @@ k_seed_gather(const uint32_t n_sp, const uint32_t K, const Control* __restrict__
         *out_n = n;
         if (counters) {
             b200seed_counters c;
-            c.n_spacepoints = n_sp;
+            c.n_spacepoints = dev_count(n_sp, n_sp_dev);
             c.n_valid = n_valid;
             c.n_active_middles = ctrl->n_active;
             c.n_mid_bot = ctrl->n_mid_bot;

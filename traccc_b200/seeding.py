@@ -33,10 +33,28 @@ class spacepoint_collection:
     z_variance: torch.Tensor | None        # (N,) f32
     radius_variance: torch.Tensor | None   # (N,) f32
     measurement_index_1: torch.Tensor | None = None   # (N,) i32 (bit pattern of u32)
+    measurement_index_2: torch.Tensor | None = None   # (N,) i32
+    # resizable buffer (vecmem::data::buffer_type::resizable): the number of filled entries is
+    # a word in device memory, `size` is then the capacity
+    size_word: torch.Tensor | None = None             # (1,) i32 on the device
 
     @property
     def size(self) -> int:
         return int(self.xyz.shape[0])
+
+    def to_host(self) -> dict:
+        """Synchronises; the filled part of every column."""
+        n = int(self.size_word.item()) if self.size_word is not None else self.size
+        out = {"xyz": self.xyz[:n].cpu().numpy()}
+        for k in ("z_variance", "radius_variance"):
+            v = getattr(self, k)
+            if v is not None:
+                out[k] = v[:n].cpu().numpy()
+        for k in ("measurement_index_1", "measurement_index_2"):
+            v = getattr(self, k)
+            if v is not None:
+                out[k] = v[:n].cpu().numpy().view(np.uint32)
+        return out
 
     @staticmethod
     def from_event(ev, device="cuda") -> "spacepoint_collection":
@@ -54,12 +72,23 @@ class measurement_collection:
 
     local_position: torch.Tensor   # (M,2) f32
     surface_link: torch.Tensor     # (M,) i64 (bit pattern of the 64-bit identifier)
+    dimensions: torch.Tensor | None = None      # (M,) i32; None == all 2D
+    surface_index: torch.Tensor | None = None   # (M,) i32 row of the surface table (formation)
+
+    @property
+    def size(self) -> int:
+        return int(self.local_position.shape[0])
 
     @staticmethod
     def from_event(ev, device="cuda") -> "measurement_collection":
         dev = torch.device(device)
-        return measurement_collection(torch.from_numpy(ev.meas_local).to(dev),
-                                      torch.from_numpy(ev.meas_surface.view(np.int64)).to(dev))
+        dim = getattr(ev, "meas_dim", None)
+        sidx = getattr(ev, "meas_surface_index", None)
+        return measurement_collection(
+            torch.from_numpy(ev.meas_local).to(dev),
+            torch.from_numpy(ev.meas_surface.view(np.int64)).to(dev),
+            torch.from_numpy(dim.view(np.int32)).to(dev) if dim is not None else None,
+            torch.from_numpy(sidx.view(np.int32)).to(dev) if sidx is not None else None)
 
 
 @dataclass
@@ -204,12 +233,16 @@ class triplet_seeding_algorithm:
                 torch.zeros(1, dtype=torch.int32, device=dev),
                 torch.zeros(C.sizeof(Counters), dtype=torch.uint8, device=dev))
         ws = self.workspace(n) if n else None
-        rc = self.lib.b200seed_run(
-            self.h, _stream_handle(stream or self.stream), n, _ptr(spacepoints.xyz),
-            _ptr(spacepoints.z_variance), _ptr(spacepoints.radius_variance), _ptr(ws),
-            ws.numel() if ws is not None else 0, out.capacity, _ptr(out.bottom_index),
-            _ptr(out.middle_index), _ptr(out.top_index), _ptr(out.quality), _ptr(out.n_seeds),
-            _ptr(out.counters))
+        tail = (_ptr(spacepoints.xyz), _ptr(spacepoints.z_variance),
+                _ptr(spacepoints.radius_variance), _ptr(ws), ws.numel() if ws is not None else 0,
+                out.capacity, _ptr(out.bottom_index), _ptr(out.middle_index), _ptr(out.top_index),
+                _ptr(out.quality), _ptr(out.n_seeds), _ptr(out.counters))
+        if spacepoints.size_word is not None and n:
+            # resizable input buffer: its size stays on the device
+            rc = self.lib.b200seed_run_n_on_device(self.h, _stream_handle(stream or self.stream), n,
+                                                   _ptr(spacepoints.size_word), *tail)
+        else:
+            rc = self.lib.b200seed_run(self.h, _stream_handle(stream or self.stream), n, *tail)
         _lib.check(rc, self.h)
         return out
 
@@ -301,6 +334,47 @@ class triplet_seeding_algorithm:
             order = np.lexsort((t["mt_idx"], t["mb_idx"], t["pos_m"]))
             res["triplets"] = t[order]
         return res
+
+
+class silicon_pixel_spacepoint_formation_algorithm:
+    """Drop-in for traccc::cuda::silicon_pixel_spacepoint_formation_algorithm
+    (device/cuda/include/traccc/cuda/seeding/silicon_pixel_spacepoint_formation_algorithm.hpp,
+    common part device/common/src/seeding/silicon_pixel_spacepoint_formation_algorithm.cpp:20-52).
+
+    __call__(det, measurements) -> resizable spacepoint buffer. `det` replaces the detray
+    detector view: a (S,12) f32 device tensor of placed surfaces (translation | x | y | z axes,
+    include/b200seed.h b200seed_surface); measurements.surface_index selects the row."""
+
+    def __init__(self, device: int = 0, stream=None):
+        f = seedfinder_config()
+        self._hd = _Handle(f, spacepoint_grid_config(f), seedfilter_config(), None, device)
+        self.lib, self.h, self.device, self.stream = self._hd.lib, self._hd.h, int(device), stream
+
+    def __call__(self, det: torch.Tensor, measurements: measurement_collection,
+                 stream=None) -> spacepoint_collection:
+        m = measurements.size
+        dev = f"cuda:{self.device}"
+        if measurements.surface_index is None and m:
+            raise B200SeedError("spacepoint formation needs measurements.surface_index")
+        cap = max(m, 1)
+        out = spacepoint_collection(
+            torch.empty((cap, 3), dtype=torch.float32, device=dev),
+            torch.empty(cap, dtype=torch.float32, device=dev),
+            torch.empty(cap, dtype=torch.float32, device=dev),
+            torch.empty(cap, dtype=torch.int32, device=dev),
+            torch.empty(cap, dtype=torch.int32, device=dev),
+            torch.zeros(1, dtype=torch.int32, device=dev))
+        rc = self.lib.b200seed_form_spacepoints(
+            self.h, _stream_handle(stream or self.stream), m, _ptr(measurements.local_position),
+            _ptr(measurements.dimensions), _ptr(measurements.surface_index), _ptr(det),
+            int(det.shape[0]) if det is not None else 0, _ptr(out.xyz), _ptr(out.z_variance),
+            _ptr(out.radius_variance), _ptr(out.measurement_index_1), _ptr(out.measurement_index_2),
+            _ptr(out.size_word))
+        _lib.check(rc, self.h)
+        if m == 0:   # "If there are no measurements, return right away": empty buffer
+            return spacepoint_collection(out.xyz[:0], out.z_variance[:0], out.radius_variance[:0],
+                                         out.measurement_index_1[:0], out.measurement_index_2[:0])
+        return out
 
 
 def _align(v, a=256):

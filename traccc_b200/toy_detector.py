@@ -35,6 +35,10 @@ class ToyEvent:
     particle: np.ndarray       # (N,)  u32  truth particle of each spacepoint
     n_particles: int
     bfield: np.ndarray         # (3,) f32
+    # only set by with_modules(): inputs of the spacepoint formation step
+    meas_dim: np.ndarray | None = None            # (M,) u32  measurement_collection::dimensions
+    meas_surface_index: np.ndarray | None = None  # (M,) u32  row of `surfaces`
+    surfaces: np.ndarray | None = None            # (S,12) f32 translation | x | y | z axes
 
     @property
     def n_spacepoints(self) -> int:
@@ -124,6 +128,93 @@ def generate_event(n_particles: int, seed: int, *, eta_max: float = 3.0, pt_rang
                     meas_local=meas_local, meas_surface=meas_surface,
                     particle=pid.astype(np.uint32), n_particles=n,
                     bfield=np.array([0.0, 0.0, B_FIELD_T * UNIT_T], np.float32))
+
+
+def module_surfaces(n_phi_barrel=(16, 32, 52, 78), n_z_barrel: int = 14, n_phi_endcap: int = 40):
+    """A flat table of placed planar module surfaces for the toy geometry: what a caller would
+    extract from the detray detector (one transform3 per sensitive surface). Barrel layer L is
+    tiled with n_phi_barrel[L] x n_z_barrel rectangles (local x tangential, local y along z,
+    normal radial); every endcap disc with n_phi_endcap trapezoids (local x tangential, local y
+    radial, normal along z). Returns (surfaces (S,12) f32, lookup) where lookup(surf, xyz)
+    gives the table row of the module a hit on layer/disc `surf` falls on."""
+    rows, first_b, first_e = [], [], []
+    dz = 2.0 * BARREL_HALF_Z / n_z_barrel
+    for L, r in enumerate(BARREL_R):
+        first_b.append(len(rows))
+        for ip in range(n_phi_barrel[L]):
+            pc = -np.pi + (ip + 0.5) * 2.0 * np.pi / n_phi_barrel[L]
+            for iz in range(n_z_barrel):
+                zc = -BARREL_HALF_Z + (iz + 0.5) * dz
+                rows.append([r * np.cos(pc), r * np.sin(pc), zc, -np.sin(pc), np.cos(pc), 0.0,
+                             0.0, 0.0, 1.0, np.cos(pc), np.sin(pc), 0.0])
+    rc = 0.5 * (ENDCAP_R_MIN + ENDCAP_R_MAX)
+    for zd in np.concatenate([ENDCAP_Z, -ENDCAP_Z]):
+        first_e.append(len(rows))
+        for ip in range(n_phi_endcap):
+            pc = -np.pi + (ip + 0.5) * 2.0 * np.pi / n_phi_endcap
+            rows.append([rc * np.cos(pc), rc * np.sin(pc), zd, -np.sin(pc), np.cos(pc), 0.0,
+                         np.cos(pc), np.sin(pc), 0.0, 0.0, 0.0, 1.0])
+    table = np.asarray(rows, np.float32)
+    first_b, first_e = np.asarray(first_b), np.asarray(first_e)
+    n_b = len(BARREL_R)
+
+    def lookup(surf, xyz):
+        phi = np.arctan2(xyz[:, 1].astype(np.float64), xyz[:, 0].astype(np.float64))
+        out = np.zeros(len(surf), np.int64)
+        isb = surf < n_b
+        L = np.where(isb, surf, 0)
+        npb = np.asarray(n_phi_barrel)[L]
+        ip = np.clip(((phi + np.pi) / (2.0 * np.pi) * npb).astype(np.int64), 0, npb - 1)
+        iz = np.clip(((xyz[:, 2] + BARREL_HALF_Z) / dz).astype(np.int64), 0, n_z_barrel - 1)
+        out[isb] = (first_b[L] + ip * n_z_barrel + iz)[isb]
+        D = np.where(isb, 0, surf - n_b)
+        ipe = np.clip(((phi + np.pi) / (2.0 * np.pi) * n_phi_endcap).astype(np.int64), 0, n_phi_endcap - 1)
+        out[~isb] = (first_e[D] + ipe)[~isb]
+        return out.astype(np.uint32)
+
+    return table, lookup
+
+
+def with_modules(ev: ToyEvent, surf_of_sp: np.ndarray | None = None, frac_1d: float = 0.0,
+                 seed: int = 0) -> ToyEvent:
+    """The same event as the input of the spacepoint formation step: every hit becomes a 2D
+    measurement in the local frame of the planar module it falls on (so that formation
+    reproduces the hit projected onto the module plane). A fraction frac_1d of extra 1D
+    (strip-like) measurements is mixed in; formation must skip them
+    (spacepoint_formation.ipp:19-23). The measurement order is a random permutation."""
+    table, lookup = module_surfaces()
+    n = ev.n_spacepoints
+    if surf_of_sp is None:
+        # layer / disc of every hit from its position
+        r = np.hypot(ev.xyz[:, 0], ev.xyz[:, 1])
+        zabs = np.abs(ev.xyz[:, 2])
+        is_b = zabs <= BARREL_HALF_Z + 1e-3
+        lay = np.argmin(np.abs(r[:, None] - BARREL_R[None, :]), axis=1)
+        disc = np.argmin(np.abs(zabs[:, None] - ENDCAP_Z[None, :]), axis=1)
+        disc = np.where(ev.xyz[:, 2] > 0, disc, disc + len(ENDCAP_Z))
+        surf_of_sp = np.where(is_b, lay, len(BARREL_R) + disc)
+    row = lookup(surf_of_sp, ev.xyz)
+    S = table[row].astype(np.float64)
+    d = ev.xyz.astype(np.float64) - S[:, 0:3]
+    l0 = np.einsum("ij,ij->i", d, S[:, 3:6]).astype(np.float32)
+    l1 = np.einsum("ij,ij->i", d, S[:, 6:9]).astype(np.float32)
+    rng = np.random.Generator(np.random.PCG64(0xF0A3 + int(seed)))
+    n_1d = int(round(frac_1d * n))
+    m = n + n_1d
+    perm = rng.permutation(m)                 # measurement slot of hit i is perm[i]
+    local = np.zeros((m, 2), np.float32)
+    dim = np.full(m, 2, np.uint32)
+    sidx = np.zeros(m, np.uint32)
+    local[perm[:n], 0], local[perm[:n], 1] = l0, l1
+    sidx[perm[:n]] = row
+    if n_1d:
+        local[perm[n:], 0] = rng.uniform(-10, 10, n_1d).astype(np.float32)
+        dim[perm[n:]] = 1
+        sidx[perm[n:]] = rng.integers(0, len(table), n_1d).astype(np.uint32)
+    surface_link = (sidx.astype(np.uint64) + np.uint64(1)) << np.uint64(12)
+    import dataclasses
+    return dataclasses.replace(ev, meas_local=local, meas_surface=surface_link, meas_dim=dim,
+                               meas_surface_index=sidx, surfaces=table)
 
 
 def helix_test_points(charge: float, path_lengths=(50.0, 100.0, 150.0)) -> np.ndarray:
