@@ -227,6 +227,27 @@ int b200seed_estimate_params(b200seed_handle* h, void* stream, const uint32_t* d
                              const float* d_meas_local, const uint64_t* d_meas_surface,
                              const float bfield[3], b200seed_bound_params* d_params);
 
+/* An inhomogeneous magnetic field sampled on a regular grid: the reference's
+ * cuda::inhom_global_bfield_backend_t = covfie affine<linear<clamp<strided<array<float3>>>>>
+ * (device/cuda/src/utils/magnetic_field_types.hpp:27-32). */
+typedef struct b200seed_field_grid {
+    float affine[12];   /* row-major 3x4: grid coordinate = A * (x, y, z, 1)              */
+    uint32_t size[3];   /* grid points per axis                                            */
+    const float* data;  /* DEVICE: size[0]*size[1]*size[2] float3 field vectors, row-major:
+                           point (i, j, k) at ((i * size[1] + j) * size[2] + k) * 3        */
+} b200seed_field_grid;
+
+/* b200seed_estimate_params with the field looked up at every seed's bottom spacepoint
+ * (device/common/.../impl/estimate_track_params.ipp:45-50): trilinear interpolation, indices
+ * clamped to the grid. `field` is a host struct whose data pointer is device memory. */
+int b200seed_estimate_params_inhom(b200seed_handle* h, void* stream, const uint32_t* d_n_seeds,
+                                   uint32_t seed_capacity, const uint32_t* d_bottom,
+                                   const uint32_t* d_middle, const uint32_t* d_top,
+                                   const float* d_xyz, const uint32_t* d_sp_meas_index_1,
+                                   const float* d_meas_local, const uint64_t* d_meas_surface,
+                                   const b200seed_field_grid* field,
+                                   b200seed_bound_params* d_params);
+
 /* ------------------------------------------------------------------------ */
 /* The step before the path: spacepoint formation       */
 /* ------------------------------------------------------------------------ */

@@ -101,6 +101,8 @@ def lib() -> C.CDLL:
         L.oracle_copy_params.argtypes = [C.c_void_p] * 2
         L.oracle_estimate_params.argtypes = [C.c_void_p, C.POINTER(TpeCfg)] + [C.c_void_p] * 5
         L.oracle_estimate_params_for.argtypes = [C.POINTER(TpeCfg), C.c_uint32] + [C.c_void_p] * 9
+        L.oracle_field_at.argtypes = [C.c_void_p] * 3
+        L.oracle_estimate_params_inhom.argtypes = [C.POINTER(TpeCfg), C.c_uint32] + [C.c_void_p] * 9
         L.oracle_form_spacepoints.restype = C.c_uint32
         L.oracle_form_spacepoints.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_uint32] + [C.c_void_p] * 5
@@ -451,3 +453,44 @@ def form_spacepoints(meas_local, meas_dim, meas_surface_index, surfaces) -> dict
                                       _ptr(mi1), _ptr(mi2))
     return {"xyz": xyz[:n].copy(), "z_variance": vz[:n].copy(), "radius_variance": vr[:n].copy(),
             "measurement_index_1": mi1[:n].copy(), "measurement_index_2": mi2[:n].copy()}
+
+
+class FieldGrid(C.Structure):
+    """b200seed_field_grid (include/b200seed.h) with a HOST data pointer."""
+    _fields_ = [("affine", C.c_float * 12), ("size", C.c_uint32 * 3), ("data", C.c_void_p)]
+
+
+def _field_grid(affine, data):
+    data = np.ascontiguousarray(data, np.float32)
+    assert data.ndim == 4 and data.shape[3] == 3
+    fg = FieldGrid()
+    fg.affine[:] = [float(v) for v in np.asarray(affine, np.float32).reshape(12)]
+    fg.size[:] = list(data.shape[:3])
+    fg.data = data.ctypes.data
+    return fg, data
+
+
+def field_at(affine, data, points) -> np.ndarray:
+    fg, keep = _field_grid(affine, data)
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    out = np.zeros_like(pts)
+    for i in range(len(pts)):
+        lib().oracle_field_at(C.addressof(fg), pts[i].ctypes.data, out[i].ctypes.data)
+    return out
+
+
+def estimate_params_inhom(bottom, middle, top, xyz, affine, data, tpe=None, sp_meas_index=None,
+                          meas_local=None, meas_surface=None) -> np.ndarray:
+    tpe = tpe or default_configs()[3]
+    fg, keep = _field_grid(affine, data)
+    b = np.ascontiguousarray(bottom, np.uint32)
+    m = np.ascontiguousarray(middle, np.uint32)
+    t = np.ascontiguousarray(top, np.uint32)
+    xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+    smi = None if sp_meas_index is None else np.ascontiguousarray(sp_meas_index, np.uint32)
+    ml = None if meas_local is None else np.ascontiguousarray(meas_local, np.float32)
+    ms = None if meas_surface is None else np.ascontiguousarray(meas_surface, np.uint64)
+    out = np.zeros(len(b), dtype=BOUND_PARAMS_DTYPE)
+    lib().oracle_estimate_params_inhom(C.byref(tpe), len(b), _ptr(b), _ptr(m), _ptr(t), _ptr(xyz),
+                                       _ptr(smi), _ptr(ml), _ptr(ms), C.addressof(fg), _ptr(out))
+    return out

@@ -1105,6 +1105,63 @@ void oracle_estimate_params(oracle_result* res, const b200seed_tpe_cfg* cfg, con
                         meas_surface ? meas_surface[mi] : 0, bfield, res->params[i]);
     }
 }
+// Field vector of an inhomogeneous field at a point: the reference's inhom_bfield_backend_t =
+// covfie affine<linear<clamp<strided<array<float3>>>>> (core/include/traccc/bfield/
+// magnetic_field_types.hpp:44-48). covfie 0.15.4 is third-party and absent: restated from its
+// published semantics ("parity unpinned" at the last ulp, like the detray arithmetic):
+//   affine  : c_i = ((A_i0 x + A_i1 y) + A_i2 z) + A_i3
+//   linear  : i = floor(c), a = c - i, sum over the 8 corners n = 4 dx + 2 dy + dz of
+//             ((wx * wy) * wz) * f(corner), accumulated in that order
+//   clamp   : corner indices clamped into [0, size - 1]
+//   strided : row-major, point (i, j, k) at (i * size[1] + j) * size[2] + k
+void oracle_field_at(const b200seed_field_grid* fg, const float p[3], float out[3]) {
+    float c[3];
+    for (int i = 0; i < 3; ++i)
+        c[i] = ((fg->affine[4 * i] * p[0] + fg->affine[4 * i + 1] * p[1]) +
+                fg->affine[4 * i + 2] * p[2]) +
+               fg->affine[4 * i + 3];
+    long i0[3], i1[3];
+    float w0[3], w1[3];
+    for (int k = 0; k < 3; ++k) {
+        const float fl = std::floor(c[k]);
+        w1[k] = c[k] - fl;
+        w0[k] = 1.f - w1[k];
+        const float hi = static_cast<float>(fg->size[k] - 1u);
+        auto clampf = [&](float v) { return (v >= 0.f) ? ((v <= hi) ? v : hi) : 0.f; };
+        i0[k] = static_cast<long>(clampf(fl));
+        i1[k] = static_cast<long>(clampf(fl + 1.f));
+    }
+    float r[3] = {0.f, 0.f, 0.f};
+    for (int n = 0; n < 8; ++n) {
+        const long ix = (n & 4) ? i1[0] : i0[0], iy = (n & 2) ? i1[1] : i0[1],
+                   iz = (n & 1) ? i1[2] : i0[2];
+        const float w = (((n & 4) ? w1[0] : w0[0]) * ((n & 2) ? w1[1] : w0[1])) *
+                        ((n & 1) ? w1[2] : w0[2]);
+        const float* f = fg->data + 3 * ((size_t(ix) * fg->size[1] + size_t(iy)) * fg->size[2] + size_t(iz));
+        for (int q = 0; q < 3; ++q) r[q] = r[q] + w * f[q];
+    }
+    out[0] = r[0], out[1] = r[1], out[2] = r[2];
+}
+
+// device::estimate_track_params with an inhomogeneous field: the field is sampled at the
+// bottom spacepoint of every seed (device/common/.../impl/estimate_track_params.ipp:45-50).
+// fg->data is HOST memory here.
+void oracle_estimate_params_inhom(const b200seed_tpe_cfg* cfg, uint32_t n_seeds, const uint32_t* b,
+                                  const uint32_t* m, const uint32_t* t, const float* xyz,
+                                  const uint32_t* sp_meas_index_1, const float* meas_local,
+                                  const uint64_t* meas_surface, const b200seed_field_grid* fg,
+                                  b200seed_bound_params* out) {
+    auto sp = [&](uint32_t i) { return Sp{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.f, 0.f}; };
+    for (uint32_t i = 0; i < n_seeds; ++i) {
+        float bf[3];
+        oracle_field_at(fg, xyz + 3 * size_t(b[i]), bf);
+        const uint32_t mi = sp_meas_index_1 ? sp_meas_index_1[b[i]] : b[i];
+        estimate_params(*cfg, sp(b[i]), sp(m[i]), sp(t[i]), meas_local ? meas_local[2 * mi] : 0.f,
+                        meas_local ? meas_local[2 * mi + 1] : 0.f,
+                        meas_surface ? meas_surface[mi] : 0, bf, out[i]);
+    }
+}
+
 // Stand-alone parameter estimation for explicit seeds (test_track_params_estimation.cpp)
 void oracle_estimate_params_for(const b200seed_tpe_cfg* cfg, uint32_t n_seeds, const uint32_t* b,
                                 const uint32_t* m, const uint32_t* t, const float* xyz,

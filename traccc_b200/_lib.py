@@ -103,6 +103,12 @@ class EventIO(C.Structure):
                 ("n_seeds", C.c_uint32), ("status", C.c_int32), ("counters", Counters)]
 
 
+class FieldGrid(C.Structure):
+    """b200seed_field_grid (include/b200seed.h): data is a DEVICE pointer."""
+
+    _fields_ = [("affine", C.c_float * 12), ("size", C.c_uint32 * 3), ("data", C.c_void_p)]
+
+
 class WsLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in (
         "bin_offsets", "sorted_index", "sp_xyzr", "mid_counts", "mid_offsets", "doublets",
@@ -119,7 +125,7 @@ EXPORTS = (
     "b200seed_set_stage_cap", "b200seed_pool_create", "b200seed_pool_process",
     "b200seed_pool_last_error", "b200seed_pool_destroy",
     "b200seed_workspace_bytes", "b200seed_run", "b200seed_estimate_params", "b200seed_run_host",
-    "b200seed_form_spacepoints", "b200seed_run_n_on_device",
+    "b200seed_form_spacepoints", "b200seed_run_n_on_device", "b200seed_estimate_params_inhom",
     "b200seed_workspace_layout", "b200seed_set_triplet_dump", "b200seed_set_timing",
     "b200seed_get_timings", "b200seed_launches_per_event", "b200seed_measure_fp32_peak",
     "b200seed_version")
@@ -164,6 +170,8 @@ def lib() -> C.CDLL:
     L.b200seed_form_spacepoints.argtypes = [vp, vp, u32, vp, vp, vp, vp, u32, vp, vp, vp, vp, vp, vp]
     L.b200seed_estimate_params.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp, vp, vp,
                                            C.POINTER(C.c_float * 3), vp]
+    L.b200seed_estimate_params_inhom.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp, vp, vp,
+                                                 C.POINTER(FieldGrid), vp]
     L.b200seed_run_host.argtypes = [vp, vp, u32, vp, vp, vp, vp, u32, vp, vp,
                                     C.POINTER(C.c_float * 3), u32, vp, vp, vp, vp, vp,
                                     C.POINTER(u32), C.POINTER(Counters)]

@@ -809,12 +809,14 @@ int b200seed_form_spacepoints(b200seed_handle* h, void* stream, uint32_t n_meas,
     return B200SEED_OK;
 }
 
-int b200seed_estimate_params(b200seed_handle* h, void* stream, const uint32_t* d_n_seeds,
-                             uint32_t seed_capacity, const uint32_t* d_bottom,
-                             const uint32_t* d_middle, const uint32_t* d_top,
-                             const float* d_xyz, const uint32_t* d_sp_meas_index_1,
-                             const float* d_meas_local, const uint64_t* d_meas_surface,
-                             const float bfield[3], b200seed_bound_params* d_params) {
+}  // extern "C"
+
+namespace {
+int estimate_impl(b200seed_handle* h, void* stream, const uint32_t* d_n_seeds,
+                  uint32_t seed_capacity, const uint32_t* d_bottom, const uint32_t* d_middle,
+                  const uint32_t* d_top, const float* d_xyz, const uint32_t* d_sp_meas_index_1,
+                  const float* d_meas_local, const uint64_t* d_meas_surface, const float bfield[3],
+                  const b200seed_field_grid& fg, b200seed_bound_params* d_params) {
     if (!h) return B200SEED_EINVAL;
     if (seed_capacity == 0) return B200SEED_OK;
     if (!d_xyz) return B200SEED_OK;  // no spacepoints => no seeds (…estimation_algorithm.cpp:49-51)
@@ -826,10 +828,39 @@ int b200seed_estimate_params(b200seed_handle* h, void* stream, const uint32_t* d
         KernelTimer t(h, s, "estimate_params");
         k_estimate_params<<<(seed_capacity + 127) / 128, 128, 0, s>>>(
             h->tpe, d_n_seeds, seed_capacity, d_bottom, d_middle, d_top, d_xyz, d_sp_meas_index_1,
-            d_meas_local, d_meas_surface, bfield[0], bfield[1], bfield[2], d_params);
+            d_meas_local, d_meas_surface, bfield[0], bfield[1], bfield[2], fg, d_params);
     }
     CUDA_TRY(h, cudaGetLastError());
     return B200SEED_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int b200seed_estimate_params(b200seed_handle* h, void* stream, const uint32_t* d_n_seeds,
+                             uint32_t seed_capacity, const uint32_t* d_bottom,
+                             const uint32_t* d_middle, const uint32_t* d_top,
+                             const float* d_xyz, const uint32_t* d_sp_meas_index_1,
+                             const float* d_meas_local, const uint64_t* d_meas_surface,
+                             const float bfield[3], b200seed_bound_params* d_params) {
+    b200seed_field_grid none{};
+    return estimate_impl(h, stream, d_n_seeds, seed_capacity, d_bottom, d_middle, d_top, d_xyz,
+                         d_sp_meas_index_1, d_meas_local, d_meas_surface, bfield, none, d_params);
+}
+
+int b200seed_estimate_params_inhom(b200seed_handle* h, void* stream, const uint32_t* d_n_seeds,
+                                   uint32_t seed_capacity, const uint32_t* d_bottom,
+                                   const uint32_t* d_middle, const uint32_t* d_top,
+                                   const float* d_xyz, const uint32_t* d_sp_meas_index_1,
+                                   const float* d_meas_local, const uint64_t* d_meas_surface,
+                                   const b200seed_field_grid* field,
+                                   b200seed_bound_params* d_params) {
+    if (!h) return B200SEED_EINVAL;
+    if (!field || !field->data || !field->size[0] || !field->size[1] || !field->size[2])
+        return fail(h, B200SEED_EINVAL, "b200seed_estimate_params_inhom: empty field grid");
+    const float unused[3] = {0.f, 0.f, 0.f};
+    return estimate_impl(h, stream, d_n_seeds, seed_capacity, d_bottom, d_middle, d_top, d_xyz,
+                         d_sp_meas_index_1, d_meas_local, d_meas_surface, unused, *field, d_params);
 }
 
 }  // extern "C"

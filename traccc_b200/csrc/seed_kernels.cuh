@@ -1359,13 +1359,55 @@ __device__ __forceinline__ V3 v3normalize(V3 a) {
 }
 __device__ __forceinline__ float perp2(float x, float y) { return sqrt_rn(x * x + y * y); }
 
+// Inhomogeneous field on a regular grid: the reference's cuda::inhom_global_bfield_backend_t =
+// covfie affine< linear< clamp< strided< device array of float3 >>>>
+// (device/cuda/src/utils/magnetic_field_types.hpp:27-32), sampled at the bottom spacepoint
+// (estimate_track_params.ipp:45-50). covfie is third-party and absent here; restated from its
+// published semantics: index-space coordinate c = A (x, y, z, 1); trilinear interpolation
+// between floor(c) and floor(c) + 1 with the indices clamped to the grid; row-major storage.
+__device__ __forceinline__ V3 field_at(const b200seed_field_grid& fg, V3 p) {
+    float c[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        c[i] = ((fg.affine[4 * i] * p.x + fg.affine[4 * i + 1] * p.y) + fg.affine[4 * i + 2] * p.z) +
+               fg.affine[4 * i + 3];
+    int i0[3], i1[3];
+    float w1[3], w0[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float fl = floorf(c[k]);
+        w1[k] = c[k] - fl;
+        w0[k] = 1.f - w1[k];
+        const int hi = int(fg.size[k]) - 1;
+        // NaN / out-of-range coordinates clamp like covfie's clamp backend
+        const float lo_f = (fl >= 0.f) ? ((fl <= float(hi)) ? fl : float(hi)) : 0.f;
+        const float up = fl + 1.f;
+        const float hi_f = (up >= 0.f) ? ((up <= float(hi)) ? up : float(hi)) : 0.f;
+        i0[k] = int(lo_f);
+        i1[k] = int(hi_f);
+    }
+    V3 r{0.f, 0.f, 0.f};
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+        const int ix = (n & 4) ? i1[0] : i0[0], iy = (n & 2) ? i1[1] : i0[1],
+                  iz = (n & 1) ? i1[2] : i0[2];
+        const float w = (((n & 4) ? w1[0] : w0[0]) * ((n & 2) ? w1[1] : w0[1])) *
+                        ((n & 1) ? w1[2] : w0[2]);
+        const float* f = fg.data + 3 * ((size_t(ix) * fg.size[1] + iy) * fg.size[2] + iz);
+        r.x = r.x + w * __ldg(f);
+        r.y = r.y + w * __ldg(f + 1);
+        r.z = r.z + w * __ldg(f + 2);
+    }
+    return r;
+}
+
 __global__ void __launch_bounds__(128)
 k_estimate_params(const b200seed_tpe_cfg cfg, const uint32_t* __restrict__ n_seeds_dev,
                   const uint32_t seed_capacity, const uint32_t* __restrict__ sd_b,
                   const uint32_t* __restrict__ sd_m, const uint32_t* __restrict__ sd_t,
                   const float* __restrict__ xyz, const uint32_t* __restrict__ sp_meas,
                   const float* __restrict__ meas_local, const uint64_t* __restrict__ meas_surface,
-                  const float bx, const float by, const float bz,
+                  const float bx, const float by, const float bz, const b200seed_field_grid fg,
                   b200seed_bound_params* __restrict__ out) {
     // Records are 176 B: written one per lane they would cost 32 sectors per store
     // instruction. Each warp builds its 32 records (5632 contiguous bytes) in shared memory
@@ -1389,7 +1431,7 @@ k_estimate_params(const b200seed_tpe_cfg cfg, const uint32_t* __restrict__ n_see
     const V3 p0{xyz[3 * size_t(ib)], xyz[3 * size_t(ib) + 1], xyz[3 * size_t(ib) + 2]};
     const V3 p1{xyz[3 * size_t(im)], xyz[3 * size_t(im) + 1], xyz[3 * size_t(im) + 2]};
     const V3 p2{xyz[3 * size_t(it)], xyz[3 * size_t(it) + 1], xyz[3 * size_t(it) + 2]};
-    const V3 bfield{bx, by, bz};
+    const V3 bfield = fg.data ? field_at(fg, p0) : V3{bx, by, bz};
     const V3 relVec = v3sub(p1, p0);
     const V3 newZ = v3normalize(bfield);
     const V3 newY = v3normalize(v3cross(newZ, relVec));

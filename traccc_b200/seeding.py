@@ -381,6 +381,21 @@ def _align(v, a=256):
     return (v + a - 1) // a * a
 
 
+class inhomogeneous_field:
+    """A magnetic field on a regular grid — the reference's cuda::inhom_global_bfield_backend_t
+    (device/cuda/src/utils/magnetic_field_types.hpp:27-32): `affine` (3x4) maps a global
+    position to grid coordinates, `data` is the (nx, ny, nz, 3) f32 device tensor of field
+    vectors, looked up with trilinear interpolation and clamped indices."""
+
+    def __init__(self, affine, data: torch.Tensor):
+        assert data.dim() == 4 and data.shape[3] == 3 and data.dtype == torch.float32
+        self.data = data.contiguous()
+        self.grid = _lib.FieldGrid()
+        self.grid.affine[:] = [float(v) for v in np.asarray(affine, np.float32).reshape(12)]
+        self.grid.size[:] = [int(v) for v in data.shape[:3]]
+        self.grid.data = self.data.data_ptr()
+
+
 class seed_parameter_estimation_algorithm:
     """Drop-in for traccc::cuda::seed_parameter_estimation_algorithm: ctor(config, device,
     stream); __call__(bfield, measurements, spacepoints, seeds) -> bound track parameters
@@ -404,13 +419,15 @@ class seed_parameter_estimation_algorithm:
         if out is None:
             out = torch.empty(cap * BOUND_PARAMS_DTYPE.itemsize, dtype=torch.uint8,
                               device=f"cuda:{self.device}")
-        bf = (C.c_float * 3)(*[float(b) for b in bfield])
-        rc = self.lib.b200seed_estimate_params(
-            self.h, _stream_handle(stream or self.stream), _ptr(seeds.n_seeds), cap,
-            _ptr(seeds.bottom_index), _ptr(seeds.middle_index), _ptr(seeds.top_index),
-            _ptr(spacepoints.xyz), _ptr(spacepoints.measurement_index_1),
-            _ptr(measurements.local_position), _ptr(measurements.surface_link), C.byref(bf),
-            _ptr(out))
+        head = (self.h, _stream_handle(stream or self.stream), _ptr(seeds.n_seeds), cap,
+                _ptr(seeds.bottom_index), _ptr(seeds.middle_index), _ptr(seeds.top_index),
+                _ptr(spacepoints.xyz), _ptr(spacepoints.measurement_index_1),
+                _ptr(measurements.local_position), _ptr(measurements.surface_link))
+        if isinstance(bfield, inhomogeneous_field):
+            rc = self.lib.b200seed_estimate_params_inhom(*head, C.byref(bfield.grid), _ptr(out))
+        else:
+            bf = (C.c_float * 3)(*[float(b) for b in bfield])
+            rc = self.lib.b200seed_estimate_params(*head, C.byref(bf), _ptr(out))
         _lib.check(rc, self.h)
         return out
 
