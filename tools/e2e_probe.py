@@ -10,7 +10,7 @@ E = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 P = int(sys.argv[2]) if len(sys.argv) > 2 else 10000
 events = [toy_detector.generate_event(P, 100 + i) for i in range(8)]
 events = [events[i % 8] for i in range(E)]
-for workers in (1, 2, 4, 6, 8):
+for workers in (2, 4, 6, 8, 12, 16):
     for with_params in (True, False):
         pool = seeding.EventPool(n_workers=workers)
         ios, outs = pool.make_batch(events, with_params=with_params)
