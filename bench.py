@@ -47,7 +47,8 @@ def parse_args():
     ap.add_argument("--events", type=int, default=64, help="events per step per GPU")
     ap.add_argument("--streams", type=int, default=8, help="algorithm instances / streams per GPU")
     ap.add_argument("--pool-workers", type=int, default=6,
-                    help="host worker threads of the end-to-end leg (2 events in flight each)")
+                    help="host worker threads of the end-to-end leg (2 events in flight each; "
+                         "they sleep on blocking-sync events, so ranks x workers may exceed the cores)")
     ap.add_argument("--particles", type=int, default=N_PARTICLES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true",
@@ -288,7 +289,19 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(dev))
+        # NCCL prints its version banner to stdout when it creates the first communicator;
+        # stdout carries exactly ONE JSON line, so route fd 1 to stderr until that is over
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device(dev))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     E, S = args.events, max(1, min(args.streams, args.events))
     events = gen_events(E, args.particles, 100 + 1000 * rank)

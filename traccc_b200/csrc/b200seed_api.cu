@@ -77,6 +77,7 @@ struct b200seed_handle {
     size_t d_stage_bytes = 0;
     b200seed_counters* h_pinned = nullptr;  // counters + n_seeds read-back
     // look-back state of b200seed_form_spacepoints (status words + ticket counter)
+    cudaEvent_t ev_host = nullptr;  // blocking-sync event of the host-buffer path
     unsigned long long* d_form = nullptr;
     size_t form_tiles = 0;
     unsigned long long form_ticket_base = 0;
@@ -484,6 +485,7 @@ void b200seed_destroy(b200seed_handle* h) {
     }
     if (h->d_stage) cudaFree(h->d_stage);
     if (h->d_form) cudaFree(h->d_form);
+    if (h->ev_host) cudaEventDestroy(h->ev_host);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     delete h;
 }
@@ -891,6 +893,18 @@ struct HostEvent {
     bool submitted = false;
 };
 
+// The host threads of a throughput job wait on an event created with cudaEventBlockingSync:
+// they sleep instead of spinning in cudaStreamSynchronize, so a node running one pool per GPU
+// (8 ranks x several workers) does not oversubscribe its cores with busy-waiting threads.
+cudaError_t host_wait_point(b200seed_handle* h, cudaStream_t s) {
+    if (!h->ev_host) {
+        const cudaError_t e =
+            cudaEventCreateWithFlags(&h->ev_host, cudaEventBlockingSync | cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaEventRecord(h->ev_host, s);
+}
+
 int host_submit(b200seed_handle* h, cudaStream_t s, HostEvent& e) {
     CUDA_TRY(h, cudaSetDevice(h->device));
     e.submitted = false;
@@ -960,6 +974,7 @@ int host_submit(b200seed_handle* h, cudaStream_t s, HostEvent& e) {
     }
     // the counters struct carries n_seeds: one small read-back, then the sized copies
     CUDA_TRY(h, cudaMemcpyAsync(h->h_pinned, d_c, sizeof(b200seed_counters), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, host_wait_point(h, s));
     e.submitted = true;
     return B200SEED_OK;
 }
@@ -971,7 +986,7 @@ int host_finish(b200seed_handle* h, cudaStream_t s, HostEvent& e, uint32_t* h_n_
     if (!e.submitted) return B200SEED_OK;
     e.submitted = false;
     CUDA_TRY(h, cudaSetDevice(h->device));
-    CUDA_TRY(h, cudaStreamSynchronize(s));
+    CUDA_TRY(h, cudaEventSynchronize(h->ev_host));
     const uint32_t n = h->h_pinned->n_seeds;
     *h_n_seeds = n;
     if (h_counters) *h_counters = *h->h_pinned;
@@ -983,7 +998,8 @@ int host_finish(b200seed_handle* h, cudaStream_t s, HostEvent& e, uint32_t* h_n_
         if (e.h_params)
             CUDA_TRY(h, cudaMemcpyAsync(e.h_params, e.d_p, size_t(n) * sizeof(b200seed_bound_params),
                                         cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(h, cudaStreamSynchronize(s));
+        CUDA_TRY(h, host_wait_point(h, s));
+        CUDA_TRY(h, cudaEventSynchronize(h->ev_host));
     }
     return B200SEED_OK;
 }
