@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--events", type=int, default=64, help="events per step per GPU")
     ap.add_argument("--streams", type=int, default=8, help="algorithm instances / streams per GPU")
-    ap.add_argument("--pool-workers", type=int, default=6,
+    ap.add_argument("--pool-workers", type=int, default=8,
                     help="host worker threads of the end-to-end leg (2 events in flight each; "
                          "they sleep on blocking-sync events, so ranks x workers may exceed the cores)")
     ap.add_argument("--particles", type=int, default=N_PARTICLES)

@@ -153,3 +153,68 @@ def test_cell_window_is_conservative(n_particles, seed, kw, cfg):
     assert vis[kind != 0].all(), "a compatible pair lies outside the visited cells"
     if cfg == "default" and n_particles >= 2000:
         assert vis.mean() < 0.5, (vis.mean(), gr)
+
+
+def _stage2(dc, xy):
+    xy = np.ascontiguousarray(xy, np.float32)
+    exact = np.zeros(len(xy), np.int32)
+    fast = np.zeros(len(xy), np.int32)
+    _lib.lib().b200seed_host_probe_stage2(dc, len(xy), _p(xy), _p(exact), _p(fast))
+    return exact, fast
+
+
+@pytest.mark.parametrize("cfg", [{}, dict(minPt=1.0), dict(impactMax=3.0), dict(minPt=0.3, impactMax=20.0)])
+def test_stage2_predecision_never_contradicts_the_exact_cut(cfg):
+    """doublet_stage2_fast (division-free) may answer "undecided", but a decided answer must be
+    the reference chain's answer (doublet_finding_helper.hpp:120-213) — on realistic pairs, on
+    pairs forced onto the cut boundary, and on degenerate / axis-parallel chords."""
+    finder = seedfinder_config(**cfg)
+    finder.setup()
+    dc = _devcfg(finder, spacepoint_grid_config(finder), seedfilter_config())
+    rng = np.random.default_rng(17)
+    n = 400000
+    # (1) realistic: two radii 20..200 mm, 20..80 mm apart, small opening angle
+    r1 = rng.uniform(25, 200, n)
+    r2 = np.clip(r1 + rng.choice([-1, 1], n) * rng.uniform(20, 80, n), 5, 260)
+    phi = rng.uniform(-np.pi, np.pi, n)
+    dphi = rng.normal(0, 0.08, n)
+    xy = np.stack([r1 * np.cos(phi), r1 * np.sin(phi), r2 * np.cos(phi + dphi), r2 * np.sin(phi + dphi)], 1)
+    exact, fast = _stage2(dc, xy)
+    decided = fast != 2
+    assert np.array_equal(fast[decided], exact[decided])
+    assert decided.mean() > 0.98, decided.mean()
+    assert 0.05 < exact.mean() < 0.95
+    # (2) on the boundary: bisect the opening angle to the flip of the exact cut, then scatter
+    #     tightly around it
+    lo, hi = np.zeros(n), np.full(n, 0.6)
+    def at(d):
+        return np.stack([r1 * np.cos(phi), r1 * np.sin(phi), r2 * np.cos(phi + d), r2 * np.sin(phi + d)], 1)
+    e_lo = _stage2(dc, at(lo))[0]
+    e_hi = _stage2(dc, at(hi))[0]
+    brack = e_lo != e_hi
+    for _ in range(40):
+        mid = 0.5 * (lo + hi)
+        e_mid = _stage2(dc, at(mid))[0]
+        go_hi = e_mid == e_lo
+        lo = np.where(go_hi, mid, lo)
+        hi = np.where(go_hi, hi, mid)
+    for scale in (0.0, 1e-7, 1e-6, 1e-5, 1e-4, 1e-3):
+        d = lo + rng.normal(0, 1, n) * scale
+        exact, fast = _stage2(dc, at(d)[brack])
+        decided = fast != 2
+        assert np.array_equal(fast[decided], exact[decided]), scale
+        if scale <= 1e-6:
+            assert decided.mean() < 0.5          # the band really is left to the exact chain
+    # (3) degenerate chords: identical points, axis-parallel, huge / tiny coordinates
+    base = at(dphi)[:20000].astype(np.float32)
+    v = base.copy(); v[:, 2] = v[:, 0]                      # dx == 0
+    h = base.copy(); h[:, 3] = h[:, 1]                      # dy == 0
+    same = base.copy(); same[:, 2:] = same[:, :2]
+    big = base * np.float32(1e18)
+    tiny = base * np.float32(1e-20)
+    far = base.copy(); far[:, 2:] *= np.float32(30)          # chord longer than the helix diameter
+    for arr in (v, h, same, big, tiny, far):
+        with np.errstate(all="ignore"):
+            exact, fast = _stage2(dc, arr)
+        decided = fast != 2
+        assert np.array_equal(fast[decided], exact[decided])

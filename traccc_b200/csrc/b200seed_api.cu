@@ -1257,6 +1257,17 @@ void b200seed_host_probe_doublets(const void* devcfg, uint32_t n, const float* m
         }
     }
 }
+// Helix-radius cut of n pairs {x1,y1,x2,y2}: exact[i] = doublet_stage2, fast[i] = the
+// division-free pre-decision (0 fail, 1 pass, 2 undecided).
+void b200seed_host_probe_stage2(const void* devcfg, uint32_t n, const float* xy, int32_t* exact,
+                                int32_t* fast) {
+    const DevCfg& d = *static_cast<const DevCfg*>(devcfg);
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* q = xy + 4 * size_t(i);
+        exact[i] = doublet_stage2(d, q[0], q[1], q[2], q[3]) ? 1 : 0;
+        fast[i] = doublet_stage2_fast(d, q[0], q[1], q[2], q[3]);
+    }
+}
 // Pruning index: for n (middle, other) pairs, whether the other spacepoint's cell lies inside
 // the cell window k_doublets visits for that middle (grid sized for n_sp spacepoints).
 // m/o = {x,y,z,varZ,varR}; bins = reference bin of each `other` (from ..._probe_bins).

@@ -580,7 +580,13 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
                     if (p < total) {
                         P = __ldg(a.csp4 + c);
                         st = doublet_stage1(cfg, M.w, M.z, P.w, P.z);
-                        if (st != 0 && !doublet_stage2(cfg, M.x, M.y, P.x, P.y)) st = 0;
+                        if (st != 0) {
+                            // division-free pre-decision; the exact reference chain only for
+                            // the few pairs inside its uncertainty band
+                            int d = doublet_stage2_fast(cfg, M.x, M.y, P.x, P.y);
+                            if (d == 2) d = doublet_stage2(cfg, M.x, M.y, P.x, P.y) ? 1 : 0;
+                            if (d == 0) st = 0;
+                        }
                     }
                     const uint32_t mB = __ballot_sync(0xffffffffu, st == 1);
                     const uint32_t mT = __ballot_sync(0xffffffffu, st == 2);

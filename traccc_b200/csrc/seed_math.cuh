@@ -289,6 +289,37 @@ B200_HD bool doublet_stage2(const DevCfg& c, float x1, float y1, float x2, float
     return true;
 }
 
+// Pre-decision of the minimum-helix-radius cut without divisions or square roots.
+// In exact arithmetic the two circle centres of doublet_stage2 are Mid +- q n (Mid the chord's
+// midpoint, n its unit normal, q^2 = R^2 - c^2/4, c the chord length), so with
+//   dot = x1 x2 + y1 y2,  cross = x1 y2 - x2 y1,  L = dot + (R^2 - margin^2)
+// min(mp1R2, mp2R2) - margin^2 = L - Rt,  Rt = |cross| sqrt(4 R^2 - c^2) / c >= 0,
+// i.e. the cut passes iff L > Rt. The reference's float chain and the polynomials below both
+// carry rounding errors far below delta = 2e-5 R^2 (about 14 mm^2 of the ~7e5 mm^2 compared:
+// the chain's own error is ~0.5 mm^2), so outside the band |L - Rt| <= delta the exact chain
+// must give the same answer. Returns 1 = passes, 0 = fails, 2 = undecided (inside the band,
+// axis-parallel or degenerate chords, non-finite values): the caller then runs doublet_stage2.
+B200_HD int doublet_stage2_fast(const DevCfg& c, float x1, float y1, float x2, float y2) {
+    const float dx = x2 - x1, dy = y2 - y1;
+    const float c2 = dx * dx + dy * dy;
+    const float fourR2 = 4.f * c.minHelixRadius2;
+    const float delta = 2e-5f * c.minHelixRadius2;
+    const float w = fourR2 - c2;  // 4 q^2
+    const float adx = absf(dx), ady = absf(dy);
+    // slope / 1/slope beyond 2^20: the reference chain saturates (s*s + 1 == s*s, NaNs at 0)
+    if (!(adx > 1e-6f * ady) || !(ady > 1e-6f * adx) || !(w > 0.01f * fourR2) || !(c2 < 1e30f))
+        return 2;
+    const float dot = x1 * x2 + y1 * y2;
+    const float cross = x1 * y2 - x2 * y1;
+    const float L = dot + (c.minHelixRadius2 - c.helixImpactMargin2);
+    const float rhs = cross * cross * w;  // Rt^2 c^2
+    if (!(absf(L) < 1e15f) || !(rhs < 1e30f)) return 2;
+    const float lo = L - delta, hi = L + delta;
+    if (lo > 0.f && lo * lo * c2 > rhs) return 1;          // L - delta > Rt
+    if (hi < 0.f || hi * hi * c2 < rhs) return 0;          // L + delta < Rt
+    return 2;
+}
+
 // ---------------------------------------------------------------------------
 // Fine (r, z) cells inside every reference grid bin — a pruning index that is NOT part of
 // the reference: the reference tests every spacepoint of the (2*scope+1)^2 neighbour bins
