@@ -4,7 +4,7 @@ kernel of one event) + the --set full counters of the search kernels + per-sourc
 usage: ncu_summary.py launches.csv full.ncu-rep lib.so out.md traffic.json"""
 import csv, io, json, subprocess, sys
 launches, rep, lib, out_md, out_json = sys.argv[1:6]
-rows = [r for r in csv.reader(open(launches)) if len(r) > 10 and r[0].isdigit()]
+rows = [r for r in csv.reader(open(launches)) if len(r) > 10 and r[0].isdigit() and "b200seed::" in r[4]]
 ev = rows[len(rows) // 2:]            # the second (warm) event of --profile-one
 md = ["# ncu summary (one 10k-particle event, second pass of `bench.py --profile-one`)", "",
       "## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`; cold-cache, serialised: compare shares)", "",

@@ -41,8 +41,8 @@ inline size_t align_up(size_t v, size_t a) {
 struct Layout {
     size_t control, cell_cnt, bin_of, blk_hist, bin_off, cell_off, sorted_index, sorted_bin, sp4,
         var2, csp4, ccanon, cnt, off, seed_cnt, seed_off, seed_b, seed_t, seed_w, arena_b, arena_t,
-        dump, total;
-    size_t zero_bytes;  // control block + cell populations: cleared at the start of an event
+        dump, gather_state, total;
+    size_t zero_bytes;  // control block, cell populations, look-back state: cleared per event
     uint32_t nblk;
     uint64_t max_doublets, max_dump;
     CellGrid g;
@@ -156,6 +156,8 @@ Layout make_layout(const b200seed_handle* h, uint32_t max_sp) {
     };
     L.control = take(sizeof(Control));
     L.cell_cnt = take(ncells * 4);
+    // look-back status words of k_seed_gather (one per 256 middles) + its ticket counter
+    L.gather_state = take((size_t(L.nblk) + 1) * sizeof(unsigned long long));
     L.zero_bytes = o;
     L.cell_off = take((ncells + 1) * 4);
     L.csp4 = take(n * 16);
@@ -170,7 +172,7 @@ Layout make_layout(const b200seed_handle* h, uint32_t max_sp) {
     L.cnt = take(2 * n * 4);
     L.off = take(2 * n * 4);
     L.seed_cnt = take(n * 4);
-    L.seed_off = take(n * 4);
+    L.seed_off = o;  // (no longer materialised: the scan is fused into k_seed_gather)
     L.seed_b = take(n * K * 4);
     L.seed_t = take(n * K * 4);
     L.seed_w = take(n * K * 4);
@@ -586,9 +588,8 @@ int b200seed_get_timings(b200seed_handle* h, const char** names, float* ms, int 
 }
 
 int b200seed_launches_per_event(const b200seed_handle*, int with_params) {
-    // k_bin_count, k_scan, k_cell_scan, k_bin_scatter, k_doublets, k_triplets, k_scan,
-    // k_seed_gather
-    return 8 + (with_params ? 1 : 0);
+    // k_bin_count, k_scan, k_cell_scan, k_bin_scatter, k_doublets, k_triplets, k_seed_gather
+    return 7 + (with_params ? 1 : 0);
 }
 
 }  // extern "C"
@@ -634,7 +635,6 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
     uint32_t* cnt = reinterpret_cast<uint32_t*>(at(L.cnt));
     uint32_t* off = reinterpret_cast<uint32_t*>(at(L.off));
     uint32_t* seed_cnt = reinterpret_cast<uint32_t*>(at(L.seed_cnt));
-    uint32_t* seed_off = reinterpret_cast<uint32_t*>(at(L.seed_off));
     uint32_t* seed_b = reinterpret_cast<uint32_t*>(at(L.seed_b));
     uint32_t* seed_t = reinterpret_cast<uint32_t*>(at(L.seed_t));
     float* seed_w = reinterpret_cast<float*>(at(L.seed_w));
@@ -725,16 +725,13 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
         k_triplets<<<grid, WARPS_PER_CTA * 32, smem, s>>>(h->dev, a);
     }
     {
-        KernelTimer t(h, s, "scan_seeds");
-        // seed_off = exclusive scan of seed_cnt over the n_valid sorted positions
-        k_scan<<<1, SCAN_THREADS, 0, s>>>(seed_cnt, seed_off, n_sp, &ctrl->n_valid,
-                                          &ctrl->n_seeds_total, nullptr, 0, 0);
-    }
-    {
+        // exclusive scan of the per-middle seed counts fused into the gather (single pass,
+        // decoupled look-back): seeds come out in the reference CPU's order
         KernelTimer t(h, s, "seed_gather");
-        k_seed_gather<<<(n_sp + 255) / 256, 256, 0, s>>>(
-            n_sp, K, ctrl, seed_cnt, seed_off, seed_b, seed_t, seed_w, sorted_index, seed_capacity,
-            d_bottom, d_middle, d_top, d_quality, d_n_seeds, d_counters, d_n_sp);
+        unsigned long long* gs = reinterpret_cast<unsigned long long*>(at(L.gather_state));
+        k_seed_gather<<<nblk, BIN_THREADS, 0, s>>>(
+            n_sp, K, ctrl, seed_cnt, seed_b, seed_t, seed_w, sorted_index, seed_capacity, d_bottom,
+            d_middle, d_top, d_quality, d_n_seeds, d_counters, d_n_sp, gs + 1, gs);
     }
     CUDA_TRY(h, cudaGetLastError());
     return B200SEED_OK;
@@ -781,7 +778,7 @@ int b200seed_form_spacepoints(b200seed_handle* h, void* stream, uint32_t n_meas,
     }
     if (!d_meas_local || !d_meas_surface_index || !d_surfaces || !d_xyz)
         return fail(h, B200SEED_EINVAL, "b200seed_form_spacepoints: null device pointer");
-    const size_t tiles = (size_t(n_meas) + FORM_THREADS - 1) / FORM_THREADS;
+    const size_t tiles = (size_t(n_meas) + FORM_TILE - 1) / FORM_TILE;
     if (tiles > h->form_tiles) {
         // grows rarely; a fresh buffer is zero == "epoch 0", which no call ever uses
         CUDA_TRY(h, cudaStreamSynchronize(s));

@@ -88,6 +88,8 @@ struct __align__(16) TripletDumpRec {
 // ticket base advance on the host with every call, so nothing has to be cleared between events.
 // ---------------------------------------------------------------------------
 constexpr int FORM_THREADS = 256;
+constexpr int FORM_ITEMS = 1;  // measurements per thread (4 was measured slower: 49 CTAs do not cover the table gathers)
+constexpr int FORM_TILE = FORM_THREADS * FORM_ITEMS;
 constexpr unsigned long long FORM_AGGREGATE = 1ull, FORM_PREFIX = 2ull;
 
 __device__ __forceinline__ unsigned long long form_pack(uint32_t epoch, unsigned long long state,
@@ -104,30 +106,40 @@ k_form_spacepoints(const uint32_t n_meas, const float* __restrict__ meas_local,
                    uint32_t* __restrict__ n_sp_out, unsigned long long* __restrict__ status,
                    unsigned long long* __restrict__ ticket_ctr, const unsigned long long ticket_base,
                    const uint32_t epoch) {
-    __shared__ uint32_t s_tile, s_warp[FORM_THREADS / 32], s_prefix;
+    __shared__ uint32_t s_tile, s_warp[FORM_ITEMS][FORM_THREADS / 32], s_prefix;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // tiles are handed out in the order the CTAs start: a CTA only ever waits for tiles
     // whose CTAs are already running
     if (threadIdx.x == 0) s_tile = uint32_t(atomicAdd(ticket_ctr, 1ull) - ticket_base);
     __syncthreads();
     const uint32_t tile = s_tile;
-    const uint32_t i = tile * FORM_THREADS + threadIdx.x;
-    bool valid = false;
-    uint32_t sf = 0;
-    if (i < n_meas) {
-        sf = __ldg(meas_surface + i);
-        // "We use 2D (pixel) measurements only" (spacepoint_formation.ipp:19-23)
-        valid = (!meas_dim || __ldg(meas_dim + i) == 2u) && sf < n_surfaces;
-    }
-    const uint32_t bal = __ballot_sync(0xffffffffu, valid);
-    if (lane == 0) s_warp[warp] = __popc(bal);
-    __syncthreads();
-    uint32_t before = 0, total = 0;
+    // item k of thread t is measurement tile * FORM_TILE + k * FORM_THREADS + t (coalesced)
+    uint32_t sf[FORM_ITEMS], bal[FORM_ITEMS];
+    bool valid[FORM_ITEMS];
 #pragma unroll
-    for (int w = 0; w < FORM_THREADS / 32; ++w) {
-        const uint32_t c = s_warp[w];
-        if (w < int(warp)) before += c;
-        total += c;
+    for (int k = 0; k < FORM_ITEMS; ++k) {
+        const uint32_t i = tile * FORM_TILE + k * FORM_THREADS + threadIdx.x;
+        valid[k] = false;
+        sf[k] = 0;
+        if (i < n_meas) {
+            sf[k] = __ldg(meas_surface + i);
+            // "We use 2D (pixel) measurements only" (spacepoint_formation.ipp:19-23)
+            valid[k] = (!meas_dim || __ldg(meas_dim + i) == 2u) && sf[k] < n_surfaces;
+        }
+        bal[k] = __ballot_sync(0xffffffffu, valid[k]);
+        if (lane == 0) s_warp[k][warp] = __popc(bal[k]);
+    }
+    __syncthreads();
+    uint32_t before[FORM_ITEMS], total = 0;
+#pragma unroll
+    for (int k = 0; k < FORM_ITEMS; ++k) {
+        before[k] = total;
+#pragma unroll
+        for (int w = 0; w < FORM_THREADS / 32; ++w) {
+            const uint32_t c = s_warp[k][w];
+            if (w < int(warp)) before[k] += c;
+            total += c;
+        }
     }
     if (warp == 0) {
         volatile unsigned long long* st = status;
@@ -160,21 +172,26 @@ k_form_spacepoints(const uint32_t n_meas, const float* __restrict__ meas_local,
         }
         if (lane == 0) {
             s_prefix = prefix;
-            if (tile == (n_meas + FORM_THREADS - 1) / FORM_THREADS - 1) *n_sp_out = prefix + total;
+            if (tile == (n_meas + FORM_TILE - 1) / FORM_TILE - 1) *n_sp_out = prefix + total;
         }
     }
     __syncthreads();
-    if (!valid) return;
-    const uint32_t p = s_prefix + before + __popc(bal & ((1u << lane) - 1u));
-    const float l0 = __ldg(meas_local + 2 * size_t(i)), l1 = __ldg(meas_local + 2 * size_t(i) + 1);
-    const b200seed_surface S = surfaces[sf];
-    xyz[3 * size_t(p)] = (S.x_axis[0] * l0 + S.y_axis[0] * l1) + S.translation[0];
-    xyz[3 * size_t(p) + 1] = (S.x_axis[1] * l0 + S.y_axis[1] * l1) + S.translation[1];
-    xyz[3 * size_t(p) + 2] = (S.x_axis[2] * l0 + S.y_axis[2] * l1) + S.translation[2];
-    if (var_z) var_z[p] = 0.f;
-    if (var_r) var_r[p] = 0.f;
-    if (mi1) mi1[p] = i;
-    if (mi2) mi2[p] = 0xFFFFFFFFu;  // INVALID_MEASUREMENT_INDEX (spacepoint_collection.hpp:47-48)
+    const uint32_t prefix = s_prefix;
+#pragma unroll
+    for (int k = 0; k < FORM_ITEMS; ++k) {
+        if (!valid[k]) continue;
+        const uint32_t i = tile * FORM_TILE + k * FORM_THREADS + threadIdx.x;
+        const uint32_t p = prefix + before[k] + __popc(bal[k] & ((1u << lane) - 1u));
+        const float l0 = __ldg(meas_local + 2 * size_t(i)), l1 = __ldg(meas_local + 2 * size_t(i) + 1);
+        const b200seed_surface S = surfaces[sf[k]];
+        xyz[3 * size_t(p)] = (S.x_axis[0] * l0 + S.y_axis[0] * l1) + S.translation[0];
+        xyz[3 * size_t(p) + 1] = (S.x_axis[1] * l0 + S.y_axis[1] * l1) + S.translation[1];
+        xyz[3 * size_t(p) + 2] = (S.x_axis[2] * l0 + S.y_axis[2] * l1) + S.translation[2];
+        if (var_z) var_z[p] = 0.f;
+        if (var_r) var_r[p] = 0.f;
+        if (mi1) mi1[p] = i;
+        if (mi2) mi2[p] = 0xFFFFFFFFu;  // INVALID_MEASUREMENT_INDEX (spacepoint_collection.hpp:47-48)
+    }
 }
 
 // Number of spacepoints of the event: the host's value, or — when the spacepoints were made on
@@ -1298,51 +1315,100 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
 }
 
 // ---------------------------------------------------------------------------
-// seeds in CPU order + counters
+// seeds in CPU order + counters. The offset of a middle's seeds is the exclusive prefix sum of
+// the per-middle counts: computed here in a single pass with decoupled look-back (status word
+// {state:2 @32, value:32}; the words and the ticket counter live in the part of the workspace
+// that is cleared at the start of every event).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(BIN_THREADS)
 k_seed_gather(const uint32_t n_sp, const uint32_t K, const Control* __restrict__ ctrl,
-              const uint32_t* __restrict__ seed_cnt, const uint32_t* __restrict__ seed_off,
-              const uint32_t* __restrict__ seed_b, const uint32_t* __restrict__ seed_t,
-              const float* __restrict__ seed_w, const uint32_t* __restrict__ sorted_index,
-              const uint32_t seed_capacity, uint32_t* __restrict__ out_b,
-              uint32_t* __restrict__ out_m, uint32_t* __restrict__ out_t,
-              float* __restrict__ out_q, uint32_t* __restrict__ out_n,
-              b200seed_counters* __restrict__ counters, const uint32_t* __restrict__ n_sp_dev) {
-    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+              const uint32_t* __restrict__ seed_cnt, const uint32_t* __restrict__ seed_b,
+              const uint32_t* __restrict__ seed_t, const float* __restrict__ seed_w,
+              const uint32_t* __restrict__ sorted_index, const uint32_t seed_capacity,
+              uint32_t* __restrict__ out_b, uint32_t* __restrict__ out_m,
+              uint32_t* __restrict__ out_t, float* __restrict__ out_q, uint32_t* __restrict__ out_n,
+              b200seed_counters* __restrict__ counters, const uint32_t* __restrict__ n_sp_dev,
+              unsigned long long* __restrict__ status, unsigned long long* __restrict__ ticket_ctr) {
+    __shared__ uint32_t s_tile, s_warp[BIN_THREADS / 32], s_prefix;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_tile = uint32_t(atomicAdd(ticket_ctr, 1ull));
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t m = tile * BIN_THREADS + threadIdx.x;
     const uint32_t n_valid = ctrl->n_valid;
-    if (m < n_valid) {
-        const uint32_t n = seed_cnt[m];
-        const uint32_t off = seed_off[m];
-        const uint32_t mi = sorted_index[m];
-        for (uint32_t k = 0; k < n; ++k) {
-            const uint32_t o = off + k;
-            if (o < seed_capacity) {
-                out_b[o] = sorted_index[seed_b[size_t(m) * K + k]];
-                out_m[o] = mi;
-                out_t[o] = sorted_index[seed_t[size_t(m) * K + k]];
-                out_q[o] = seed_w[size_t(m) * K + k];
+    const uint32_t n = (m < n_valid) ? seed_cnt[m] : 0u;
+    const uint32_t incl = warp_incl_scan(n, lane);
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < BIN_THREADS / 32; ++w) {
+        const uint32_t c = s_warp[w];
+        if (w < int(warp)) before += c;
+        total += c;
+    }
+    if (warp == 0) {
+        volatile unsigned long long* st = status;
+        uint32_t prefix = 0;
+        if (tile == 0) {
+            if (lane == 0) st[0] = (FORM_PREFIX << 32) | total;
+        } else {
+            if (lane == 0) st[tile] = (FORM_AGGREGATE << 32) | total;
+            int base = int(tile) - 1;
+            while (true) {
+                const int j = base - int(lane);
+                unsigned long long w = FORM_PREFIX << 32;  // before tile 0: prefix 0
+                if (j >= 0) {
+                    do {
+                        w = st[j];
+                    } while ((w >> 32) == 0ull);
+                }
+                const uint32_t is_pref = __ballot_sync(0xffffffffu, (w >> 32) == FORM_PREFIX);
+                const uint32_t first = is_pref ? uint32_t(__ffs(int(is_pref)) - 1) : 32u;
+                uint32_t v = (lane <= first) ? uint32_t(w) : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                prefix += v;
+                if (is_pref) break;
+                base -= 32;
+            }
+            if (lane == 0) st[tile] = (FORM_PREFIX << 32) | (prefix + total);
+        }
+        if (lane == 0) {
+            s_prefix = prefix;
+            if (tile == gridDim.x - 1) {  // the last tile knows the total
+                const uint32_t all = prefix + total;
+                const uint32_t nout = all < seed_capacity ? all : seed_capacity;
+                *out_n = nout;
+                if (counters) {
+                    b200seed_counters c;
+                    c.n_spacepoints = dev_count(n_sp, n_sp_dev);
+                    c.n_valid = n_valid;
+                    c.n_active_middles = ctrl->n_active;
+                    c.n_mid_bot = ctrl->n_mid_bot;
+                    c.n_mid_top = ctrl->n_mid_top;
+                    c.n_triplets = ctrl->n_triplets;
+                    c.n_seeds = nout;
+                    c.overflow = ctrl->overflow | (all > seed_capacity ? B200SEED_OVF_SEEDS : 0u);
+                    c.pair_tests = ctrl->pair_tests;
+                    c.triplet_tests = ctrl->triplet_tests;
+                    c.pair_visited = ctrl->pair_visited;
+                    *counters = c;
+                }
             }
         }
     }
-    if (m == 0) {
-        const uint32_t total = ctrl->n_seeds_total;
-        const uint32_t n = total < seed_capacity ? total : seed_capacity;
-        *out_n = n;
-        if (counters) {
-            b200seed_counters c;
-            c.n_spacepoints = dev_count(n_sp, n_sp_dev);
-            c.n_valid = n_valid;
-            c.n_active_middles = ctrl->n_active;
-            c.n_mid_bot = ctrl->n_mid_bot;
-            c.n_mid_top = ctrl->n_mid_top;
-            c.n_triplets = ctrl->n_triplets;
-            c.n_seeds = n;
-            c.overflow = ctrl->overflow | (total > seed_capacity ? B200SEED_OVF_SEEDS : 0u);
-            c.pair_tests = ctrl->pair_tests;
-            c.triplet_tests = ctrl->triplet_tests;
-            c.pair_visited = ctrl->pair_visited;
-            *counters = c;
+    __syncthreads();
+    if (n == 0) return;
+    const uint32_t off = s_prefix + before + incl - n;
+    const uint32_t mi = sorted_index[m];
+    for (uint32_t k = 0; k < n; ++k) {
+        const uint32_t o = off + k;
+        if (o < seed_capacity) {
+            out_b[o] = sorted_index[seed_b[size_t(m) * K + k]];
+            out_m[o] = mi;
+            out_t[o] = sorted_index[seed_t[size_t(m) * K + k]];
+            out_q[o] = seed_w[size_t(m) * K + k];
         }
     }
 }
