@@ -116,11 +116,24 @@ CellGrid make_cell_grid(const DevCfg& dev, const b200seed_finder_cfg& finder, ui
     const uint32_t nbins = nb64 ? uint32_t(nb64) : 1u;
     const double per_bin = double(n_sp) / double(nbins);
     uint32_t cpb = 1;
-    while (cpb < 4096u && double(cpb) < 2.0 * per_bin) cpb <<= 1;
+#ifndef B200_CELL_DENSITY
+#define B200_CELL_DENSITY 2.0
+#endif
+#ifndef B200_NR_BIG
+#define B200_NR_BIG 16u
+#endif
+    while (cpb < 4096u && double(cpb) < B200_CELL_DENSITY * per_bin) cpb <<= 1;
     if (cpb < 64u) cpb = 64u;
     while (cpb > 1u && uint64_t(cpb) * nbins > (1ull << 21)) cpb >>= 1;
-    uint32_t nr = cpb >= 2048u ? 32u : (cpb >= 512u ? 16u : (cpb >= 64u ? 8u : 1u));
+#ifndef B200_NR_MID
+#define B200_NR_MID 16u
+#endif
+    uint32_t nr = cpb >= 2048u ? B200_NR_BIG : (cpb >= 512u ? B200_NR_MID : (cpb >= 64u ? 8u : 1u));
     if (nr > cpb) nr = cpb;
+#ifdef B200_FORCE_NR
+    nr = B200_FORCE_NR;
+    cpb = B200_FORCE_NR * B200_FORCE_NZC;
+#endif
     CellGrid g{};
     g.NR = nr;
     g.NZc = cpb / nr;
