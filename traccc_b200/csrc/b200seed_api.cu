@@ -974,6 +974,11 @@ int host_submit(b200seed_handle* h, cudaStream_t s, HostEvent& e) {
         if (d_ms)
             CUDA_TRY(h, cudaMemcpyAsync(d_ms, e.h_ms, size_t(n_meas) * 8, cudaMemcpyHostToDevice, s));
     }
+    // The 56-byte counters record (it carries n_seeds, which sizes the copies below) is written by
+    // k_seed_gather straight into the handle's pinned, device-mapped host word: a D->H copy of it
+    // would queue behind other events' 11-MB parameter copies on the copy engine.
+    static const bool mapped_counters = std::getenv("B200SEED_COPY_COUNTERS") == nullptr;
+    if (mapped_counters) d_c = h->h_pinned;
     int rc = b200seed_run(h, s, n_sp, d_xyz, d_vz, d_vr, d + o_ws, ws_bytes, seed_capacity, e.d_b,
                           e.d_m, e.d_t, e.d_q, d_n, d_c);
     if (rc != B200SEED_OK) return rc;
@@ -983,7 +988,8 @@ int host_submit(b200seed_handle* h, cudaStream_t s, HostEvent& e) {
         if (rc != B200SEED_OK) return rc;
     }
     // the counters struct carries n_seeds: one small read-back, then the sized copies
-    CUDA_TRY(h, cudaMemcpyAsync(h->h_pinned, d_c, sizeof(b200seed_counters), cudaMemcpyDeviceToHost, s));
+    if (!mapped_counters)
+        CUDA_TRY(h, cudaMemcpyAsync(h->h_pinned, d_c, sizeof(b200seed_counters), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(h, host_wait_point(h, s));
     e.submitted = true;
     return B200SEED_OK;
