@@ -261,6 +261,47 @@ def test_parity_other_configs(cfg):
     _check_event(ev, finder=finder, filt=filt, grid=grid)
 
 
+@pytest.mark.parametrize("cfg", ["beam_offset", "phi_window", "z_window", "doublet_cuts", "high_pt",
+                                 "low_pt_wide_impact", "tiny_delta_r_min"])
+def test_parity_cut_configurations(cfg):
+    """Every cut constant the pruning index and the division-free helix pre-decision depend on,
+    moved away from its default (the conservative windows and bands are derived from them):
+    beam position (is_valid_sp, spacepoint_binning_helper.hpp:112-127), phi / z acceptance,
+    deltaR / collision region / deltaZ / cotTheta (doublet_finding_helper.hpp:59-84), minPt and
+    impactMax (helix radius and margin, :120-213)."""
+    from traccc_b200 import seedfilter_config, seedfinder_config, spacepoint_grid_config, toy_detector
+    finder = seedfinder_config()
+    filt = seedfilter_config()
+    kw = dict(shuffle=True)
+    if cfg == "beam_offset":
+        finder.beamPos[0], finder.beamPos[1] = 1.5, -2.0
+    elif cfg == "phi_window":
+        finder.phiMin, finder.phiMax = -2.0, 2.5
+    elif cfg == "z_window":
+        finder.zMin, finder.zMax = -800.0, 1200.0
+    elif cfg == "doublet_cuts":
+        finder.deltaRMin, finder.deltaRMax = 8.0, 120.0
+        finder.collisionRegionMin, finder.collisionRegionMax = -80.0, 150.0
+        finder.deltaZMax = 300.0
+        finder.cotThetaMax = 9.0
+    elif cfg == "high_pt":
+        finder.minPt = 1.0
+        finder.impactMax = 3.0
+    elif cfg == "low_pt_wide_impact":
+        finder.minPt = 0.4
+        finder.impactMax = 25.0
+        kw["pt_range"] = (0.3, 3.0)
+    elif cfg == "tiny_delta_r_min":
+        finder.deltaRMin = 0.5          # the row holding the middle itself can hold partners
+        finder.deltaRMax = 50.0
+        kw["variances"] = 0.05
+    finder.setup()
+    grid = spacepoint_grid_config(finder)
+    ev = toy_detector.generate_event(2500, 77, **kw)
+    got, ref = _check_event(ev, finder=finder, filt=filt, grid=grid)
+    assert got["counters"]["n_mid_bot"] > 1000
+
+
 def test_edge_cases():
     """Empty input, a single spacepoint, only invalid spacepoints, ragged sizes."""
     from traccc_b200 import toy_detector
