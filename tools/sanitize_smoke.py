@@ -1,0 +1,32 @@
+#!/usr/bin/env python
+"""Small end-to-end run (formation -> seeding -> parameters, host-buffer path, inhomogeneous
+field) for compute-sanitizer: `compute-sanitizer --tool memcheck python tools/sanitize_smoke.py`."""
+import os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from traccc_b200 import seedfilter_config, seedfinder_config, seeding, spacepoint_grid_config, toy_detector  # noqa: E402
+
+for n, seed in ((3, 1), (700, 2), (2500, 3)):
+    ev = toy_detector.with_modules(toy_detector.generate_event(n, seed), frac_1d=0.1, seed=seed)
+    f = seedfinder_config()
+    form = seeding.silicon_pixel_spacepoint_formation_algorithm()
+    sa = seeding.triplet_seeding_algorithm(f, spacepoint_grid_config(f), seedfilter_config())
+    tp = seeding.seed_parameter_estimation_algorithm()
+    meas = seeding.measurement_collection.from_event(ev)
+    det = torch.from_numpy(ev.surfaces).cuda()
+    sps = form(det, meas)
+    seeds = sa(sps)
+    params = tp(ev.bfield, meas, sps, seeds)
+    data = torch.zeros((5, 5, 9, 3), device="cuda")
+    data[..., 2] = float(ev.bfield[2])
+    aff = np.zeros((3, 4), np.float32)
+    aff[0, 0] = aff[1, 1] = 4 / 500.0; aff[2, 2] = 8 / 4000.0; aff[:, 3] = (2, 2, 4)
+    p2 = tp(seeding.inhomogeneous_field(aff, data), meas, sps, seeds)
+    torch.cuda.synchronize()
+    print(n, seeds.host_counters()["n_seeds"])
+base = toy_detector.generate_event(1500, 5)
+pool = seeding.EventPool(n_workers=2)
+ios, outs = pool.make_batch([base, base, base])
+pool.process(ios)
+print("pool", [int(io.n_seeds) for io in ios])
