@@ -41,7 +41,7 @@ inline size_t align_up(size_t v, size_t a) {
 struct Layout {
     size_t control, cell_cnt, bin_of, blk_hist, bin_off, cell_off, sorted_index, sorted_bin, sp4,
         var2, csp4, ccanon, cnt, off, seed_cnt, seed_off, seed_b, seed_t, seed_w, arena_b, arena_t,
-        dump, gather_state, total;
+        dump, gather_state, spill_list, total;
     size_t zero_bytes;  // control block, cell populations, look-back state: cleared per event
     uint32_t nblk;
     uint64_t max_doublets, max_dump;
@@ -184,6 +184,7 @@ Layout make_layout(const b200seed_handle* h, uint32_t max_sp) {
     L.var2 = take(n * 8);
     L.cnt = take(2 * n * 4);
     L.off = take(2 * n * 4);
+    L.spill_list = take(n * 4);
     L.seed_cnt = take(n * 4);
     L.seed_off = o;  // (no longer materialised: the scan is fused into k_seed_gather)
     L.seed_b = take(n * K * 4);
@@ -476,7 +477,9 @@ int b200seed_create(const b200seed_finder_cfg* finder, const b200seed_grid_cfg* 
     cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     // allow the large dynamic shared memory configurations
     // (static shared memory counts against the same limit, hence the margin)
-    cudaFuncSetAttribute(k_doublets, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(k_doublets<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         h->smem_optin - 1024);
+    cudaFuncSetAttribute(k_doublets<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          h->smem_optin - 1024);
     cudaFuncSetAttribute(k_triplets, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          h->smem_optin - 1024);
@@ -601,8 +604,9 @@ int b200seed_get_timings(b200seed_handle* h, const char** names, float* ms, int 
 }
 
 int b200seed_launches_per_event(const b200seed_handle*, int with_params) {
-    // k_bin_count, k_scan, k_cell_scan, k_bin_scatter, k_doublets, k_triplets, k_seed_gather
-    return 7 + (with_params ? 1 : 0);
+    // k_bin_count, k_scan, k_cell_scan, k_bin_scatter, k_doublets<false>, k_doublets<true>,
+    // k_triplets, k_seed_gather
+    return 8 + (with_params ? 1 : 0);
 }
 
 }  // extern "C"
@@ -709,7 +713,12 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
         const uint32_t max_grid = uint32_t(h->num_sms) * (32 / WARPS_PER_CTA) * 2;
         if (grid > max_grid) grid = max_grid;
         KernelTimer t(h, s, "doublets");
-        k_doublets<<<grid, WARPS_PER_CTA * 32, smem, s>>>(h->dev, a);
+        a.spill_list = reinterpret_cast<uint32_t*>(at(L.spill_list));
+        k_doublets<false><<<grid, WARPS_PER_CTA * 32, smem, s>>>(h->dev, a);
+        // middles whose lists outgrew the staging area (none for ordinary events: the CTAs
+        // find an empty list and exit)
+        const uint32_t grid_s = grid < uint32_t(h->num_sms) * 4u ? grid : uint32_t(h->num_sms) * 4u;
+        k_doublets<true><<<grid_s, WARPS_PER_CTA * 32, smem, s>>>(h->dev, a);
     }
     {
         TripletArgs a{};

@@ -58,7 +58,8 @@ struct Control {
     uint32_t n_valid;         // written by the first scan
     uint32_t n_seeds_total;   // written by the second scan
     uint32_t ticket_d;        // k_doublets work queue
-    uint32_t pad[2];
+    uint32_t n_spill;         // middles handed to k_doublets<true> (lists longer than the staging area)
+    uint32_t ticket_s;        // its work queue
     unsigned long long pair_visited;  // candidates actually loaded by k_doublets
 };
 
@@ -413,6 +414,7 @@ struct DoubletArgs {
     CellGrid g;
     uint32_t max_doublets;
     uint32_t cap_b, cap_t;        // staged doublets per warp (shared memory)
+    uint32_t* spill_list;         // [n_sp] middles whose lists do not fit the staging area
 };
 
 __device__ __forceinline__ uint32_t lanemask_lt() {
@@ -512,6 +514,12 @@ __host__ __device__ inline uint32_t doublet_smem_words(uint32_t cap_b, uint32_t 
 #ifndef B200_DOUBLET_MIN_CTAS
 #define B200_DOUBLET_MIN_CTAS (32 / B200_WARPS_PER_CTA)
 #endif
+// SPILL == false: every middle; a middle whose lists do not fit the shared-memory staging area
+// is only recorded in spill_list. SPILL == true: those (rare) middles, two scans each — count,
+// then write straight to the arena and bucket-sort the mid-tops. Two instantiations because the
+// second scan and the sort cost the common kernel 76 bytes of register spills when they
+// live in the same function (169 -> 153 us for the 10k-particle event).
+template <bool SPILL>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B200_DOUBLET_MIN_CTAS)
 k_doublets(const DevCfg cfg, const DoubletArgs a) {
     extern __shared__ __align__(16) uint32_t s_mem[];
@@ -533,19 +541,23 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
     unsigned long long pairs = 0ull, visited = 0ull;  // per lane
     uint32_t acc_active = 0, acc_nb = 0, acc_nt = 0;
 
+    const uint32_t n_work = SPILL ? a.ctrl->n_spill : n_valid;
     while (true) {
         uint32_t m = 0;
-        if (lane == 0) m = atomicAdd(&a.ctrl->ticket_d, 1u);
+        if (lane == 0) m = atomicAdd(SPILL ? &a.ctrl->ticket_s : &a.ctrl->ticket_d, 1u);
         m = __shfl_sync(0xffffffffu, m, 0);
-        if (m >= n_valid) break;
+        if (m >= n_work) break;
+        if (SPILL) m = a.spill_list[m];
         const float4 M = __ldg(a.sp4 + m);
         const float2 VM = __ldg(a.var2 + m);  // {varZ, varR}
         NeighbourWalk walk;
         walk.init(cfg, __ldg(a.sorted_bin + m), M.z);
         // the reference tests every spacepoint of the neighbour bins: count them
-        for (uint32_t q = lane; q < walk.nq; q += 32) {
-            const uint32_t b = walk.bin(cfg, q);
-            pairs += __ldg(a.bin_off + b + 1) - __ldg(a.bin_off + b);
+        if (!SPILL) {
+            for (uint32_t q = lane; q < walk.nq; q += 32) {
+                const uint32_t b = walk.bin(cfg, q);
+                pairs += __ldg(a.bin_off + b + 1) - __ldg(a.bin_off + b);
+            }
         }
         // rows that can hold a doublet partner: |r - rM| <= deltaRMax
         const float er = 1e-2f + 1e-5f * (M.w + absf(cfg.deltaRMax));
@@ -564,8 +576,33 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
         uint32_t offB = 0, offT = 0;
         // pass 0: stage the doublets' cell-sorted positions in shared memory. pass 1 (only
         // when a staging list overflowed): same scan, records written straight to the arena.
-        for (int pass = 0; pass < 2; ++pass) {
-            const bool direct = (pass == 1);
+        bool deferred = false;  // handed to the SPILL instantiation
+        // room in the arena for the two lists of this middle (bump allocation)
+        auto allocate = [&](const uint32_t allocT) -> bool {
+            if (lane == 0) {
+                offB = atomicAdd(&a.ctrl->cursor[0], nB);
+                offT = atomicAdd(&a.ctrl->cursor[1], allocT);
+            }
+            offB = __shfl_sync(0xffffffffu, offB, 0);
+            offT = __shfl_sync(0xffffffffu, offT, 0);
+            if (offB > a.max_doublets || nB > a.max_doublets - offB || offT > a.max_doublets ||
+                allocT > a.max_doublets - offT) {
+                if (lane == 0) atomicOr(&a.ctrl->overflow, B200SEED_OVF_DOUBLETS);
+                nB = nT = 0;
+                return false;
+            }
+            return true;
+        };
+        bool run = true;
+        if (SPILL) {
+            // the common kernel counted this middle's doublets already; unsorted mid-tops go to
+            // the second half of a 2 * nT allocation (room to sort in place)
+            nB = a.cnt_b[m];
+            nT = a.cnt_t[m];
+            run = allocate(2u * nT);
+        }
+        for (int pass = SPILL ? 1 : 0; run && pass < (SPILL ? 2 : 1); ++pass) {
+            const bool direct = SPILL;
             uint32_t wB = 0, wT = 0;  // doublets found so far in this pass
             for (uint32_t j0 = 0; j0 < ncombo; j0 += 32) {
                 // lane j: one (neighbour bin, row) -> contiguous run of cells
@@ -585,7 +622,7 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
                 const uint32_t incl = warp_incl_scan(len, lane);
                 const uint32_t excl = incl - len;
                 const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-                if (pass == 0 && lane == 0) visited += total;
+                if (!SPILL && lane == 0) visited += total;
                 for (uint32_t p0 = 0; p0 < total; p0 += 32) {
                     const uint32_t p = p0 + lane;
                     const uint32_t o = owner_lane(incl, p);
@@ -716,21 +753,18 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
                 nB = nT = 0;
                 break;
             }
-            const bool spill = (nB > a.cap_b || nT > a.cap_t);
-            const uint32_t allocT = spill ? 2u * nT : nT;  // room to sort in place
-            if (lane == 0) {
-                offB = atomicAdd(&a.ctrl->cursor[0], nB);
-                offT = atomicAdd(&a.ctrl->cursor[1], allocT);
-            }
-            offB = __shfl_sync(0xffffffffu, offB, 0);
-            offT = __shfl_sync(0xffffffffu, offT, 0);
-            if (offB > a.max_doublets || nB > a.max_doublets - offB || offT > a.max_doublets ||
-                allocT > a.max_doublets - offT) {
-                if (lane == 0) atomicOr(&a.ctrl->overflow, B200SEED_OVF_DOUBLETS);
+            if (nB > a.cap_b || nT > a.cap_t) {
+                // does not fit the staging area: leave the counts for k_doublets<true>
+                if (lane == 0) {
+                    a.spill_list[atomicAdd(&a.ctrl->n_spill, 1u)] = m;
+                    a.cnt_b[m] = nB;
+                    a.cnt_t[m] = nT;
+                }
                 nB = nT = 0;
+                deferred = true;
                 break;
             }
-            if (spill) continue;  // rare: redo the scan in direct mode
+            if (!allocate(nT)) break;
             __syncwarp();
             // common path: lin_circle of every staged doublet, full lanes
             for (uint32_t k = lane; k < nB; k += 32) {
@@ -817,7 +851,7 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
             break;
         }
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0 && !deferred) {
             a.cnt_b[m] = nB;
             a.cnt_t[m] = nT;
             a.off_b[m] = offB;
