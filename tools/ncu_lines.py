@@ -1,14 +1,18 @@
 #!/usr/bin/env python
 """Executed warp instructions and stall samples of one kernel per SOURCE LINE: joins the SASS
 page of an .ncu-rep with `nvdisasm -g` line info of the same build (by instruction address).
-usage: ncu_lines.py rep kernel-regex lib.so [top_n]"""
+usage: ncu_lines.py rep kernel-regex lib.so [top_n [mangled-regex [table-index]]]
+(template instantiations share a demangled name: give the mangled section regex, e.g.
+k_doubletsILb0, and the index of the launch among those the kernel regex matches)"""
 import csv, io, os, re, subprocess, sys, tempfile
 rep, kern, lib = sys.argv[1], sys.argv[2], sys.argv[3]
 top_n = int(sys.argv[4]) if len(sys.argv) > 4 else 45
+mangled = sys.argv[5] if len(sys.argv) > 5 else kern
+table = int(sys.argv[6]) if len(sys.argv) > 6 else 0
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{kern}"],
                      capture_output=True, text=True).stdout
 lines = out.splitlines()
-start = next(i for i, l in enumerate(lines) if l.startswith('"Address"'))
+start = [i for i, l in enumerate(lines) if l.startswith('"Address"')][table]
 end = next((i for i in range(start + 1, len(lines)) if lines[i].startswith('"Kernel Name"') or lines[i].startswith('"Address"')), len(lines))
 rows = list(csv.DictReader(io.StringIO("\n".join(lines[start:end]))))
 base = int(rows[0]["Address"], 16)
@@ -19,7 +23,7 @@ dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture
 addr2line, cur, infunc = {}, None, False
 for l in dis.splitlines():
     if l.startswith(".text."):
-        infunc = re.search(kern, l) is not None
+        infunc = re.search(mangled, l) is not None
         continue
     if not infunc:
         continue

@@ -44,9 +44,16 @@ for r in rr[2:]:
         v = float(r[i].replace(",", ""))
         u = units[i].lower()
         return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
-    traffic["k_" + kname.split("k_")[-1]] = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
+    # template instantiations: k_doublets<0> is the common kernel, k_doublets<1> the spill pass
+    tkey = ("k_" + kname.split("k_")[-1]).replace("<0>", "").replace("<1>", "_spill")
+    traffic[tkey] = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
     md.append("")
-    lines = subprocess.run([sys.executable, __file__.replace("ncu_summary", "ncu_lines"), rep, kname, lib, "22"],
+    if "<1>" in kname:      # the spill pass: an empty launch for ordinary events
+        continue
+    base = kname.replace("void ", "").split("<")[0]
+    mangled = base + ("ILb0" if "<0>" in kname else "ILb1" if "<1>" in kname else "")
+    lines = subprocess.run([sys.executable, __file__.replace("ncu_summary", "ncu_lines"), rep, base, lib, "22",
+                            mangled, "1" if "<1>" in kname else "0"],
                            capture_output=True, text=True).stdout
     md += ["Executed warp instructions / stall samples per source line (top 22):", "", "```", lines.rstrip(), "```", ""]
 open(out_md, "w").write("\n".join(md) + "\n")

@@ -542,6 +542,7 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
     uint32_t acc_active = 0, acc_nb = 0, acc_nt = 0;
 
     const uint32_t n_work = SPILL ? a.ctrl->n_spill : n_valid;
+    if (SPILL && n_work == 0u) return;  // the usual case: no ticket traffic at all
     while (true) {
         uint32_t m = 0;
         if (lane == 0) m = atomicAdd(SPILL ? &a.ctrl->ticket_s : &a.ctrl->ticket_d, 1u);
