@@ -22,7 +22,8 @@ if len(sys.argv) > 4:
     kw["eta_max"] = float(sys.argv[4])
 events = [toy_detector.generate_event(particles, 100 + i, **kw) for i in range(n_events)]
 finder = seedfinder_config()
-alg = seeding.triplet_seeding_algorithm(finder, spacepoint_grid_config(finder), seedfilter_config())
+SC = int(os.environ.get("KBENCH_STAGE_CAP", "0"))   # k_doublets staging knob (0 = automatic)
+alg = seeding.triplet_seeding_algorithm(finder, spacepoint_grid_config(finder), seedfilter_config(), stage_cap=SC)
 tpe = seeding.seed_parameter_estimation_algorithm()
 sps = [seeding.spacepoint_collection.from_event(e) for e in events]
 meas = [seeding.measurement_collection.from_event(e) for e in events]
@@ -52,7 +53,7 @@ if os.environ.get("KBENCH_NO_THROUGHPUT"):
 E, S = 32, 8
 evs = [events[i % n_events] for i in range(E)]
 streams = [torch.cuda.Stream() for _ in range(S)]
-algs = [seeding.triplet_seeding_algorithm(finder, spacepoint_grid_config(finder), seedfilter_config())
+algs = [seeding.triplet_seeding_algorithm(finder, spacepoint_grid_config(finder), seedfilter_config(), stage_cap=SC)
         for _ in range(S)]
 tpes = [seeding.seed_parameter_estimation_algorithm() for _ in range(S)]
 outs = [algs[i % S](sps[i % n_events], stream=streams[i % S]) for i in range(E)]

@@ -322,8 +322,11 @@ uint32_t doublet_stage_cap(uint32_t n_sp) {
     if (n_sp <= 300000) return 1024;
     return 2048;
 }
+#ifndef B200_LIST_CAP_SMALL
+#define B200_LIST_CAP_SMALL 96
+#endif
 uint32_t triplet_list_cap(uint32_t n_sp) {
-    if (n_sp <= 80000) return 192;
+    if (n_sp <= 80000) return B200_LIST_CAP_SMALL;
     if (n_sp <= 300000) return 384;
     return 768;
 }
