@@ -318,6 +318,9 @@ struct KernelTimer {
 // doublet staging capacity per warp and direction (shared memory): sized so that the
 // common case never takes the two-pass fallback, bounded to keep >= 2 CTAs per SM.
 uint32_t doublet_stage_cap(uint32_t n_sp) {
+    // 384: 4 CTAs x 31 KB fit the 132-KB shared-memory carve-out, which leaves 124 KB of L1
+    // (512: 200 KB / 56 KB); busier events need the longer lists more than the cache
+    if (n_sp <= 55000) return 384;
     if (n_sp <= 80000) return 512;
     if (n_sp <= 300000) return 1024;
     return 2048;
