@@ -45,10 +45,11 @@ for r in rr[2:]:
         u = units[i].lower()
         return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
     # template instantiations: k_doublets<0> is the common kernel, k_doublets<1> the spill pass
-    tkey = ("k_" + kname.split("k_")[-1]).replace("<0>", "").replace("<1>", "_spill")
+    tkey = ("k_" + kname.split("k_")[-1]).replace("<0>", "")
+    tkey = tkey.replace("<1>", "_spill" if "doublets" in tkey else "_dense")
     traffic[tkey] = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
     md.append("")
-    if "<1>" in kname:      # the spill pass: an empty launch for ordinary events
+    if "<1>" in kname and "doublets" in kname:   # the spill pass: an empty launch for ordinary events
         continue
     base = kname.replace("void ", "").split("<")[0]
     mangled = base + ("ILb0" if "<0>" in kname else "ILb1" if "<1>" in kname else "")

@@ -487,7 +487,9 @@ int b200seed_create(const b200seed_finder_cfg* finder, const b200seed_grid_cfg* 
                          h->smem_optin - 1024);
     cudaFuncSetAttribute(k_doublets<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          h->smem_optin - 1024);
-    cudaFuncSetAttribute(k_triplets, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(k_triplets<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         h->smem_optin - 1024);
+    cudaFuncSetAttribute(k_triplets<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          h->smem_optin - 1024);
     e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -750,7 +752,10 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
         const uint32_t max_grid = uint32_t(h->num_sms) * (32 / WARPS_PER_CTA) * 3 / 2;
         if (grid > max_grid) grid = max_grid;
         KernelTimer t(h, s, "triplets");
-        k_triplets<<<grid, WARPS_PER_CTA * 32, smem, s>>>(h->dev, a);
+        if (n_sp > 80000u)
+            k_triplets<true><<<grid, WARPS_PER_CTA * 32, smem, s>>>(h->dev, a);
+        else
+            k_triplets<false><<<grid, WARPS_PER_CTA * 32, smem, s>>>(h->dev, a);
     }
     {
         // exclusive scan of the per-middle seed counts fused into the gather (single pass,
