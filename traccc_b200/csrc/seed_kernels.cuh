@@ -1228,6 +1228,63 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
                         ncand += __popc(cm);
                     }
                     __syncwarp();
+                    if (ncand > 32u) {
+                        // Many candidates: K rounds of warp-wide selection instead of ranking
+                        // every candidate against all others. Round r picks the best entry of
+                        // (candidates + current top-K) that sorts after the winner of round r-1;
+                        // lane r keeps it. Same result: `before` is a strict total order.
+                        float pw = 0.f, ps = 0.f;        // previous winner
+                        uint32_t pb = 0, pt = 0;
+                        float mw = 0.f, ms = 0.f, mrb = 0.f;  // the entry this lane will hold
+                        uint32_t mb = 0, mt = 0;
+                        uint32_t nnew = 0;
+                        for (uint32_t r = 0; r < K; ++r) {
+                            bool have = false;
+                            float bw = 0.f, bs = 0.f;
+                            uint32_t bb = 0, bt = 0, bsrc = 0;
+                            auto offer = [&](float w, float s_, uint32_t b, uint32_t t, uint32_t src) {
+                                if (r != 0 && !before(pw, ps, pb, pt, w, s_, b, t)) return;
+                                if (!have || before(w, s_, b, t, bw, bs, bb, bt)) {
+                                    have = true;
+                                    bw = w, bs = s_, bb = b, bt = t, bsrc = src;
+                                }
+                            };
+                            for (uint32_t q = lane; q < ncand; q += 32) {
+                                const uint32_t i = cand[q];
+                                const BlockTriplet c = list[i];
+                                offer(c.weight, c.rT, c.key, lpos[i], i);
+                            }
+                            if (lane < ntop)
+                                offer(top_w[lane], top_s[lane], top_b[lane], top_t[lane], 0x8000u | lane);
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) {
+                                const bool oh = __shfl_xor_sync(0xffffffffu, have, o);
+                                const float ow = __shfl_xor_sync(0xffffffffu, bw, o);
+                                const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+                                const uint32_t ob = __shfl_xor_sync(0xffffffffu, bb, o);
+                                const uint32_t ot = __shfl_xor_sync(0xffffffffu, bt, o);
+                                const uint32_t osrc = __shfl_xor_sync(0xffffffffu, bsrc, o);
+                                if (oh && (!have || before(ow, os, ob, ot, bw, bs, bb, bt))) {
+                                    have = true;
+                                    bw = ow, bs = os, bb = ob, bt = ot, bsrc = osrc;
+                                }
+                            }
+                            if (!have) break;  // warp-uniform after the butterfly
+                            pw = bw, ps = bs, pb = bb, pt = bt;
+                            if (lane == r) {
+                                mw = bw, ms = bs, mb = bb, mt = bt;
+                                mrb = (bsrc & 0x8000u) ? top_rb[bsrc & 0x7FFFu] : list[bsrc].curvature;
+                            }
+                            ++nnew;
+                        }
+                        __syncwarp();
+                        if (lane < nnew) {
+                            top_w[lane] = mw, top_s[lane] = ms, top_rb[lane] = mrb;
+                            top_b[lane] = mb, top_t[lane] = mt;
+                        }
+                        ntop = nnew;
+                        ncand = 0;  // nothing left for the ranking path below
+                    }
                     for (uint32_t q0 = 0; q0 < ncand; q0 += 32) {
                         const uint32_t qi = q0 + lane;
                         uint32_t rank = 0xFFu;
