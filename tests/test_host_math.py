@@ -94,6 +94,13 @@ def test_bins_doublets_triplets_bit_exact(n_particles, seed, kw):
                                    _p(np.ascontiguousarray(ref.mb["lc"][rb])),
                                    _p(np.ascontiguousarray(ref.mt["lc"][rt])), _p(ok), _p(c1), _p(out))
     assert (c1 >= ok).all()            # cut-1 is a necessary condition
+    # the division-free pre-filter of k_triplets<DENSE> only ever drops pairs the exact cuts reject
+    rej = np.zeros(len(rm), np.int32)
+    L.b200seed_host_probe_triplet_prefilter(dc, len(rm), _p(np.ascontiguousarray(sp5[rm])),
+                                            _p(np.ascontiguousarray(ref.mb["lc"][rb])),
+                                            _p(np.ascontiguousarray(ref.mt["lc"][rt])), _p(rej))
+    assert not ((rej == 1) & (ok == 1)).any()
+    assert rej.mean() > 0.5, rej.mean()          # and it is worth having
     # compare with the oracle's triplet list restricted to these middles
     key_ref = set(zip(ref.triplets["m"].tolist(), ref.triplets["b"].tolist(), ref.triplets["t"].tolist()))
     got = set(zip(rm[ok == 1].tolist(), ref.mb["other"][rb[ok == 1]].tolist(),
@@ -218,3 +225,57 @@ def test_stage2_predecision_never_contradicts_the_exact_cut(cfg):
             exact, fast = _stage2(dc, arr)
         decided = fast != 2
         assert np.array_equal(fast[decided], exact[decided])
+
+
+def test_triplet_prefilter_is_conservative_at_the_cut_boundaries():
+    """triplet_certainly_rejected (division-free) against the exact triplet_is_compatible on
+    combinations pushed onto the helix-diameter / impact-parameter boundaries: accepted triplets
+    of real events, their top doublet's V shifted until the exact cut flips (bisection), then
+    scattered tightly around the flip. rejected-by-the-pre-filter must imply rejected-by-the-cuts."""
+    L = _lib.lib()
+    finder = seedfinder_config()
+    grid = spacepoint_grid_config(finder)
+    filt = seedfilter_config()
+    dc = _devcfg(finder, grid, filt)
+    ev = toy_detector.generate_event(3000, 23)
+    of, og, ofl = oracle_cfgs(finder, grid, filt)
+    ref = oracle.run(ev.xyz, ev.var_z, ev.var_r, finder=of, grid=og, filt=ofl, dump=True)
+    sp5 = np.concatenate([ev.xyz, ev.var_z[:, None], ev.var_r[:, None]], axis=1).astype(np.float32)
+    mb_key = {(int(m), int(o)): i for i, (m, o) in enumerate(zip(ref.mb["mid"], ref.mb["other"]))}
+    mt_key = {(int(m), int(o)): i for i, (m, o) in enumerate(zip(ref.mt["mid"], ref.mt["other"]))}
+    n = min(20000, len(ref.triplets["m"]))
+    tm, tb, tt = (ref.triplets[k][:n] for k in ("m", "b", "t"))
+    ib = np.array([mb_key[(int(m), int(b))] for m, b in zip(tm, tb)])
+    it = np.array([mt_key[(int(m), int(t))] for m, t in zip(tm, tt)])
+    M = np.ascontiguousarray(sp5[tm])
+    LB = np.ascontiguousarray(ref.mb["lc"][ib])
+    LT0 = np.ascontiguousarray(ref.mt["lc"][it])
+
+    def run(shift):
+        lt = LT0.copy()
+        lt[:, 5] = (LT0[:, 5].astype(np.float64) + shift).astype(np.float32)
+        ok = np.zeros(n, np.int32); c1 = np.zeros(n, np.int32); out = np.zeros((n, 2), np.float32)
+        rej = np.zeros(n, np.int32)
+        L.b200seed_host_probe_triplets(dc, n, _p(M), _p(LB), _p(lt), _p(ok), _p(c1), _p(out))
+        L.b200seed_host_probe_triplet_prefilter(dc, n, _p(M), _p(LB), _p(lt), _p(rej))
+        return ok, rej
+
+    ok0, rej0 = run(np.zeros(n))
+    assert ok0.all() and not rej0.any()
+    for sign in (+1.0, -1.0):
+        lo, hi = np.zeros(n), np.full(n, sign * 0.02)
+        ok_hi, _ = run(hi)
+        brack = ok_hi == 0
+        assert brack.mean() > 0.9
+        for _ in range(45):
+            mid = 0.5 * (lo + hi)
+            okm, rejm = run(mid)
+            assert not ((rejm == 1) & (okm == 1)).any()
+            lo = np.where(okm == 1, mid, lo)
+            hi = np.where(okm == 1, hi, mid)
+        rng = np.random.default_rng(5)
+        for scale in (0.0, 1e-9, 1e-8, 1e-7, 1e-6, 1e-5):
+            ok, rej = run(lo + rng.normal(0, 1, n) * scale)
+            assert not ((rej == 1) & (ok == 1)).any(), (sign, scale)
+        ok, rej = run(hi * 0 + sign * 0.05)            # far beyond the boundary it does reject
+        assert rej[brack].mean() > 0.9

@@ -198,6 +198,9 @@ def lib() -> C.CDLL:
     L.b200seed_host_probe_bins.restype = None
     L.b200seed_host_probe_doublets.argtypes = [vp, u32, vp, vp, vp, vp]
     L.b200seed_host_probe_doublets.restype = None
+    if hasattr(L, "b200seed_host_probe_triplet_prefilter"):
+        L.b200seed_host_probe_triplet_prefilter.argtypes = [vp, u32, vp, vp, vp, vp]
+        L.b200seed_host_probe_triplet_prefilter.restype = None
     if hasattr(L, "b200seed_host_probe_stage2"):   # test-only probe; older A/B builds lack it
         L.b200seed_host_probe_stage2.argtypes = [vp, u32, vp, vp, vp]
         L.b200seed_host_probe_stage2.restype = None

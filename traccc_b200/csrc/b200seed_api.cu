@@ -673,6 +673,8 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
     // canon_key (seed_kernels.cuh) is a 32-bit word
     if (uint64_t(h->dev.scope0 + h->dev.scope1 + 1u) * n_sp > 0xFFFFFFFFull)
         return fail(h, B200SEED_EINVAL, "b200seed_run: too many spacepoints for this neighbor_scope");
+    // k_triplets<DENSE> packs (row, mid-top index) into one word: 27 bits for the index
+    if (n_sp >= (1u << 27)) return fail(h, B200SEED_EINVAL, "b200seed_run: more than 2^27 spacepoints");
 
     CUDA_TRY(h, cudaMemsetAsync(ws, 0, L.zero_bytes, s));
     {
@@ -747,12 +749,13 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
         a.dump = L.max_dump ? reinterpret_cast<TripletDumpRec*>(at(L.dump)) : nullptr;
         a.max_dump = uint32_t(L.max_dump);
         a.list_cap = triplet_list_cap(n_sp);
-        const size_t smem = triplet_smem_per_warp(a.list_cap) * WARPS_PER_CTA;
+        const bool dense = n_sp > 80000u;
+        const size_t smem = triplet_smem_per_warp(a.list_cap, dense) * WARPS_PER_CTA;
         uint32_t grid = (n_sp + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
         const uint32_t max_grid = uint32_t(h->num_sms) * (32 / WARPS_PER_CTA) * 3 / 2;
         if (grid > max_grid) grid = max_grid;
         KernelTimer t(h, s, "triplets");
-        if (n_sp > 80000u)
+        if (dense)
             k_triplets<true><<<grid, WARPS_PER_CTA * 32, smem, s>>>(h->dev, a);
         else
             k_triplets<false><<<grid, WARPS_PER_CTA * 32, smem, s>>>(h->dev, a);
@@ -1354,6 +1357,19 @@ void b200seed_host_probe_triplets(const void* devcfg, uint32_t n, const float* m
         ok[i] = triplet_is_compatible(d, sp_radius(a[0], a[1]), a[4], a[3], b, t, is2, s2, c, ip) ? 1 : 0;
         out[2 * size_t(i)] = c;
         out[2 * size_t(i) + 1] = ip;
+    }
+}
+
+// division-free pre-filter of the triplet cuts for n (middle, lb, lt) combinations:
+// rej[i] = 1 if triplet_certainly_rejected (then the exact cuts must reject as well)
+void b200seed_host_probe_triplet_prefilter(const void* devcfg, uint32_t n, const float* m,
+                                           const float* lb, const float* lt, int32_t* rej) {
+    const DevCfg& d = *static_cast<const DevCfg*>(devcfg);
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* a = m + 5 * size_t(i);
+        const float* pb = lb + 6 * size_t(i);
+        const float* pt = lt + 6 * size_t(i);
+        rej[i] = triplet_certainly_rejected(d, sp_radius(a[0], a[1]), pb[4], pb[5], pt[4], pt[5]) ? 1 : 0;
     }
 }
 

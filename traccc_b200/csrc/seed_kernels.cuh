@@ -972,9 +972,11 @@ __device__ __forceinline__ float warp_min(float v) {
 }
 
 // Per-warp shared memory of k_triplets.
-__host__ __device__ inline size_t triplet_smem_per_warp(uint32_t list_cap) {
+__host__ __device__ inline size_t triplet_smem_per_warp(uint32_t list_cap, bool dense) {
     // list (16) + pos of top (4) + mid-bottom index (4) + order (2) + bonus / rank (1) per entry
-    return size_t(list_cap) * (16 + 4 + 4 + 2 + 1) + MAX_TOPK * 5 * 4 + TCOT_CAP * 4;
+    // + 64 pending (row, mid-top) pairs of k_triplets<DENSE>'s pre-filter
+    return size_t(list_cap) * (16 + 4 + 4 + 2 + 1) + MAX_TOPK * 5 * 4 + TCOT_CAP * 4 +
+           (dense ? 64 * 4 : 0);
 }
 
 // Warp per middle spacepoint (atomic ticket queue). For every block of 32 mid-bottom doublets
@@ -997,7 +999,7 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
     __shared__ unsigned long long s_tests;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t ltmask = lanemask_lt();
-    unsigned char* base = s_raw + triplet_smem_per_warp(a.list_cap) * warp;
+    unsigned char* base = s_raw + triplet_smem_per_warp(a.list_cap, DENSE) * warp;
     BlockTriplet* list = reinterpret_cast<BlockTriplet*>(base);
     uint32_t* lpos = reinterpret_cast<uint32_t*>(base + size_t(a.list_cap) * 16);  // pos of top
     uint32_t* lrow = lpos + a.list_cap;  // index of the mid-bottom doublet
@@ -1007,7 +1009,8 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
     uint32_t* top_b = reinterpret_cast<uint32_t*>(top_rb + MAX_TOPK);
     uint32_t* top_t = top_b + MAX_TOPK;
     float* cot_sm = reinterpret_cast<float*>(top_t + MAX_TOPK);
-    uint16_t* ord = reinterpret_cast<uint16_t*>(cot_sm + TCOT_CAP);  // list order inside a row
+    uint32_t* pend = reinterpret_cast<uint32_t*>(cot_sm + TCOT_CAP);  // [64] (row << 27) | top
+    uint16_t* ord = reinterpret_cast<uint16_t*>(pend + (DENSE ? 64 : 0));  // list order inside a row
     uint8_t* aux = reinterpret_cast<uint8_t*>(ord + a.list_cap);     // bonus count, later rank
     if (threadIdx.x == 0) {
         s_ntrip = 0;
@@ -1408,47 +1411,125 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
 
             // ---- evaluate the (row, mid-top) pairs inside the windows, 32 at a time ----
             const uint32_t base_n = nlist;
-            for (uint32_t p0 = 0; p0 < total; p0 += 32) {
-                const uint32_t p = p0 + lane;
-                const bool valid = p < total;
-                const uint32_t r = owner_lane(incl, p);
-                const uint32_t er = __shfl_sync(0xffffffffu, excl, r);
-                const uint32_t lor = __shfl_sync(0xffffffffu, lo, r);
-                bool ok = false;
-                uint32_t key = 0, pos_t = 0;
-                float curvature = 0.f, impact = 0.f, rT = 0.f;
-                if (valid) {
-                    const uint32_t tt = lor + (p - er);
-                    const float4 ba = __ldg(&LB[row0 + r].a);
-                    const float4 bb = __ldg(&LB[row0 + r].b);
-                    const float4 ta = __ldg(&LT[tt].a);
-                    const float4 tb = __ldg(&LT[tt].b);
-                    LinCircle lb, lt;
-                    lb.cotTheta = ba.x, lb.iDeltaR = ba.y, lb.Er = ba.z, lb.U = ba.w;
-                    lb.V = bb.x, lb.Zo = bb.y;
-                    lt.cotTheta = ta.x, lt.iDeltaR = ta.y, lt.Er = ta.z, lt.U = ta.w;
-                    lt.V = tb.x, lt.Zo = 0.f;
-                    float is2, s2;
-                    triplet_row_constants(cfg, lb.cotTheta, is2, s2);
-                    ok = triplet_is_compatible(cfg, rM, varRM, varZM, lb, lt, is2, s2, curvature,
-                                               impact);
-                    key = __float_as_uint(tb.y);
-                    rT = tb.z;
-                    pos_t = __float_as_uint(tb.w);
+#ifndef B200_PREFILTER_MIN_PAIRS
+#define B200_PREFILTER_MIN_PAIRS 256u
+#endif
+            if (DENSE && total >= B200_PREFILTER_MIN_PAIRS) {
+                // Blocks with hundreds of pairs (busy events). All pairs go through a
+                // division-free pre-filter (only U and V of both doublets) 32 at a time; the
+                // survivors queue up in `pend` and take the exact cuts 32 at a time, at full lane
+                // occupancy, in order (the rows must stay contiguous in the list).
+                auto eval_exact = [&](const uint32_t cnt) {
+                    bool ok = false;
+                    uint32_t key = 0, pos_t = 0, r = 0;
+                    float curvature = 0.f, impact = 0.f, rT = 0.f;
+                    if (lane < cnt) {
+                        const uint32_t e = pend[lane];
+                        r = e >> 27;
+                        const uint32_t tt = e & 0x7FFFFFFu;
+                        const float4 ba = __ldg(&LB[row0 + r].a);
+                        const float4 bb = __ldg(&LB[row0 + r].b);
+                        const float4 ta = __ldg(&LT[tt].a);
+                        const float4 tb = __ldg(&LT[tt].b);
+                        LinCircle lb, lt;
+                        lb.cotTheta = ba.x, lb.iDeltaR = ba.y, lb.Er = ba.z, lb.U = ba.w;
+                        lb.V = bb.x, lb.Zo = bb.y;
+                        lt.cotTheta = ta.x, lt.iDeltaR = ta.y, lt.Er = ta.z, lt.U = ta.w;
+                        lt.V = tb.x, lt.Zo = 0.f;
+                        float is2, s2;
+                        triplet_row_constants(cfg, lb.cotTheta, is2, s2);
+                        ok = triplet_is_compatible(cfg, rM, varRM, varZM, lb, lt, is2, s2, curvature,
+                                                   impact);
+                        key = __float_as_uint(tb.y);
+                        rT = tb.z;
+                        pos_t = __float_as_uint(tb.w);
+                    }
+                    const uint32_t mk = __ballot_sync(0xffffffffu, ok);
+                    const uint32_t k = nlist + __popc(mk & ltmask);
+                    if (ok && k < a.list_cap) {
+                        BlockTriplet e;
+                        e.key = key;
+                        e.curvature = curvature;
+                        e.weight = -impact * cfg.impactWeightFactor;
+                        e.rT = rT;
+                        list[k] = e;
+                        lpos[k] = pos_t;
+                        lrow[k] = row0 + r;
+                    }
+                    nlist += __popc(mk);
+                };
+                uint32_t npend = 0;
+                for (uint32_t p0 = 0; p0 < total; p0 += 32) {
+                    const uint32_t p = p0 + lane;
+                    const uint32_t r = owner_lane(incl, p);
+                    const uint32_t er = __shfl_sync(0xffffffffu, excl, r);
+                    const uint32_t lor = __shfl_sync(0xffffffffu, lo, r);
+                    bool maybe = false;
+                    uint32_t tt = 0;
+                    if (p < total) {
+                        tt = lor + (p - er);
+                        const float Ub = __ldg(&LB[row0 + r].a.w), Vb = __ldg(&LB[row0 + r].b.x);
+                        const float Ut = __ldg(&LT[tt].a.w), Vt = __ldg(&LT[tt].b.x);
+                        maybe = !triplet_certainly_rejected(cfg, rM, Ub, Vb, Ut, Vt);
+                    }
+                    const uint32_t mm = __ballot_sync(0xffffffffu, maybe);
+                    if (maybe) pend[npend + __popc(mm & ltmask)] = (r << 27) | (tt & 0x7FFFFFFu);
+                    npend += __popc(mm);
+                    __syncwarp();
+                    if (npend >= 32u) {
+                        eval_exact(32u);  // first in, first out
+                        __syncwarp();
+                        npend -= 32u;
+                        const uint32_t mv = (lane < npend) ? pend[32u + lane] : 0u;
+                        __syncwarp();
+                        if (lane < npend) pend[lane] = mv;
+                        __syncwarp();
+                    }
                 }
-                const uint32_t mk = __ballot_sync(0xffffffffu, ok);
-                const uint32_t k = nlist + __popc(mk & ltmask);
-                if (ok && k < a.list_cap) {
-                    BlockTriplet e;
-                    e.key = key;
-                    e.curvature = curvature;
-                    e.weight = -impact * cfg.impactWeightFactor;
-                    e.rT = rT;
-                    list[k] = e;
-                    lpos[k] = pos_t;
-                    lrow[k] = row0 + r;
+                if (npend) eval_exact(npend);
+            } else {
+                for (uint32_t p0 = 0; p0 < total; p0 += 32) {
+                    const uint32_t p = p0 + lane;
+                    const bool valid = p < total;
+                    const uint32_t r = owner_lane(incl, p);
+                    const uint32_t er = __shfl_sync(0xffffffffu, excl, r);
+                    const uint32_t lor = __shfl_sync(0xffffffffu, lo, r);
+                    bool ok = false;
+                    uint32_t key = 0, pos_t = 0;
+                    float curvature = 0.f, impact = 0.f, rT = 0.f;
+                    if (valid) {
+                        const uint32_t tt = lor + (p - er);
+                        const float4 ba = __ldg(&LB[row0 + r].a);
+                        const float4 bb = __ldg(&LB[row0 + r].b);
+                        const float4 ta = __ldg(&LT[tt].a);
+                        const float4 tb = __ldg(&LT[tt].b);
+                        LinCircle lb, lt;
+                        lb.cotTheta = ba.x, lb.iDeltaR = ba.y, lb.Er = ba.z, lb.U = ba.w;
+                        lb.V = bb.x, lb.Zo = bb.y;
+                        lt.cotTheta = ta.x, lt.iDeltaR = ta.y, lt.Er = ta.z, lt.U = ta.w;
+                        lt.V = tb.x, lt.Zo = 0.f;
+                        float is2, s2;
+                        triplet_row_constants(cfg, lb.cotTheta, is2, s2);
+                        ok = triplet_is_compatible(cfg, rM, varRM, varZM, lb, lt, is2, s2, curvature,
+                                                   impact);
+                        key = __float_as_uint(tb.y);
+                        rT = tb.z;
+                        pos_t = __float_as_uint(tb.w);
+                    }
+                    const uint32_t mk = __ballot_sync(0xffffffffu, ok);
+                    const uint32_t k = nlist + __popc(mk & ltmask);
+                    if (ok && k < a.list_cap) {
+                        BlockTriplet e;
+                        e.key = key;
+                        e.curvature = curvature;
+                        e.weight = -impact * cfg.impactWeightFactor;
+                        e.rT = rT;
+                        list[k] = e;
+                        lpos[k] = pos_t;
+                        lrow[k] = row0 + r;
+                    }
+                    nlist += __popc(mk);
                 }
-                nlist += __popc(mk);
             }
             __syncwarp();
             if (nlist > a.list_cap) {  // only possible when the list was empty before the block

@@ -529,6 +529,42 @@ B200_HD bool triplet_is_compatible(const DevCfg& c, float rM, float varRM, float
     return true;
 }
 
+// Division-free pre-filter of triplet_is_compatible: true = the (mid-bottom, mid-top) pair is
+// CERTAINLY rejected by the helix-diameter cut (:95-103) or the impact-parameter cut (:127-131),
+// false = undecided (run the exact chain). With dU = Ut - Ub, dV = Vt - Vb (the reference's own
+// first operations, so identical floats) and num = Vb dU - dV Ub:
+//   A = dV / dU,  B = num / dU,  S2 = (dU^2 + dV^2) / dU^2,  B2 = num^2 / dU^2
+//   helix : S2 < B2 D                      <=>  dU^2 + dV^2 < num^2 D
+//   impact: |(A - B rM) rM| > impactMax    <=>  |dV - num rM| rM > impactMax |dU|
+// The reference evaluates B = Vb - A Ub with cancellation: its absolute error is bounded by
+// eB = 2^-22 (|Vb| + |A Ub|); eN = eB |dU| is that bound on num. The polynomials carry a few
+// 2^-24 relative roundings of their own (covered by the 1e-5 factors). A pair is only declared
+// rejected when the inequality holds with those error bounds applied against it. All cuts of
+// the reference are pure rejections, so testing these two first does not change the result.
+// Used by k_triplets<DENSE> only: on ordinary events a 32-row block holds ~23 pairs, the exact
+// evaluation runs once per block whatever it contains, and the filter costs more than it saves.
+B200_HD bool triplet_certainly_rejected(const DevCfg& c, float rM, float Ub, float Vb, float Ut,
+                                        float Vt) {
+    const float dU = Ut - Ub;
+    if (dU == 0.f) return true;  // :88-90
+    const float dV = Vt - Vb;
+    const float adU = absf(dU);
+    const float t1 = Vb * dU, t2 = dV * Ub;
+    const float num = t1 - t2;
+    const float eN = 4.8e-7f * (absf(t1) + absf(t2));
+    const float anum = absf(num);
+    const float s2 = dU * dU + dV * dV;
+    // helix: surely S2 < B2 D
+    const float nlo = anum - eN;
+    if (nlo > 0.f && s2 * 1.00001f < nlo * nlo * c.minHelixDiameter2) return true;
+    // impact: surely |(A - B rM) rM| > impactMax
+    const float nr = num * rM;
+    const float g = absf(dV - nr);
+    const float eG = eN * rM + 2.4e-7f * (absf(dV) + absf(nr));
+    if ((g - eG) * rM > c.impactMax * adU * 1.00001f) return true;
+    return false;
+}
+
 // ---------------------------------------------------------------------------
 // Seed selection (core/include/traccc/seeding/seed_selecting_helper.hpp:28-80)
 // ---------------------------------------------------------------------------
