@@ -41,7 +41,7 @@ inline size_t align_up(size_t v, size_t a) {
 struct Layout {
     size_t control, cell_cnt, bin_of, blk_hist, bin_off, cell_off, sorted_index, sorted_bin, sp4,
         var2, csp4, ccanon, cnt, off, seed_cnt, seed_off, seed_b, seed_t, seed_w, arena_b, arena_t,
-        dump, gather_state, spill_list, total;
+        dump, gather_state, spill_list, active_list, total;
     size_t zero_bytes;  // control block, cell populations, look-back state: cleared per event
     uint32_t nblk;
     uint64_t max_doublets, max_dump;
@@ -185,6 +185,7 @@ Layout make_layout(const b200seed_handle* h, uint32_t max_sp) {
     L.cnt = take(2 * n * 4);
     L.off = take(2 * n * 4);
     L.spill_list = take(n * 4);
+    L.active_list = take(n * 4);
     L.seed_cnt = take(n * 4);
     L.seed_off = o;  // (no longer materialised: the scan is fused into k_seed_gather)
     L.seed_b = take(n * K * 4);
@@ -724,6 +725,9 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
         if (grid > max_grid) grid = max_grid;
         KernelTimer t(h, s, "doublets");
         a.spill_list = reinterpret_cast<uint32_t*>(at(L.spill_list));
+        a.active_list = reinterpret_cast<uint32_t*>(at(L.active_list));
+        a.seed_cnt = seed_cnt;
+        a.n_sp = n_sp;
         k_doublets<false><<<grid, WARPS_PER_CTA * 32, smem, s>>>(h->dev, a);
         // middles whose lists outgrew the staging area (none for ordinary events: the CTAs
         // find an empty list and exit)
@@ -749,6 +753,8 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
         a.dump = L.max_dump ? reinterpret_cast<TripletDumpRec*>(at(L.dump)) : nullptr;
         a.max_dump = uint32_t(L.max_dump);
         a.list_cap = triplet_list_cap(n_sp);
+        a.active_list = reinterpret_cast<const uint32_t*>(at(L.active_list));
+        a.n_sp = n_sp;
         const bool dense = n_sp > 80000u;
         const size_t smem = triplet_smem_per_warp(a.list_cap, dense) * WARPS_PER_CTA;
         uint32_t grid = (n_sp + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
