@@ -30,3 +30,11 @@ pool = seeding.EventPool(n_workers=2)
 ios, outs = pool.make_batch([base, base, base])
 pool.process(ios)
 print("pool", [int(io.n_seeds) for io in ios])
+if os.environ.get("SANITIZE_DENSE"):
+    # busy event: k_triplets<DENSE>, the pre-filter queue and the spill pass of k_doublets
+    ev = toy_detector.generate_event(21000, 9, eta_max=1.5)
+    f = seedfinder_config()
+    sa = seeding.triplet_seeding_algorithm(f, spacepoint_grid_config(f), seedfilter_config(), stage_cap=64)
+    seeds = sa(seeding.spacepoint_collection.from_event(ev))
+    torch.cuda.synchronize()
+    print("dense", ev.n_spacepoints, seeds.host_counters()["n_seeds"], seeds.host_counters()["overflow"])
