@@ -316,23 +316,28 @@ struct KernelTimer {
     }
 };
 
-// doublet staging capacity per warp and direction (shared memory): sized so that the
-// common case never takes the two-pass fallback, bounded to keep >= 2 CTAs per SM.
+// Doublet staging capacity per warp (mid-bottoms; mid-tops: half of it), shared memory.
+// 384: 4 CTAs x 31 KB fit the 132-KB shared-memory carve-out, which leaves 124 KB of L1
+// (512: 200 KB / 56 KB); busier events need the longer lists more than the cache (a 15k-particle
+// event loses 20 % with 384: too many middles take the spill pass). Longer lists than 512 cost
+// occupancy and lose even on the busiest events (100k particles in |eta| < 1, k_doublets:
+// 2048 -> 105 ms at one CTA per SM, 1024 -> 60 ms, 512 -> 40 ms): the spill pass is cheaper.
 uint32_t doublet_stage_cap(uint32_t n_sp) {
-    // 384: 4 CTAs x 31 KB fit the 132-KB shared-memory carve-out, which leaves 124 KB of L1
-    // (512: 200 KB / 56 KB); busier events need the longer lists more than the cache
-    if (n_sp <= 55000) return 384;
-    if (n_sp <= 80000) return 512;
-    if (n_sp <= 300000) return 1024;
-    return 2048;
+    return n_sp <= 55000 ? 384 : 512;
 }
+// Triplet list per warp of k_triplets (shared memory). Small lists mean more resident warps and
+// more L1: 96 entries below 80k spacepoints (192 needed the 233-KB carve-out: 153 -> 148 us on the
+// 10k-particle event), 128 above — the busiest event (100k particles in |eta| < 1) takes
+// 306 ms in k_triplets with 768 entries (one CTA per SM), 144 / 118 / 106 / 110 / 167 ms with
+// 256 / 192 / 128 / 96 / 64.
 #ifndef B200_LIST_CAP_SMALL
 #define B200_LIST_CAP_SMALL 96
 #endif
+#ifndef B200_LIST_CAP_BIG
+#define B200_LIST_CAP_BIG 128
+#endif
 uint32_t triplet_list_cap(uint32_t n_sp) {
-    if (n_sp <= 80000) return B200_LIST_CAP_SMALL;
-    if (n_sp <= 300000) return 384;
-    return 768;
+    return n_sp <= 80000 ? B200_LIST_CAP_SMALL : B200_LIST_CAP_BIG;
 }
 
 }  // namespace
