@@ -1437,7 +1437,7 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
             // ---- evaluate the (row, mid-top) pairs inside the windows, 32 at a time ----
             const uint32_t base_n = nlist;
 #ifndef B200_PREFILTER_MIN_PAIRS
-#define B200_PREFILTER_MIN_PAIRS 256u
+#define B200_PREFILTER_MIN_PAIRS 512u
 #endif
             if (DENSE && total >= B200_PREFILTER_MIN_PAIRS) {
                 // Blocks with hundreds of pairs (busy events). All pairs go through a
