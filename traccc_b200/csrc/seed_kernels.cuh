@@ -3,24 +3,31 @@
 // Pipeline of one event (all on one stream, no host synchronisation, every intermediate
 // addressed through the workspace):
 //
+//   k_form_spacepoints  (optional, the step before the path) 2D measurements -> spacepoints in
+//                    measurement order; single-pass compaction with decoupled look-back
 //   k_bin_count      is_valid_sp + bin index per spacepoint, per-block bin histogram,
 //                    population of the fine (r, z) cells inside every bin
 //   k_scan           single-CTA exclusive scan of the [bin][block] histogram matrix
 //   k_cell_scan      CTA per bin: start of every (r row, z cell) inside the bin
 //   k_bin_scatter    stable scatter into bin-sorted float4 {x,y,z,r} / float2 {varZ,varR}
 //                    (the reference's grid order) + the cell-sorted copy used for pruning
-//   k_doublets       warp per middle (ticket queue): cell windows of the neighbour bins ->
-//                    flattened candidate list -> exact doublet cuts at full lane occupancy,
-//                    ballot/popc compaction, lin_circle, arena write
-//   k_triplets       warp per middle (atomic ticket queue): lane-owns-mid-bottom x loop over
-//                    mid-tops, cut-1 -> ballot compaction -> full cut, compatible-seed bonus,
-//                    per-middle top-N in shared memory
-//   k_scan           exclusive scan of the per-middle seed counts
-//   k_seed_gather    seeds in the reference CPU's order, original spacepoint indices
-//   k_estimate_params one thread per seed
+//   k_doublets<false> warp per middle (ticket queue): cell windows of the neighbour bins ->
+//                    flattened candidate list -> doublet cuts at full lane occupancy (helix cut
+//                    decided by a division-free polynomial, exact chain only near its boundary),
+//                    ballot/popc compaction, lin_circle, arena write; work lists for the next
+//                    kernels (active middles heavy-first, middles whose lists outgrow shared memory)
+//   k_doublets<true> the latter middles only: records written straight to the arena, bucket sort
+//   k_triplets<DENSE> warp per active middle, longest jobs first: lane-owns-mid-bottom windows in
+//                    the cotTheta-sorted mid-tops -> flattened pairs -> exact cuts, compatible-seed
+//                    bonus, per-middle top-N in shared memory (DENSE: candidate compaction, warp
+//                    selection and a division-free pre-filter for the busiest events)
+//   k_seed_gather    seed offsets (single-pass look-back scan) + seeds in the reference CPU's
+//                    order, original spacepoint indices, counters
+//   k_estimate_params one thread per seed, records staged per warp and written coalesced
 //
 // Replaces device/cuda/src/seeding/triplet_seeding_algorithm.cu:30-160 (9 kernels, 7
-// blocking D->H reads between them) and seed_parameter_estimation_algorithm.cu:22-33.
+// blocking D->H reads between them), seed_parameter_estimation_algorithm.cu:22-33 and
+// silicon_pixel_spacepoint_formation_algorithm.cu.
 #pragma once
 
 #include <cuda_runtime.h>
