@@ -702,7 +702,7 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
         k_bin_scatter<<<nblk, BIN_THREADS, 0, s>>>(h->dev, L.g, n_sp, d_xyz, d_var_z, d_var_r, bin_of,
                                                    blk_hist, nblk, sp4, var2, sorted_index,
                                                    sorted_bin, cell_off, cell_cnt, csp4, ccanon,
-                                                   d_n_sp);
+                                                   d_n_sp, ctrl);
     }
     {
         DoubletArgs a{};

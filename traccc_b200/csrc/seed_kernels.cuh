@@ -77,6 +77,8 @@ struct Control {
     uint32_t ticket_s;        // its work queue
     uint32_t n_heavy;         // active middles with much triplet work (front of active_list)
     uint32_t n_light;         // the other active middles (back of active_list)
+    uint32_t has_variance;    // set by k_bin_scatter if any z / radius variance is non-zero
+    uint32_t pad_;
     unsigned long long pair_visited;  // candidates actually loaded by k_doublets
 };
 
@@ -325,7 +327,7 @@ k_bin_scatter(const DevCfg cfg, const CellGrid g, const uint32_t n_sp_max,
               uint32_t* __restrict__ sorted_index, uint32_t* __restrict__ sorted_bin,
               const uint32_t* __restrict__ cell_off, uint32_t* __restrict__ cell_cur,
               float4* __restrict__ csp4, uint32_t* __restrict__ ccanon,
-              const uint32_t* __restrict__ n_sp_dev) {
+              const uint32_t* __restrict__ n_sp_dev, Control* __restrict__ ctrl) {
     __shared__ uint32_t s_bin[BIN_THREADS];
     const uint32_t n_sp = dev_count(n_sp_max, n_sp_dev);
     const uint32_t i = blockIdx.x * BIN_THREADS + threadIdx.x;
@@ -345,7 +347,11 @@ k_bin_scatter(const DevCfg cfg, const CellGrid g, const uint32_t n_sp_max,
     const float r = sp_radius(x, y);
     const float4 P = make_float4(x, y, z, r);
     sp4[pos] = P;
-    var2[pos] = make_float2(var_z ? __ldg(var_z + i) : 0.f, var_r ? __ldg(var_r + i) : 0.f);
+    const float2 VV = make_float2(var_z ? __ldg(var_z + i) : 0.f, var_r ? __ldg(var_r + i) : 0.f);
+    var2[pos] = VV;
+    // the reference's standard input has zero variances (read_spacepoints.cpp:72-77): the search
+    // kernels then skip the per-partner variance loads (same arithmetic with the zeros in place)
+    if (VV.x != 0.f || VV.y != 0.f) ctrl->has_variance = 1u;
     sorted_index[pos] = i;
     sorted_bin[pos] = bin;
     // cell-sorted copy (order inside a cell is arbitrary: nothing downstream depends on it)
@@ -558,6 +564,7 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
     }
     __syncthreads();
     const uint32_t n_valid = a.ctrl->n_valid;
+    const bool has_var = a.ctrl->has_variance != 0u;
     const CellGrid g = a.g;
     unsigned long long pairs = 0ull, visited = 0ull;  // per lane
     uint32_t acc_active = 0, acc_nb = 0, acc_nt = 0;
@@ -681,7 +688,7 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
                             }
                         } else {
                             const uint32_t pos = __ldg(a.ccanon + c);
-                            const float2 V = __ldg(a.var2 + pos);
+                            const float2 V = has_var ? __ldg(a.var2 + pos) : make_float2(0.f, 0.f);
                             const LinCircle l = transform_coordinates(
                                 !top, M.x, M.y, M.z, M.w, VM.x, VM.y, P.x, P.y, P.z, V.x, V.y);
                             DoubletRec r;
@@ -793,7 +800,7 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
                 const uint32_t c = stage_b[k];
                 const float4 P = __ldg(a.csp4 + c);
                 const uint32_t pos = __ldg(a.ccanon + c);
-                const float2 V = __ldg(a.var2 + pos);
+                const float2 V = has_var ? __ldg(a.var2 + pos) : make_float2(0.f, 0.f);
                 const LinCircle l = transform_coordinates(true, M.x, M.y, M.z, M.w, VM.x, VM.y, P.x,
                                                           P.y, P.z, V.x, V.y);
                 DoubletRec r;
@@ -809,7 +816,7 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
                     const uint32_t c = stage_t[k];
                     const float4 P = __ldg(a.csp4 + c);
                     const uint32_t pos = __ldg(a.ccanon + c);
-                    const float2 V = __ldg(a.var2 + pos);
+                    const float2 V = has_var ? __ldg(a.var2 + pos) : make_float2(0.f, 0.f);
                     cot_s[k] = transform_coordinates(false, M.x, M.y, M.z, M.w, VM.x, VM.y, P.x,
                                                      P.y, P.z, V.x, V.y).cotTheta;
                     key_s[k] = canon_key(key_s[k], n_valid, pos);
@@ -860,7 +867,7 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
                     const uint32_t c = stage_t[k];
                     const float4 P = __ldg(a.csp4 + c);
                     const uint32_t pos = __ldg(a.ccanon + c);
-                    const float2 V = __ldg(a.var2 + pos);
+                    const float2 V = has_var ? __ldg(a.var2 + pos) : make_float2(0.f, 0.f);
                     const LinCircle l = transform_coordinates(false, M.x, M.y, M.z, M.w, VM.x, VM.y,
                                                               P.x, P.y, P.z, V.x, V.y);
                     const uint32_t ks = rank_s[k];
