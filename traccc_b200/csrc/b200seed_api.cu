@@ -40,7 +40,7 @@ inline size_t align_up(size_t v, size_t a) {
 
 struct Layout {
     size_t control, cell_cnt, bin_of, blk_hist, bin_off, cell_off, sorted_index, sorted_bin, sp4,
-        var2, csp4, ccanon, cnt, off, seed_cnt, seed_off, seed_b, seed_t, seed_w, arena_b, arena_t,
+        var2, csp4, ccanon, cnt, off, seed_cnt, seed_b, seed_t, seed_w, arena_b, arena_t,
         dump, gather_state, spill_list, active_list, total;
     size_t zero_bytes;  // control block, cell populations, look-back state: cleared per event
     uint32_t nblk;
@@ -187,7 +187,6 @@ Layout make_layout(const b200seed_handle* h, uint32_t max_sp) {
     L.spill_list = take(n * 4);
     L.active_list = take(n * 4);
     L.seed_cnt = take(n * 4);
-    L.seed_off = o;  // (no longer materialised: the scan is fused into k_seed_gather)
     L.seed_b = take(n * K * 4);
     L.seed_t = take(n * K * 4);
     L.seed_w = take(n * K * 4);
