@@ -41,5 +41,40 @@ def main():
         print(name, ev.n_spacepoints, "spacepoints", len(r.seeds["bottom"]), "seeds")
 
 
+def main_next_rows():
+    """Fixtures of the rows either side of the path (tests/golden/next_rows/*.npz): spacepoint
+    formation from module-frame measurements, and parameters in a grid field."""
+    out = os.path.join(HERE, "next_rows")
+    os.makedirs(out, exist_ok=True)
+    ev = toy_detector.with_modules(toy_detector.generate_event(120, 41), frac_1d=0.2, seed=41)
+    f = oracle.form_spacepoints(ev.meas_local, ev.meas_dim, ev.meas_surface_index, ev.surfaces)
+    np.savez_compressed(os.path.join(out, "formation120.npz"), meas_local=ev.meas_local,
+                        meas_dim=ev.meas_dim, meas_surface_index=ev.meas_surface_index,
+                        surfaces=ev.surfaces, xyz=f["xyz"], measurement_index_1=f["measurement_index_1"])
+    print("formation120", len(ev.meas_local), "measurements ->", len(f["xyz"]), "spacepoints")
+    ev = toy_detector.generate_event(150, 42)
+    r = oracle.run(ev.xyz, ev.var_z, ev.var_r, dump=False)
+    n = (9, 9, 17)
+    half = (250.0, 250.0, 2000.0)
+    ax = [np.linspace(-h, h, k) for h, k in zip(half, n)]
+    X, Y, Z = np.meshgrid(*ax, indexing="ij")
+    bz = ev.bfield[2] * (1.0 - 0.15 * (Z / half[2]) ** 2 - 0.05 * (X * X + Y * Y) / half[0] ** 2)
+    br = -0.1 * ev.bfield[2] * Z / half[2]
+    data = np.stack([br * X / half[0], br * Y / half[0], bz], axis=3).astype(np.float32)
+    affine = np.zeros((3, 4), np.float32)
+    for i in range(3):
+        affine[i, i] = (n[i] - 1) / (2.0 * half[i])
+        affine[i, 3] = (n[i] - 1) / 2.0
+    s = r.seeds
+    p = oracle.estimate_params_inhom(s["bottom"], s["middle"], s["top"], ev.xyz, affine, data,
+                                     sp_meas_index=ev.meas_index, meas_local=ev.meas_local,
+                                     meas_surface=ev.meas_surface)
+    np.savez_compressed(os.path.join(out, "inhom_field150.npz"), xyz=ev.xyz, meas_index=ev.meas_index,
+                        meas_local=ev.meas_local, meas_surface=ev.meas_surface, affine=affine,
+                        field=data, sd_b=s["bottom"], sd_m=s["middle"], sd_t=s["top"], params=p)
+    print("inhom_field150", len(p), "parameter records")
+
+
 if __name__ == "__main__":
     main()
+    main_next_rows()

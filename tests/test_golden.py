@@ -57,3 +57,57 @@ def test_cuda_reproduces_golden(path):
     for k in ("n_valid", "n_active_middles", "n_mid_bot", "n_mid_top", "pair_tests", "triplet_tests",
               "n_triplets"):
         assert res["counters"][k] == c[k], k
+
+
+# ---- rows either side of the path (tests/golden/next_rows, made by make_golden.main_next_rows) ----
+NEXT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "next_rows")
+
+
+def test_oracle_reproduces_formation_golden():
+    g = np.load(os.path.join(NEXT, "formation120.npz"))
+    f = oracle.form_spacepoints(g["meas_local"], g["meas_dim"], g["meas_surface_index"], g["surfaces"])
+    assert np.array_equal(f["xyz"].view(np.uint32), g["xyz"].view(np.uint32))
+    assert np.array_equal(f["measurement_index_1"], g["measurement_index_1"])
+
+
+def test_oracle_reproduces_inhom_field_golden():
+    g = np.load(os.path.join(NEXT, "inhom_field150.npz"))
+    p = oracle.estimate_params_inhom(g["sd_b"], g["sd_m"], g["sd_t"], g["xyz"], g["affine"], g["field"],
+                                     sp_meas_index=g["meas_index"], meas_local=g["meas_local"],
+                                     meas_surface=g["meas_surface"])
+    assert rel_close(p["vec"], g["params"]["vec"], 1e-6).all()
+    assert np.array_equal(p["surface_link"], g["params"]["surface_link"])
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_next_row_goldens():
+    import torch
+    from traccc_b200 import seeding
+    g = np.load(os.path.join(NEXT, "formation120.npz"))
+    form = seeding.silicon_pixel_spacepoint_formation_algorithm()
+    meas = seeding.measurement_collection(
+        torch.from_numpy(g["meas_local"]).cuda(), torch.zeros(len(g["meas_local"]), dtype=torch.int64, device="cuda"),
+        torch.from_numpy(g["meas_dim"].view(np.int32)).cuda(),
+        torch.from_numpy(g["meas_surface_index"].view(np.int32)).cuda())
+    sps = form(torch.from_numpy(g["surfaces"]).cuda(), meas)
+    torch.cuda.synchronize()
+    h = sps.to_host()
+    assert np.array_equal(h["xyz"].view(np.uint32), g["xyz"].view(np.uint32))
+    assert np.array_equal(h["measurement_index_1"], g["measurement_index_1"])
+    g = np.load(os.path.join(NEXT, "inhom_field150.npz"))
+    n = len(g["sd_b"])
+    dev = "cuda"
+    i32 = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).to(dev)
+    seeds = seeding.seed_collection(i32(g["sd_b"]), i32(g["sd_m"]), i32(g["sd_t"]),
+                                    torch.zeros(n, dtype=torch.float32, device=dev),
+                                    torch.tensor([n], dtype=torch.int32, device=dev),
+                                    torch.zeros(64, dtype=torch.uint8, device=dev))
+    sp = seeding.spacepoint_collection(torch.from_numpy(g["xyz"]).to(dev), None, None, i32(g["meas_index"]))
+    ms = seeding.measurement_collection(torch.from_numpy(g["meas_local"]).to(dev),
+                                        torch.from_numpy(g["meas_surface"].view(np.int64)).to(dev))
+    tp = seeding.seed_parameter_estimation_algorithm()
+    field = seeding.inhomogeneous_field(g["affine"], torch.from_numpy(g["field"]).to(dev))
+    out = tp.to_host(tp(field, ms, sp, seeds), n)
+    torch.cuda.synchronize()
+    assert rel_close(out["vec"], g["params"]["vec"], 1e-5).all()
+    assert np.array_equal(out["surface_link"], g["params"]["surface_link"])
