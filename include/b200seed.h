@@ -143,7 +143,10 @@ typedef struct b200seed_counters {
                                     bins == candidate pairs the reference tests */
     uint64_t triplet_tests;      /* sum over active middles of nMidBot * nMidTop */
     uint64_t pair_visited;       /* candidate pairs this library actually evaluated (after the
-                                    conservative (r, z) cell pruning) */
+                                    conservative (r, z) cell pruning); a performance counter: it
+                                    depends on how middles are grouped, not only on the event */
+    uint32_t n_fallback_middles; /* middles the group kernel handed to the warp-per-middle kernel */
+    uint32_t reserved_;
 } b200seed_counters;
 
 #define B200SEED_OVF_DOUBLETS 1u /* doublet arena too small: raise max_doublets */
@@ -157,6 +160,9 @@ typedef struct b200seed_counters {
 #define B200SEED_EINVAL -1   /* bad argument / unsupported configuration (std::domain_error upstream) */
 #define B200SEED_ECUDA -2    /* CUDA runtime error (TRACCC_CUDA_ERROR_CHECK upstream) */
 #define B200SEED_ENOMEM -3   /* workspace too small */
+#define B200SEED_EOVERFLOW -4 /* a capacity-bounded buffer was too small: the event's results are
+                                 truncated (counters.overflow says which); the reference never
+                                 truncates, so callers must treat this as a failed event */
 
 typedef struct b200seed_handle b200seed_handle;
 
@@ -187,9 +193,18 @@ int b200seed_set_max_doublets(b200seed_handle* h, uint64_t max_doublets);
 
 /* Tuning knob: mid-bottom doublets of one middle staged in shared memory by the doublet
  * kernel (mid-tops: half of it) before its list is allocated in the arena; longer lists
- * take a second scan that writes straight to the arena. 0 = automatic (512 ... 2048 by
- * event size). Results do not depend on it. */
+ * take a second scan that writes straight to the arena. 0 = automatic (384 up to 55k
+ * spacepoints, 512 above). Values whose shared-memory footprint (80 bytes * cap per CTA) exceeds
+ * the device's opt-in limit are rejected with B200SEED_EINVAL. Results do not depend on it. */
 int b200seed_set_stage_cap(b200seed_handle* h, uint32_t cap);
+
+/* Truncation check for the asynchronous entry points (b200seed_run, b200seed_run_n_on_device):
+ * after the caller has synchronised the stream, returns B200SEED_EOVERFLOW (and the B200SEED_OVF_*
+ * mask in *mask_out, may be NULL) if any event run on this handle since the last call overflowed a
+ * capacity-bounded buffer, B200SEED_OK otherwise; the record is cleared. Works whether or not
+ * d_counters was passed. The host-buffer entry points (b200seed_run_host, b200seed_pool_process)
+ * return B200SEED_EOVERFLOW themselves. */
+int b200seed_check_overflow(b200seed_handle* h, uint32_t* mask_out);
 
 /* Bytes of device scratch b200seed_run needs for events of up to max_spacepoints. */
 size_t b200seed_workspace_bytes(const b200seed_handle* h, uint32_t max_spacepoints);

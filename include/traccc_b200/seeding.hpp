@@ -227,7 +227,12 @@ class triplet_seeding_algorithm {
         out.quality = reinterpret_cast<float*>(base + o_cols + 3 * detail::up256(cap * 4));
         // scratch lives as long as this algorithm object (grown on demand, reused per event)
         const std::size_t need = b200seed_workspace_bytes(m_handle.get(), n);
-        if (need > m_workspace.bytes()) m_workspace = device_allocation(*m_mr, need + need / 4);
+        if (need > m_workspace.bytes()) {
+            // kernels of the previous event may still use the old scratch on this stream: a
+            // caching / pool memory_resource would hand it out again right away
+            if (m_workspace.bytes()) cudaStreamSynchronize(static_cast<cudaStream_t>(m_stream.cudaStream()));
+            m_workspace = device_allocation(*m_mr, need + need / 4);
+        }
         if (spacepoints.size_ptr && n) {
             // resizable input: its size stays on the device, no D->H read
             detail::check(
@@ -248,6 +253,11 @@ class triplet_seeding_algorithm {
                       m_handle.get());
         return out;
     }
+
+    /// After the caller has synchronised the stream: throws std::runtime_error if an event run
+    /// through this object since the last call was truncated by a capacity-bounded buffer (the
+    /// reference never truncates; see B200SEED_EOVERFLOW).
+    void check_complete() const { detail::check(b200seed_check_overflow(m_handle.get(), nullptr), m_handle.get()); }
 
     private:
     std::unique_ptr<b200seed_handle, detail::handle_deleter> m_handle;

@@ -16,6 +16,13 @@ from tests.helpers import canonical_doublets, oracle_cfgs, rel_close
 pytestmark = pytest.mark.gpu
 
 
+def _physics_counters(c):
+    """The counters that are a function of the event alone. pair_visited / n_fallback_middles are
+    performance counters: they depend on which middles share a group of k_doublets_tile, and the
+    order inside a pruning cell (hence the membership of split cells) is not fixed."""
+    return {k: v for k, v in c.items() if k not in ("pair_visited", "n_fallback_middles", "reserved_")}
+
+
 def _run_gpu(ev, finder=None, filt=None, grid=None, dump=True, max_doublets=0, stage_cap=0):
     import torch
     from traccc_b200 import (seedfilter_config, seedfinder_config, seeding,
@@ -341,7 +348,7 @@ def test_run_host_matches_device_path():
     for k in ("bottom", "middle", "top", "quality"):
         assert np.array_equal(res[k], got["seeds"][k])
     assert np.array_equal(res["params"]["vec"].view(np.uint32), got["params"]["vec"].view(np.uint32))
-    assert res["counters"] == got["counters"]
+    assert _physics_counters(res["counters"]) == _physics_counters(got["counters"])
 
 
 def test_event_pool_matches_device_path():
@@ -368,7 +375,7 @@ def test_event_pool_matches_device_path():
         for k in ("bottom", "middle", "top", "quality"):
             assert np.array_equal(res[k], got["seeds"][k])
         assert np.array_equal(res["params"]["vec"].view(np.uint32), got["params"]["vec"].view(np.uint32))
-        assert res["counters"] == got["counters"]
+        assert _physics_counters(res["counters"]) == _physics_counters(got["counters"])
 
 
 def test_overflow_flags():
@@ -405,7 +412,8 @@ def test_determinism_and_properties_large():
     ev = toy_detector.generate_event(20000, 61)
     a, _ = _run_gpu(ev, dump=False)
     b, _ = _run_gpu(ev, dump=False)
-    assert a["counters"] == b["counters"] and a["counters"]["overflow"] == 0
+    assert _physics_counters(a["counters"]) == _physics_counters(b["counters"])
+    assert a["counters"]["overflow"] == 0
     for k in ("bottom", "middle", "top", "quality"):
         assert np.array_equal(a["seeds"][k], b["seeds"][k])
     assert np.array_equal(a["params"]["vec"].view(np.uint32), b["params"]["vec"].view(np.uint32))
@@ -419,3 +427,25 @@ def test_determinism_and_properties_large():
     for g in groups[:5000]:
         assert (np.diff(s["quality"][g]) <= 0).all()
     assert np.isfinite(a["params"]["vec"]).all()
+
+
+@pytest.mark.parametrize("mode", ["tile", "ldgsts"])
+def test_parity_group_kernel(mode, monkeypatch):
+    """k_doublets_tile (groups of neighbouring middles, candidates staged with cp.async.bulk resp.
+    16-byte cp.async; selected with B200SEED_DOUBLETS, off by default — DESIGN.md §5) against the
+    oracle: binning, doublet and triplet sets, seeds, parameters; also with 7 z bins (groups whose
+    neighbourhood has more runs than the kernel's table go back to the warp-per-middle kernel),
+    a forced group size of 1 and of 16, and non-zero variances."""
+    from traccc_b200 import seedfinder_config, spacepoint_grid_config, toy_detector
+    monkeypatch.setenv("B200SEED_DOUBLETS", mode)
+    _check_event(toy_detector.generate_event(1000, 3))
+    _check_event(toy_detector.generate_event(1000, 4, shuffle=True, variances=0.05))
+    _check_event(toy_detector.generate_event(3000, 5, eta_max=1.0))
+    finder = seedfinder_config(cotThetaMax=7.0)      # 7 z bins
+    _check_event(toy_detector.generate_event(1500, 23), finder=finder, grid=spacepoint_grid_config(finder))
+    for gmax in ("1", "16"):
+        monkeypatch.setenv("B200SEED_GROUP_MAX", gmax)
+        got, _ = _check_event(toy_detector.generate_event(2000, 29))
+    monkeypatch.delenv("B200SEED_GROUP_MAX")
+    got, _ = _check_event(toy_detector.generate_event(10000, 31), dump=False)
+    assert got["counters"]["n_fallback_middles"] < got["counters"]["n_valid"]

@@ -8,6 +8,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "b200seed_api.cu")
 DEPS = [SRC, os.path.join(_HERE, "csrc", "seed_kernels.cuh"), os.path.join(_HERE, "csrc", "seed_math.cuh"),
+        os.path.join(_HERE, "csrc", "seed_tile.cuh"),
         os.path.join(_HERE, "..", "include", "b200seed.h")]
 OUT = os.path.join(_HERE, "libb200seed.so")
 
@@ -25,9 +26,11 @@ def build(force: bool = False, verbose: bool = False, out: str = OUT, defines=()
         return out
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(os.path.dirname(out), exist_ok=True)
+    tmp = out + ".tmp"   # built aside and moved into place: a snapshot never sees a partial file
     cmd = ([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) +
-           [f"-D{d}" for d in defines] + ["-o", out, SRC])
+           [f"-D{d}" for d in defines] + ["-o", tmp, SRC])
     subprocess.check_call(cmd)
+    os.replace(tmp, out)
     return out
 
 

@@ -20,6 +20,7 @@
 
 #include "../../include/b200seed.h"
 #include "seed_kernels.cuh"
+#include "seed_tile.cuh"
 
 using namespace b200seed;
 
@@ -41,7 +42,7 @@ inline size_t align_up(size_t v, size_t a) {
 struct Layout {
     size_t control, cell_cnt, bin_of, blk_hist, bin_off, cell_off, sorted_index, sorted_bin, sp4,
         var2, csp4, ccanon, cnt, off, seed_cnt, seed_b, seed_t, seed_w, arena_b, arena_t,
-        dump, gather_state, spill_list, active_list, total;
+        dump, gather_state, spill_list, active_list, group_list, fallback_list, total;
     size_t zero_bytes;  // control block, cell populations, look-back state: cleared per event
     uint32_t nblk;
     uint64_t max_doublets, max_dump;
@@ -66,6 +67,12 @@ struct b200seed_handle {
     uint64_t max_doublets_user = 0;
     uint64_t max_dump = 0;
     uint32_t stage_cap_user = 0;
+    // doublet search: 2 = warp-per-middle k_doublets<0> (default: the faster one),
+    // 0 = k_doublets_tile (groups of middles, cp.async.bulk staging), 1 = the same with 16-byte
+    // cp.async (B200SEED_DOUBLETS=warp|tile|ldgsts, read at b200seed_create)
+    int doublet_mode = 2;
+    uint32_t group_max = 0;      // 0 = automatic (by event size)
+    float group_zspan_mm = 0.f;  // 0 = default
     int num_sms = 148;
     int smem_optin = 0;
     bool timing = false;
@@ -76,6 +83,10 @@ struct b200seed_handle {
     void* d_stage = nullptr;
     size_t d_stage_bytes = 0;
     b200seed_counters* h_pinned = nullptr;  // counters + n_seeds read-back
+    // OR of the overflow masks of the events run on this handle since the last
+    // b200seed_check_overflow: one pinned, device-mapped word that k_seed_gather writes only when
+    // an event was truncated (so a caller that passes d_counters == NULL still learns about it)
+    uint32_t* h_sticky = nullptr;
     // look-back state of b200seed_form_spacepoints (status words + ticket counter)
     cudaEvent_t ev_host = nullptr;  // blocking-sync event of the host-buffer path
     unsigned long long* d_form = nullptr;
@@ -101,6 +112,15 @@ int fail(const b200seed_handle* h, int code, const std::string& msg) {
             return fail(h, B200SEED_ECUDA,                                                \
                         std::string(#expr) + ": " + cudaGetErrorString(e__));             \
     } while (0)
+
+std::string overflow_message(uint32_t ovf) {
+    std::string m = "event truncated:";
+    if (ovf & B200SEED_OVF_DOUBLETS) m += " doublet arena too small (raise b200seed_set_max_doublets);";
+    if (ovf & B200SEED_OVF_SEEDS) m += " seed_capacity too small;";
+    if (ovf & B200SEED_OVF_DUMP) m += " triplet dump buffer too small;";
+    if (ovf & B200SEED_OVF_TRIPLETS) m += " a mid-bottom doublet has more triplets than the list holds;";
+    return m;
+}
 
 uint64_t default_max_doublets(uint32_t max_sp) {
     const double q = 4e-3 * double(max_sp) * double(max_sp);
@@ -186,6 +206,8 @@ Layout make_layout(const b200seed_handle* h, uint32_t max_sp) {
     L.off = take(2 * n * 4);
     L.spill_list = take(n * 4);
     L.active_list = take(n * 4);
+    L.group_list = take(n * 4);
+    L.fallback_list = take(n * 4);
     L.seed_cnt = take(n * 4);
     L.seed_b = take(n * K * 4);
     L.seed_t = take(n * K * 4);
@@ -227,13 +249,22 @@ int compute_axes(const b200seed_grid_cfg& g, DevCfg& d, std::string& why) {
             std::fabs(std::asin(g.impactMax / (rMin)) - std::asin(g.impactMax / g.rMax));
         float deltaPhi = (outerAngle - innerAngle + deltaAngleWithMaxD0) /
                          static_cast<float>(g.phiBinDeflectionCoverage);
-        if (deltaPhi <= 0.) {
+        if (!(deltaPhi > 0.f) || !std::isfinite(deltaPhi)) {
             why =
                 "Delta phi value is equal to or less than zero, leading to an impossible number "
                 "of bins (negative or infinite)";
             return -1;
         }
-        phiBins = static_cast<uint32_t>(std::llround(2 * M_PI / deltaPhi + 0.5));
+        const long long nb = std::llround(2 * M_PI / deltaPhi + 0.5);
+        if (nb < 1 || nb > (1ll << 30)) {
+            why = "Delta phi value leads to an impossible number of phi bins";
+            return -1;
+        }
+        phiBins = static_cast<uint32_t>(nb);
+    }
+    if (!(g.zMax > g.zMin) || !(g.cotThetaMax * g.deltaRMax > 0.f)) {
+        why = "empty z range or non-positive cotThetaMax * deltaRMax";
+        return -1;
     }
     float zBinSize = g.cotThetaMax * g.deltaRMax;
     uint32_t zBins = std::max(static_cast<uint32_t>(1),
@@ -292,6 +323,13 @@ void fill_devcfg(const b200seed_finder_cfg& f, const b200seed_filter_cfg& fl, De
     d.good_spB_min_weight = fl.good_spB_min_weight;
     d.seed_min_weight = fl.seed_min_weight;
     d.spB_min_radius = fl.spB_min_radius;
+    {
+        // bound on |x|, |y| of a valid spacepoint (is_valid_sp: perp to the beam < numRBins)
+        const double rb = double(d.numRBins) + std::sqrt(double(f.beamPos[0]) * f.beamPos[0] +
+                                                         double(f.beamPos[1]) * f.beamPos[1]) + 1.0;
+        const double R2 = double(d.minHelixRadius2);
+        d.fast_bounded = (R2 > 0.0 && R2 < 1e12 && rb < 1e5 && rb < 0.99 * std::sqrt(R2)) ? 1u : 0u;
+    }
 }
 
 struct KernelTimer {
@@ -454,6 +492,8 @@ int b200seed_create(const b200seed_finder_cfg* finder, const b200seed_grid_cfg* 
                         " bins (limit 8192)");
     if (finder->maxSeedsPerSpM > uint32_t(MAX_TOPK))
         return fail(nullptr, B200SEED_EINVAL, "maxSeedsPerSpM > 16 is not supported");
+    if (finder->maxSeedsPerSpM == 0)
+        return fail(nullptr, B200SEED_EINVAL, "maxSeedsPerSpM == 0: no seed could ever be kept");
     if (filter->compatSeedLimit > size_t(MAX_COMPAT))
         return fail(nullptr, B200SEED_EINVAL, "compatSeedLimit > 8 is not supported");
     if (!(finder->deltaRMin >= 0.f))
@@ -488,10 +528,23 @@ int b200seed_create(const b200seed_finder_cfg* finder, const b200seed_grid_cfg* 
     cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     // allow the large dynamic shared memory configurations
     // (static shared memory counts against the same limit, hence the margin)
-    cudaFuncSetAttribute(k_doublets<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(k_doublets<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          h->smem_optin - 1024);
-    cudaFuncSetAttribute(k_doublets<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(k_doublets<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          h->smem_optin - 1024);
+    cudaFuncSetAttribute(k_doublets<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         h->smem_optin - 1024);
+    cudaFuncSetAttribute(k_doublets_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         h->smem_optin - 1024);
+    cudaFuncSetAttribute(k_doublets_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         h->smem_optin - 1024);
+    if (const char* m = std::getenv("B200SEED_DOUBLETS")) {
+        if (!std::strcmp(m, "tile")) h->doublet_mode = 0;
+        else if (!std::strcmp(m, "ldgsts")) h->doublet_mode = 1;
+        else h->doublet_mode = 2;  // "warp" / "legacy"
+    }
+    if (const char* m = std::getenv("B200SEED_GROUP_MAX")) h->group_max = uint32_t(std::atoi(m));
+    if (const char* m = std::getenv("B200SEED_GROUP_ZSPAN")) h->group_zspan_mm = float(std::atof(m));
     cudaFuncSetAttribute(k_triplets<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          h->smem_optin - 1024);
     cudaFuncSetAttribute(k_triplets<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -503,6 +556,12 @@ int b200seed_create(const b200seed_finder_cfg* finder, const b200seed_grid_cfg* 
         delete h;
         return fail(nullptr, B200SEED_ECUDA, msg);
     }
+    if (cudaHostAlloc(reinterpret_cast<void**>(&h->h_sticky), 64, cudaHostAllocMapped | cudaHostAllocPortable) !=
+        cudaSuccess) {
+        delete h;
+        return fail(nullptr, B200SEED_ECUDA, "cudaHostAlloc (overflow word) failed");
+    }
+    *h->h_sticky = 0u;
     *out = h;
     return B200SEED_OK;
 }
@@ -518,6 +577,7 @@ void b200seed_destroy(b200seed_handle* h) {
     if (h->d_form) cudaFree(h->d_form);
     if (h->ev_host) cudaEventDestroy(h->ev_host);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    if (h->h_sticky) cudaFreeHost(h->h_sticky);
     delete h;
 }
 
@@ -558,6 +618,12 @@ int b200seed_set_stage_cap(b200seed_handle* h, uint32_t cap) {
     if (!h) return B200SEED_EINVAL;
     if (cap != 0 && (cap < 16 || cap > 4096 || (cap & 15u)))
         return fail(h, B200SEED_EINVAL, "stage cap must be 0 or a multiple of 16 in [16, 4096]");
+    // k_doublets needs doublet_smem_words(cap, cap / 2) words per warp
+    if (cap != 0 && size_t(WARPS_PER_CTA) * doublet_smem_words(cap, cap / 2) * 4 + 1024 >
+                        size_t(h->smem_optin > 0 ? h->smem_optin : 0))
+        return fail(h, B200SEED_EINVAL,
+                    "stage cap " + std::to_string(cap) + " needs more shared memory than the " +
+                        std::to_string(h->smem_optin) + " bytes a CTA can have on this device");
     h->stage_cap_user = cap;
     return B200SEED_OK;
 }
@@ -616,10 +682,11 @@ int b200seed_get_timings(b200seed_handle* h, const char** names, float* ms, int 
     return n;
 }
 
-int b200seed_launches_per_event(const b200seed_handle*, int with_params) {
-    // k_bin_count, k_scan, k_cell_scan, k_bin_scatter, k_doublets<false>, k_doublets<true>,
-    // k_triplets, k_seed_gather
-    return 8 + (with_params ? 1 : 0);
+int b200seed_launches_per_event(const b200seed_handle* h, int with_params) {
+    // k_bin_count, k_scan, k_cell_scan, k_bin_scatter, k_doublets<0>, k_doublets<1>, k_triplets,
+    // k_seed_gather; the group kernel adds one launch (k_doublets_tile + k_doublets<2>)
+    const int doublets = (h && h->doublet_mode != 2) ? 3 : 2;
+    return 6 + doublets + (with_params ? 1 : 0);
 }
 
 }  // extern "C"
@@ -694,7 +761,17 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
     }
     {
         KernelTimer t(h, s, "cell_scan");
-        k_cell_scan<<<h->nbins, 256, 0, s>>>(cell_cnt, cell_off, bin_off, L.g.CPB, h->nbins);
+        // groups of neighbouring middles for k_doublets_tile: as many members as its mid-top
+        // segments hold for this occupancy (~7e-4 N mid-tops per active middle, with headroom)
+        uint32_t gmax = h->group_max ? h->group_max : uint32_t(double(TILE_QT) * 1500.0 / double(n_sp));
+        gmax = gmax < 1u ? 1u : (gmax > TILE_GCAP ? TILE_GCAP : gmax);
+        const float zspan_mm = h->group_zspan_mm > 0.f ? h->group_zspan_mm : 64.f;
+        uint32_t zspan = uint32_t(zspan_mm * L.g.invZw + 0.5f);
+        if (zspan < 1u) zspan = 1u;
+        k_cell_scan<<<h->nbins, 256, h->doublet_mode == 2 ? 0 : (L.g.CPB + 1) * sizeof(uint32_t), s>>>(
+            cell_cnt, cell_off, bin_off, L.g.CPB, h->nbins,
+            h->doublet_mode == 2 ? nullptr : reinterpret_cast<uint32_t*>(at(L.group_list)), ctrl,
+            L.g.NZc, gmax, zspan, gmax >= 4u ? gmax / 2u : 2u, n_sp);
     }
     {
         KernelTimer t(h, s, "bin_scatter");
@@ -732,11 +809,42 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
         a.active_list = reinterpret_cast<uint32_t*>(at(L.active_list));
         a.seed_cnt = seed_cnt;
         a.n_sp = n_sp;
-        k_doublets<false><<<grid, WARPS_PER_CTA * 32, smem, s>>>(h->dev, a);
+        a.fallback_list = reinterpret_cast<const uint32_t*>(at(L.fallback_list));
+        const uint32_t grid_s = grid < uint32_t(h->num_sms) * 4u ? grid : uint32_t(h->num_sms) * 4u;
+        if (h->doublet_mode == 2) {
+            k_doublets<0><<<grid, WARPS_PER_CTA * 32, smem, s>>>(h->dev, a);
+        } else {
+            TileArgs ta{};
+            ta.bin_off = bin_off;
+            ta.sorted_bin = sorted_bin;
+            ta.var2 = var2;
+            ta.cell_off = cell_off;
+            ta.csp4 = csp4;
+            ta.ccanon = ccanon;
+            ta.group_list = reinterpret_cast<const uint32_t*>(at(L.group_list));
+            ta.cnt_b = a.cnt_b, ta.cnt_t = a.cnt_t, ta.off_b = a.off_b, ta.off_t = a.off_t;
+            ta.arena_b = a.arena_b, ta.arena_t = a.arena_t;
+            ta.ctrl = ctrl;
+            ta.g = L.g;
+            ta.max_doublets = a.max_doublets;
+            ta.fallback_list = reinterpret_cast<uint32_t*>(at(L.fallback_list));
+            ta.active_list = a.active_list;
+            ta.seed_cnt = seed_cnt;
+            ta.n_sp = n_sp;
+            const size_t tsmem = size_t(TILE_WARPS) * sizeof(TileWarp);
+            uint32_t tgrid = uint32_t(h->num_sms) * B200_TILE_MIN_CTAS;
+            const uint32_t need = (n_sp + TILE_WARPS - 1) / TILE_WARPS;
+            if (tgrid > need) tgrid = need;
+            if (h->doublet_mode == 1)
+                k_doublets_tile<1><<<tgrid, TILE_WARPS * 32, tsmem, s>>>(h->dev, ta);
+            else
+                k_doublets_tile<0><<<tgrid, TILE_WARPS * 32, tsmem, s>>>(h->dev, ta);
+            // groups it handed back (doublets that outgrow its queues): warp per middle
+            k_doublets<2><<<grid_s, WARPS_PER_CTA * 32, smem, s>>>(h->dev, a);
+        }
         // middles whose lists outgrew the staging area (none for ordinary events: the CTAs
         // find an empty list and exit)
-        const uint32_t grid_s = grid < uint32_t(h->num_sms) * 4u ? grid : uint32_t(h->num_sms) * 4u;
-        k_doublets<true><<<grid_s, WARPS_PER_CTA * 32, smem, s>>>(h->dev, a);
+        k_doublets<1><<<grid_s, WARPS_PER_CTA * 32, smem, s>>>(h->dev, a);
     }
     {
         TripletArgs a{};
@@ -777,7 +885,7 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
         unsigned long long* gs = reinterpret_cast<unsigned long long*>(at(L.gather_state));
         k_seed_gather<<<nblk, BIN_THREADS, 0, s>>>(
             n_sp, K, ctrl, seed_cnt, seed_b, seed_t, seed_w, sorted_index, seed_capacity, d_bottom,
-            d_middle, d_top, d_quality, d_n_seeds, d_counters, d_n_sp, gs + 1, gs);
+            d_middle, d_top, d_quality, d_n_seeds, d_counters, d_n_sp, gs + 1, gs, h->h_sticky);
     }
     CUDA_TRY(h, cudaGetLastError());
     return B200SEED_OK;
@@ -1050,8 +1158,25 @@ int host_finish(b200seed_handle* h, cudaStream_t s, HostEvent& e, uint32_t* h_n_
         CUDA_TRY(h, host_wait_point(h, s));
         CUDA_TRY(h, cudaEventSynchronize(h->ev_host));
     }
+    if (const uint32_t ovf = h->h_pinned->overflow) {
+        *h->h_sticky = 0u;  // reported here
+        return fail(h, B200SEED_EOVERFLOW, overflow_message(ovf));
+    }
     return B200SEED_OK;
 }
+
+}  // namespace
+
+extern "C" int b200seed_check_overflow(b200seed_handle* h, uint32_t* mask_out) {
+    if (!h) return B200SEED_EINVAL;
+    const uint32_t ovf = h->h_sticky ? *static_cast<volatile uint32_t*>(h->h_sticky) : 0u;
+    if (mask_out) *mask_out = ovf;
+    if (ovf == 0u) return B200SEED_OK;
+    *h->h_sticky = 0u;
+    return fail(h, B200SEED_EOVERFLOW, overflow_message(ovf));
+}
+
+namespace {
 
 HostEvent host_event_of(const b200seed_event_io& io) {
     HostEvent e;

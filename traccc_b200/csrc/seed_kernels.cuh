@@ -80,6 +80,13 @@ struct Control {
     uint32_t has_variance;    // set by k_bin_scatter if any z / radius variance is non-zero
     uint32_t pad_;
     unsigned long long pair_visited;  // candidates actually loaded by k_doublets
+    // k_doublets_tile (seed_tile.cuh): groups of neighbouring middles
+    uint32_t n_group_big;     // groups listed from the front of group_list (many middles: drawn first)
+    uint32_t n_group_small;   // groups listed from the back
+    uint32_t ticket_g;        // its work queue
+    uint32_t n_fallback;      // middles handed back to the warp-per-middle kernel
+    uint32_t ticket_f;        // work queue of that pass
+    uint32_t pad2_;
 };
 
 // One doublet record in the arena: two float4.
@@ -364,9 +371,16 @@ k_bin_scatter(const DevCfg cfg, const CellGrid g, const uint32_t n_sp_max,
 // CTA per reference bin: cell_off[bin * CPB + c] = bin_off[bin] + exclusive scan of the
 // cell populations of this bin; the population array is zeroed again (k_bin_scatter uses
 // it as its cursor). cell_off[nbins * CPB] = n_valid.
+// With group_list != null the CTA also cuts the cell-ordered content of its bin into the work
+// items of k_doublets_tile: a group = up to gmax consecutive (in cell order) spacepoints of one
+// r row inside one block of zspan z cells; descriptor = (first cell-ordered position << 5) |
+// (size - 1). Groups of at least `big` middles are listed from the front (drawn first), the
+// others from the back of group_list[n_sp].
 __global__ void __launch_bounds__(256)
 k_cell_scan(uint32_t* __restrict__ cell_cnt, uint32_t* __restrict__ cell_off,
-            const uint32_t* __restrict__ bin_off, const uint32_t CPB, const uint32_t nbins) {
+            const uint32_t* __restrict__ bin_off, const uint32_t CPB, const uint32_t nbins,
+            uint32_t* __restrict__ group_list, Control* __restrict__ ctrl, const uint32_t NZc,
+            const uint32_t gmax, const uint32_t zspan, const uint32_t big, const uint32_t n_sp) {
     __shared__ uint32_t s_warp[8];
     __shared__ uint32_t s_total;
     const uint32_t bin = blockIdx.x;
@@ -414,6 +428,58 @@ k_cell_scan(uint32_t* __restrict__ cell_cnt, uint32_t* __restrict__ cell_off,
         __syncthreads();
     }
     if (bin == nbins - 1 && threadIdx.x == 0) cell_off[size_t(nbins) * CPB] = carry;
+    if (!group_list) return;
+    // the offsets of this bin in shared memory (dynamic, CPB + 1 words)
+    extern __shared__ uint32_t s_off[];
+    __syncthreads();  // the offsets of this bin, written above by other threads of the CTA
+    for (uint32_t c = threadIdx.x; c < CPB; c += 256) s_off[c] = cell_off[size_t(bin) * CPB + c];
+    if (threadIdx.x == 0) s_off[CPB] = carry;  // end of the bin
+    __syncthreads();
+    const uint32_t NR = CPB / NZc;
+    // groups of this CTA are collected in shared memory and appended with two atomics
+    __shared__ uint32_t s_nbig, s_nsmall, s_bbig, s_bsmall;
+    if (threadIdx.x == 0) s_nbig = s_nsmall = 0u;
+    __syncthreads();
+    // one thread per (row, block of zspan z cells): the block's spacepoints, in near-equal
+    // pieces of at most gmax. pass 0 counts, pass 1 writes: the CTA's groups land in two
+    // contiguous runs of group_list (two global atomics per CTA).
+    const uint32_t zblocks = (NZc + zspan - 1u) / zspan;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (uint32_t bi = threadIdx.x; bi < NR * zblocks; bi += 256) {
+            const uint32_t row = bi / zblocks, zb0 = (bi - row * zblocks) * zspan;
+            const uint32_t zb1 = (zb0 + zspan < NZc) ? (zb0 + zspan) : NZc;
+            const uint32_t start = s_off[row * NZc + zb0];
+            const uint32_t n = s_off[row * NZc + zb1] - start;
+            if (n == 0u) continue;
+            const uint32_t pieces = (n + gmax - 1u) / gmax;
+            if (pass == 0) {
+                // pieces differ by at most one in size: all >= big or all < big unless n / pieces
+                // sits on the threshold; count them one by one (pieces is small)
+                uint32_t nb = 0;
+                for (uint32_t k = 0; k < pieces; ++k)
+                    nb += (uint32_t((unsigned long long)n * (k + 1u) / pieces) -
+                               uint32_t((unsigned long long)n * k / pieces) >= big) ? 1u : 0u;
+                if (nb) atomicAdd(&s_nbig, nb);
+                if (pieces - nb) atomicAdd(&s_nsmall, pieces - nb);
+            } else {
+                for (uint32_t k = 0; k < pieces; ++k) {
+                    const uint32_t a0 = uint32_t((unsigned long long)n * k / pieces);
+                    const uint32_t a1 = uint32_t((unsigned long long)n * (k + 1u) / pieces);
+                    const uint32_t sz = a1 - a0;
+                    const uint32_t slot = (sz >= big) ? (s_bbig + atomicAdd(&s_nbig, 1u))
+                                                      : n_sp - 1u - (s_bsmall + atomicAdd(&s_nsmall, 1u));
+                    group_list[slot] = ((start + a0) << 5) | (sz - 1u);
+                }
+            }
+        }
+        __syncthreads();
+        if (pass == 0 && threadIdx.x == 0) {
+            s_bbig = s_nbig ? atomicAdd(&ctrl->n_group_big, s_nbig) : 0u;
+            s_bsmall = s_nsmall ? atomicAdd(&ctrl->n_group_small, s_nsmall) : 0u;
+            s_nbig = s_nsmall = 0u;
+        }
+        __syncthreads();
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -442,6 +508,7 @@ struct DoubletArgs {
                                   // k_triplets: heavy ones from the front, light ones from the back
     uint32_t* seed_cnt;           // [n_sp] set to 0 here for the middles without work
     uint32_t n_sp;
+    const uint32_t* fallback_list;  // [n_sp] middles handed back by k_doublets_tile (MODE 2)
 };
 
 __device__ __forceinline__ uint32_t lanemask_lt() {
@@ -546,9 +613,14 @@ __host__ __device__ inline uint32_t doublet_smem_words(uint32_t cap_b, uint32_t 
 // then write straight to the arena and bucket-sort the mid-tops. Two instantiations because the
 // second scan and the sort cost the common kernel 76 bytes of register spills when they
 // live in the same function (169 -> 153 us for the 10k-particle event).
-template <bool SPILL>
+// MODE 0: every middle (the whole search in this kernel; kept as the A/B baseline of
+// k_doublets_tile, B200SEED_DOUBLETS=legacy). MODE 1: the spill pass. MODE 2: the middles
+// k_doublets_tile handed back (fallback_list): groups whose doublets outgrow its queues.
+template <int MODE>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B200_DOUBLET_MIN_CTAS)
 k_doublets(const DevCfg cfg, const DoubletArgs a) {
+    constexpr bool SPILL = (MODE == 1);
+    constexpr bool LISTED = (MODE == 2);
     extern __shared__ __align__(16) uint32_t s_mem[];
     __shared__ unsigned long long s_pairs[2];
     __shared__ uint32_t s_acc[3];  // active, nb, nt
@@ -569,14 +641,21 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
     unsigned long long pairs = 0ull, visited = 0ull;  // per lane
     uint32_t acc_active = 0, acc_nb = 0, acc_nt = 0;
 
-    const uint32_t n_work = SPILL ? a.ctrl->n_spill : n_valid;
-    if (SPILL && n_work == 0u) return;  // the usual case: no ticket traffic at all
+    const uint32_t n_work = SPILL ? a.ctrl->n_spill : (LISTED ? a.ctrl->n_fallback : n_valid);
+    if ((SPILL || LISTED) && n_work == 0u) return;  // the usual case: no ticket traffic at all
     while (true) {
         uint32_t m = 0;
-        if (lane == 0) m = atomicAdd(SPILL ? &a.ctrl->ticket_s : &a.ctrl->ticket_d, 1u);
+        if (lane == 0)
+            m = atomicAdd(SPILL ? &a.ctrl->ticket_s : (LISTED ? &a.ctrl->ticket_f : &a.ctrl->ticket_d), 1u);
         m = __shfl_sync(0xffffffffu, m, 0);
         if (m >= n_work) break;
         if (SPILL) m = a.spill_list[m];
+        if (LISTED) m = a.fallback_list[m];
+#ifdef B200_CELL_ORDER_TICKETS
+        // tickets in CELL order: the warps of a CTA then work on middles of the same
+        // (bin, r row, z cell) neighbourhood at the same time and share their candidate cells in L1
+        if (MODE == 0) m = __ldg(a.ccanon + m);
+#endif
         const float4 M = __ldg(a.sp4 + m);
         const float2 VM = __ldg(a.var2 + m);  // {varZ, varR}
         NeighbourWalk walk;
@@ -1625,7 +1704,8 @@ k_seed_gather(const uint32_t n_sp, const uint32_t K, const Control* __restrict__
               uint32_t* __restrict__ out_b, uint32_t* __restrict__ out_m,
               uint32_t* __restrict__ out_t, float* __restrict__ out_q, uint32_t* __restrict__ out_n,
               b200seed_counters* __restrict__ counters, const uint32_t* __restrict__ n_sp_dev,
-              unsigned long long* __restrict__ status, unsigned long long* __restrict__ ticket_ctr) {
+              unsigned long long* __restrict__ status, unsigned long long* __restrict__ ticket_ctr,
+              uint32_t* __restrict__ sticky_overflow) {
     __shared__ uint32_t s_tile, s_warp[BIN_THREADS / 32], s_prefix;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_tile = uint32_t(atomicAdd(ticket_ctr, 1ull));
@@ -1677,6 +1757,10 @@ k_seed_gather(const uint32_t n_sp, const uint32_t K, const Control* __restrict__
                 const uint32_t all = prefix + total;
                 const uint32_t nout = all < seed_capacity ? all : seed_capacity;
                 *out_n = nout;
+                // a truncated event is never silent: the handle's host-mapped word collects the
+                // overflow bits even when the caller passed no counters record
+                const uint32_t ovf = ctrl->overflow | (all > seed_capacity ? B200SEED_OVF_SEEDS : 0u);
+                if (ovf != 0u && sticky_overflow) atomicOr_system(sticky_overflow, ovf);
                 if (counters) {
                     b200seed_counters c;
                     c.n_spacepoints = dev_count(n_sp, n_sp_dev);
@@ -1686,10 +1770,12 @@ k_seed_gather(const uint32_t n_sp, const uint32_t K, const Control* __restrict__
                     c.n_mid_top = ctrl->n_mid_top;
                     c.n_triplets = ctrl->n_triplets;
                     c.n_seeds = nout;
-                    c.overflow = ctrl->overflow | (all > seed_capacity ? B200SEED_OVF_SEEDS : 0u);
+                    c.overflow = ovf;
                     c.pair_tests = ctrl->pair_tests;
                     c.triplet_tests = ctrl->triplet_tests;
                     c.pair_visited = ctrl->pair_visited;
+                    c.n_fallback_middles = ctrl->n_fallback;
+                    c.reserved_ = 0u;
                     *counters = c;
                 }
             }

@@ -42,6 +42,9 @@ struct DevCfg {
     uint32_t compatSeedLimit, maxSeedsPerSpM;
     float good_spB_min_radius, good_spB_weight_increase, good_spT_max_radius,
         good_spT_weight_increase, good_spB_min_weight, seed_min_weight, spB_min_radius;
+    // 1 if every valid spacepoint is so far inside the minimum helix radius that the magnitude
+    // guards of doublet_stage2_fast can never fire (set on the host, see fill_devcfg)
+    uint32_t fast_bounded;
 };
 
 B200_HD uint32_t f2u(float f) {
@@ -320,6 +323,27 @@ B200_HD int doublet_stage2_fast(const DevCfg& c, float x1, float y1, float x2, f
     return 2;
 }
 
+// The same decision without the magnitude guards, for configurations where they cannot fire
+// (DevCfg::fast_bounded: every valid spacepoint has |x|, |y| <= rb with rb < 0.99 R, rb < 1e5,
+// R^2 < 1e12, so w > 0.01 * 4 R^2, c2 < 1e30, |L| < 1e15 and rhs < 1e30 hold for finite inputs;
+// NaN inputs fail every comparison below and come out undecided, like in the guarded version).
+B200_HD int doublet_stage2_fast_bounded(const DevCfg& c, float x1, float y1, float x2, float y2) {
+    const float dx = x2 - x1, dy = y2 - y1;
+    const float c2 = dx * dx + dy * dy;
+    const float adx = absf(dx), ady = absf(dy);
+    if (!(adx > 1e-6f * ady) || !(ady > 1e-6f * adx)) return 2;
+    const float w = 4.f * c.minHelixRadius2 - c2;  // 4 q^2
+    const float dot = x1 * x2 + y1 * y2;
+    const float cross = x1 * y2 - x2 * y1;
+    const float L = dot + (c.minHelixRadius2 - c.helixImpactMargin2);
+    const float rhs = cross * cross * w;  // Rt^2 c^2
+    const float delta = 2e-5f * c.minHelixRadius2;
+    const float lo = L - delta, hi = L + delta;
+    if (lo > 0.f && lo * lo * c2 > rhs) return 1;  // L - delta > Rt
+    if (hi < 0.f || hi * hi * c2 < rhs) return 0;  // L + delta < Rt
+    return 2;
+}
+
 // ---------------------------------------------------------------------------
 // Fine (r, z) cells inside every reference grid bin — a pruning index that is NOT part of
 // the reference: the reference tests every spacepoint of the (2*scope+1)^2 neighbour bins
@@ -359,6 +383,22 @@ B200_HD uint32_t cell_z(const CellGrid& g, uint32_t zb, float z) {
     else
         zg = static_cast<long long>(static_cast<int>(t));
     long long l = zg - static_cast<long long>(zb) * g.NZc;
+    if (l < 0) l = 0;
+    if (l > static_cast<long long>(g.NZc) - 1) l = static_cast<long long>(g.NZc) - 1;
+    return static_cast<uint32_t>(l);
+}
+
+// The same in two steps, for windows shared by several middles (k_doublets_tile): cell_zg is
+// the cell over the whole z axis (monotone in z), cell_z_of turns it into the cell inside
+// reference z bin zb; cell_z_of(g, zb, cell_zg(g, z)) == cell_z(g, zb, z).
+B200_HD int cell_zg(const CellGrid& g, float z) {
+    const float t = (z - g.zMin) * g.invZw;
+    if (!(t >= 0.f)) return 0;
+    if (t >= static_cast<float>(g.NZg)) return static_cast<int>(g.NZg) - 1;
+    return static_cast<int>(t);
+}
+B200_HD uint32_t cell_z_of(const CellGrid& g, uint32_t zb, int zg) {
+    long long l = static_cast<long long>(zg) - static_cast<long long>(zb) * g.NZc;
     if (l < 0) l = 0;
     if (l > static_cast<long long>(g.NZc) - 1) l = static_cast<long long>(g.NZc) - 1;
     return static_cast<uint32_t>(l);
@@ -435,12 +475,11 @@ struct LinCircle {
     float Zo, cotTheta, iDeltaR, Er, U, V;
 };
 
-// doublet_finding_helper::transform_coordinates (:218-272)
-B200_HD LinCircle transform_coordinates(bool bottom, float xM, float yM, float zM, float rM,
-                                        float varianceZM, float varianceRM, float x2, float y2,
-                                        float z2, float varZ2, float varR2) {
-    const float cosPhiM = xM / rM;
-    const float sinPhiM = yM / rM;
+// doublet_finding_helper::transform_coordinates (:218-272). cosPhiM = xM / rM and sinPhiM = yM / rM
+// depend on the middle only: callers that process many doublets of one middle pass them in.
+B200_HD LinCircle transform_coordinates_cs(bool bottom, float cosPhiM, float sinPhiM, float xM, float yM,
+                                           float zM, float rM, float varianceZM, float varianceRM,
+                                           float x2, float y2, float z2, float varZ2, float varR2) {
     const float deltaX = x2 - xM;
     const float deltaY = y2 - yM;
     const float deltaZ = z2 - zM;
@@ -458,6 +497,35 @@ B200_HD LinCircle transform_coordinates(bool bottom, float xM, float yM, float z
     l.V = y * iDeltaR2;
     l.Er = ((varianceZM + varZ2) + (cot_theta * cot_theta) * (varianceRM + varR2)) * iDeltaR2;
     return l;
+}
+B200_HD LinCircle transform_coordinates(bool bottom, float xM, float yM, float zM, float rM,
+                                        float varianceZM, float varianceRM, float x2, float y2,
+                                        float z2, float varZ2, float varR2) {
+    return transform_coordinates_cs(bottom, xM / rM, yM / rM, xM, yM, zM, rM, varianceZM, varianceRM,
+                                    x2, y2, z2, varZ2, varR2);
+}
+
+// doublet_stage1 for a candidate known to lie in a LOWER r row than the middle (so r2 < rM:
+// it can only be a bottom doublet) resp. a HIGHER one (only a top doublet): the same
+// comparisons as doublet_stage1 without the direction selects. true = passes.
+B200_HD bool doublet_stage1_bottom(const DevCfg& c, float rM, float zM, float r2, float z2) {
+    const float dR = rM - r2;
+    const float dz = zM - z2;
+    const float zo = zM * dR - rM * dz;
+    const float acot = absf(dz);
+    return !((dR >= c.deltaRMax) || (dR <= c.deltaRMin) || (acot >= c.cotThetaMax * dR) ||
+             (zo <= c.collisionRegionMin * dR) || (zo >= c.collisionRegionMax * dR) ||
+             (acot >= c.deltaZMax));
+}
+B200_HD bool doublet_stage1_top(const DevCfg& c, float rM, float zM, float r2, float z2) {
+    const float dR = rM - r2;
+    const float dz = zM - z2;
+    const float zo = zM * dR - rM * dz;
+    const float deltaR = -dR, zOrigin = -zo;  // exact negations of the <bottom> operands
+    const float acot = absf(dz);
+    return !((deltaR >= c.deltaRMax) || (deltaR <= c.deltaRMin) || (acot >= c.cotThetaMax * deltaR) ||
+             (zOrigin <= c.collisionRegionMin * deltaR) || (zOrigin >= c.collisionRegionMax * deltaR) ||
+             (acot >= c.deltaZMax));
 }
 
 // ---------------------------------------------------------------------------

@@ -111,8 +111,15 @@ class seed_collection:
         """copy.get_size(): blocking read of the size word."""
         return int(self.n_seeds.item())
 
-    def to_host(self) -> dict:
+    def to_host(self, allow_truncated: bool = False) -> dict:
+        """Synchronises. A truncated event (counters.overflow != 0: a capacity-bounded buffer was
+        too small) raises, like B200SEED_EOVERFLOW of the host-buffer entry points — the
+        reference never truncates."""
         n = self.size()
+        ovf = self.host_counters()["overflow"]
+        if ovf and not allow_truncated:
+            raise B200SeedError(f"event truncated (overflow mask {ovf:#x}): raise max_doublets / "
+                                "the seed capacity")
         return {"bottom": self.bottom_index[:n].cpu().numpy().view(np.uint32),
                 "middle": self.middle_index[:n].cpu().numpy().view(np.uint32),
                 "top": self.top_index[:n].cpu().numpy().view(np.uint32),
@@ -211,12 +218,20 @@ class triplet_seeding_algorithm:
         return int(self.lib.b200seed_launches_per_event(self.h, 1 if with_params else 0))
 
     # --- the hot path ----------------------------------------------------------------
-    def workspace(self, n: int) -> torch.Tensor:
+    def workspace(self, n: int, stream=None) -> torch.Tensor:
         need = self.workspace_bytes(n)
         if self._ws is None or self._ws.numel() < need:
+            if self._ws is not None:
+                # the previous event's kernels may still run on a stream that is not torch's
+                # current one: keep the caching allocator from reusing the old block early
+                self._ws.record_stream(stream or self.stream or torch.cuda.current_stream())
             self._ws = torch.empty(need, dtype=torch.uint8, device=f"cuda:{self.device}")
         self._ws_n = n
         return self._ws
+
+    def check_overflow(self) -> None:
+        """After a synchronisation: raises if an event since the last call was truncated."""
+        _lib.check(self.lib.b200seed_check_overflow(self.h, None), self.h)
 
     def __call__(self, spacepoints: spacepoint_collection, out: seed_collection | None = None,
                  stream=None) -> seed_collection:
@@ -232,7 +247,7 @@ class triplet_seeding_algorithm:
                 torch.empty(cap, dtype=torch.float32, device=dev),
                 torch.zeros(1, dtype=torch.int32, device=dev),
                 torch.zeros(C.sizeof(Counters), dtype=torch.uint8, device=dev))
-        ws = self.workspace(n) if n else None
+        ws = self.workspace(n, stream) if n else None
         tail = (_ptr(spacepoints.xyz), _ptr(spacepoints.z_variance),
                 _ptr(spacepoints.radius_variance), _ptr(ws), ws.numel() if ws is not None else 0,
                 out.capacity, _ptr(out.bottom_index), _ptr(out.middle_index), _ptr(out.top_index),
@@ -522,7 +537,6 @@ class EventPool:
                                                  C.byref(self.filter), C.byref(self.tpe), int(device),
                                                  int(n_workers), C.byref(p)), None)
         self.p = p
-        self._keep = []
 
     def __del__(self):
         p = getattr(self, "p", None)
@@ -532,7 +546,9 @@ class EventPool:
 
     def make_batch(self, events, with_params: bool = True):
         """Pinned host buffers + the b200seed_event_io array for a list of ToyEvent-like
-        objects. Returns (io_array, outputs) where outputs[i] holds the pinned result tensors."""
+        objects. Returns (io_array, outputs) where outputs[i] holds the pinned result tensors
+        (and, under "_inputs", the pinned inputs): the caller owns the batch, the pool keeps
+        nothing alive."""
         K = max(int(self.finder.maxSeedsPerSpM), 1)
         ios = (EventIO * len(events))()
         outs = []
@@ -560,7 +576,7 @@ class EventPool:
                                             out["top"].data_ptr())
             io.quality = out["quality"].data_ptr()
             io.params = out["params"].data_ptr() if with_params else None
-            self._keep.append((inp, out))
+            out["_inputs"] = inp   # the pinned input buffers live as long as the caller's batch
             outs.append(out)
         return ios, outs
 
