@@ -658,6 +658,8 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
 #endif
         const float4 M = __ldg(a.sp4 + m);
         const float2 VM = __ldg(a.var2 + m);  // {varZ, varR}
+        // lin_circle's cosPhiM / sinPhiM (doublet_finding_helper.hpp:225-226) depend on the middle only
+        const float cosM = M.x / M.w, sinM = M.y / M.w;
         NeighbourWalk walk;
         walk.init(cfg, __ldg(a.sorted_bin + m), M.z);
         // the reference tests every spacepoint of the neighbour bins: count them
@@ -768,8 +770,7 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
                         } else {
                             const uint32_t pos = __ldg(a.ccanon + c);
                             const float2 V = has_var ? __ldg(a.var2 + pos) : make_float2(0.f, 0.f);
-                            const LinCircle l = transform_coordinates(
-                                !top, M.x, M.y, M.z, M.w, VM.x, VM.y, P.x, P.y, P.z, V.x, V.y);
+                            const LinCircle l = transform_coordinates_cs(!top, cosM, sinM, M.x, M.y, M.z, M.w, VM.x, VM.y, P.x, P.y, P.z, V.x, V.y);
                             DoubletRec r;
                             r.a = make_float4(l.cotTheta, l.iDeltaR, l.Er, l.U);
                             r.b = make_float4(l.V,
@@ -880,7 +881,7 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
                 const float4 P = __ldg(a.csp4 + c);
                 const uint32_t pos = __ldg(a.ccanon + c);
                 const float2 V = has_var ? __ldg(a.var2 + pos) : make_float2(0.f, 0.f);
-                const LinCircle l = transform_coordinates(true, M.x, M.y, M.z, M.w, VM.x, VM.y, P.x,
+                const LinCircle l = transform_coordinates_cs(true, cosM, sinM, M.x, M.y, M.z, M.w, VM.x, VM.y, P.x,
                                                           P.y, P.z, V.x, V.y);
                 DoubletRec r;
                 r.a = make_float4(l.cotTheta, l.iDeltaR, l.Er, l.U);
@@ -896,7 +897,7 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
                     const float4 P = __ldg(a.csp4 + c);
                     const uint32_t pos = __ldg(a.ccanon + c);
                     const float2 V = has_var ? __ldg(a.var2 + pos) : make_float2(0.f, 0.f);
-                    cot_s[k] = transform_coordinates(false, M.x, M.y, M.z, M.w, VM.x, VM.y, P.x,
+                    cot_s[k] = transform_coordinates_cs(false, cosM, sinM, M.x, M.y, M.z, M.w, VM.x, VM.y, P.x,
                                                      P.y, P.z, V.x, V.y).cotTheta;
                     key_s[k] = canon_key(key_s[k], n_valid, pos);
                 }
@@ -947,7 +948,7 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
                     const float4 P = __ldg(a.csp4 + c);
                     const uint32_t pos = __ldg(a.ccanon + c);
                     const float2 V = has_var ? __ldg(a.var2 + pos) : make_float2(0.f, 0.f);
-                    const LinCircle l = transform_coordinates(false, M.x, M.y, M.z, M.w, VM.x, VM.y,
+                    const LinCircle l = transform_coordinates_cs(false, cosM, sinM, M.x, M.y, M.z, M.w, VM.x, VM.y,
                                                               P.x, P.y, P.z, V.x, V.y);
                     const uint32_t ks = rank_s[k];
                     DoubletRec r;
@@ -1076,6 +1077,27 @@ __device__ __forceinline__ uint32_t cot_upper_bound(const TopCot& cot, uint32_t 
             hi = mid;
     }
     return lo;
+}
+
+// The same two searches over a list that lies completely in shared memory (n >= 1), without
+// data-dependent branches: halve the interval log2(n) times.
+__device__ __forceinline__ uint32_t smem_lower_bound(const float* sm, uint32_t n, float v) {
+    uint32_t base = 0;
+    while (n > 1u) {
+        const uint32_t half = n >> 1;
+        base += (sm[base + half - 1u] < v) ? half : 0u;
+        n -= half;
+    }
+    return base + ((sm[base] < v) ? 1u : 0u);
+}
+__device__ __forceinline__ uint32_t smem_upper_bound(const float* sm, uint32_t n, float v) {
+    uint32_t base = 0;
+    while (n > 1u) {
+        const uint32_t half = n >> 1;
+        base += (sm[base + half - 1u] <= v) ? half : 0u;
+        n -= half;
+    }
+    return base + ((sm[base] <= v) ? 1u : 0u);
 }
 
 __device__ __forceinline__ float warp_max(float v) {
@@ -1210,8 +1232,15 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
                 const float W = 1.004f * sqrt_rn(e2max) + 1.002f * sqrt_rn(sir2) +
                                 4e-6f * (absf(la.x) + maxAbsCot) + 1e-30f;
                 const bool prune = sane && (la.z >= 0.f) && (W < 1e30f) && (sir2 >= 0.f);
-                lo = prune ? cot_lower_bound(top_cot, nt, la.x - W) : 0u;
-                hi = prune ? cot_upper_bound(top_cot, lo, nt, la.x + W) : nt;
+                if (nt <= TCOT_CAP) {
+                    // the whole list is in shared memory: branch-free searches whose trip count
+                    // depends on nt only (the same for all rows of the middle: no divergence)
+                    lo = prune ? smem_lower_bound(cot_sm, nt, la.x - W) : 0u;
+                    hi = prune ? smem_upper_bound(cot_sm, nt, la.x + W) : nt;
+                } else {
+                    lo = prune ? cot_lower_bound(top_cot, nt, la.x - W) : 0u;
+                    hi = prune ? cot_upper_bound(top_cot, lo, nt, la.x + W) : nt;
+                }
                 if (hi < lo) hi = lo;
             }
             const uint32_t wdt = hi - lo;
@@ -1665,17 +1694,17 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
             rows = 32;
         }
         // ---- final per-middle selection (seed_filtering.cpp:84-122) ----
-        if (lane == 0) {
-            uint32_t nout = 0;
-            for (uint32_t i = 0; i < ntop; ++i) {
-                if (i == 0 || cut_per_middle_sp(cfg, top_rb[i], top_w[i])) {
-                    a.seed_b[size_t(m) * K + nout] = top_b[i];
-                    a.seed_t[size_t(m) * K + nout] = top_t[i];
-                    a.seed_w[size_t(m) * K + nout] = top_w[i];
-                    ++nout;
-                }
+        {
+            // lane i decides entry i; survivors keep their order
+            const bool keep = lane < ntop && (lane == 0 || cut_per_middle_sp(cfg, top_rb[lane], top_w[lane]));
+            const uint32_t km = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const uint32_t o = __popc(km & ltmask);
+                a.seed_b[size_t(m) * K + o] = top_b[lane];
+                a.seed_t[size_t(m) * K + o] = top_t[lane];
+                a.seed_w[size_t(m) * K + o] = top_w[lane];
             }
-            a.seed_cnt[m] = nout;
+            if (lane == 0) a.seed_cnt[m] = __popc(km);
         }
         __syncwarp();
     }
