@@ -449,3 +449,22 @@ def test_parity_group_kernel(mode, monkeypatch):
     monkeypatch.delenv("B200SEED_GROUP_MAX")
     got, _ = _check_event(toy_detector.generate_event(10000, 31), dump=False)
     assert got["counters"]["n_fallback_middles"] < got["counters"]["n_valid"]
+
+
+def test_parity_pooled_triplet_kernel(monkeypatch):
+    """k_triplets_pool (eight light middles per warp, one pair queue and one triplet list for all of
+    them; B200SEED_TRIPLETS=pool, off by default — DESIGN.md §5) against the oracle: triplet sets
+    with curvature / weight after the bonus, seeds, parameters; default and tight-filter
+    configurations, maxSeedsPerSpM = 12, non-zero variances."""
+    from traccc_b200 import seedfilter_config, seedfinder_config, spacepoint_grid_config, toy_detector
+    monkeypatch.setenv("B200SEED_TRIPLETS", "pool")
+    _check_event(toy_detector.generate_event(1000, 3))
+    _check_event(toy_detector.generate_event(1000, 4, shuffle=True, variances=0.05))
+    _check_event(toy_detector.generate_event(3000, 5, eta_max=1.0))
+    finder = seedfinder_config(maxSeedsPerSpM=2)
+    filt = seedfilter_config(compatSeedLimit=1, deltaInvHelixDiameter=1e-4, seed_min_weight=100.0)
+    _check_event(toy_detector.generate_event(1500, 37), finder=finder, filt=filt,
+                 grid=spacepoint_grid_config(finder))
+    finder = seedfinder_config(maxSeedsPerSpM=12)
+    _check_event(toy_detector.generate_event(1500, 41), finder=finder, grid=spacepoint_grid_config(finder))
+    _check_event(toy_detector.generate_event(10000, 43), dump=False)

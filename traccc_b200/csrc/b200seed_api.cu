@@ -21,6 +21,7 @@
 #include "../../include/b200seed.h"
 #include "seed_kernels.cuh"
 #include "seed_tile.cuh"
+#include "seed_pool.cuh"
 
 using namespace b200seed;
 
@@ -71,6 +72,9 @@ struct b200seed_handle {
     // 0 = k_doublets_tile (groups of middles, cp.async.bulk staging), 1 = the same with 16-byte
     // cp.async (B200SEED_DOUBLETS=warp|tile|ldgsts, read at b200seed_create)
     int doublet_mode = 2;
+    // triplet search of the light middles: 0 = k_triplets for all (default: faster),
+    // 1 = k_triplets_pool (several middles per warp); B200SEED_TRIPLETS=warp|pool
+    int triplet_pool = 0;
     uint32_t group_max = 0;      // 0 = automatic (by event size)
     float group_zspan_mm = 0.f;  // 0 = default
     int num_sms = 148;
@@ -543,6 +547,9 @@ int b200seed_create(const b200seed_finder_cfg* finder, const b200seed_grid_cfg* 
         else if (!std::strcmp(m, "ldgsts")) h->doublet_mode = 1;
         else h->doublet_mode = 2;  // "warp" / "legacy"
     }
+    if (const char* m = std::getenv("B200SEED_TRIPLETS")) h->triplet_pool = std::strcmp(m, "pool") == 0;
+    cudaFuncSetAttribute(k_triplets_pool, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         h->smem_optin - 1024);
     if (const char* m = std::getenv("B200SEED_GROUP_MAX")) h->group_max = uint32_t(std::atoi(m));
     if (const char* m = std::getenv("B200SEED_GROUP_ZSPAN")) h->group_zspan_mm = float(std::atof(m));
     cudaFuncSetAttribute(k_triplets<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -686,7 +693,8 @@ int b200seed_launches_per_event(const b200seed_handle* h, int with_params) {
     // k_bin_count, k_scan, k_cell_scan, k_bin_scatter, k_doublets<0>, k_doublets<1>, k_triplets,
     // k_seed_gather; the group kernel adds one launch (k_doublets_tile + k_doublets<2>)
     const int doublets = (h && h->doublet_mode != 2) ? 3 : 2;
-    return 6 + doublets + (with_params ? 1 : 0);
+    const int triplets = (h && h->triplet_pool) ? 2 : 1;
+    return 5 + doublets + triplets + (with_params ? 1 : 0);
 }
 
 }  // extern "C"
@@ -873,10 +881,19 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
         const uint32_t max_grid = uint32_t(h->num_sms) * (32 / WARPS_PER_CTA) * 3 / 2;
         if (grid > max_grid) grid = max_grid;
         KernelTimer t(h, s, "triplets");
+        a.heavy_only = h->triplet_pool ? 1u : 0u;
         if (dense)
             k_triplets<true><<<grid, WARPS_PER_CTA * 32, smem, s>>>(h->dev, a);
         else
             k_triplets<false><<<grid, WARPS_PER_CTA * 32, smem, s>>>(h->dev, a);
+        if (h->triplet_pool) {
+            // the light middles, POOL_G per warp
+            const size_t psmem = pool_smem_per_warp(K) * POOL_WARPS;
+            uint32_t pgrid = (n_sp / POOL_G + POOL_WARPS) / POOL_WARPS;
+            const uint32_t pmax = uint32_t(h->num_sms) * B200_POOL_MIN_CTAS;
+            if (pgrid > pmax) pgrid = pmax;
+            k_triplets_pool<<<pgrid, POOL_WARPS * 32, psmem, s>>>(h->dev, a);
+        }
     }
     {
         // exclusive scan of the per-middle seed counts fused into the gather (single pass,

@@ -57,6 +57,14 @@ constexpr int MAX_COMPAT = 8;       // upper bound on compatSeedLimit
 #define B200_TRIPLET_HEAVY_WORK 2048ull
 #endif
 constexpr unsigned long long TRIPLET_HEAVY_WORK = B200_TRIPLET_HEAVY_WORK;
+// Work split between k_triplets (heavy middles, a warp each) and k_triplets_pool (light middles,
+// several per warp; seed_pool.cuh): decided by the doublet kernels when they append a middle to
+// the work list (heavy from the front, light from the back).
+constexpr uint32_t POOL_NT = 64;    // a light middle has at most this many mid-tops
+constexpr uint32_t POOL_NB = 2047;  // ... and mid-bottoms
+__host__ __device__ inline bool pool_is_light(uint32_t nB, uint32_t nT) {
+    return nT <= POOL_NT && nB <= POOL_NB && (unsigned long long)nB * nT < TRIPLET_HEAVY_WORK;
+}
 
 // Small control block at the start of the workspace, zeroed at the start of each event.
 struct Control {
@@ -86,7 +94,7 @@ struct Control {
     uint32_t ticket_g;        // its work queue
     uint32_t n_fallback;      // middles handed back to the warp-per-middle kernel
     uint32_t ticket_f;        // work queue of that pass
-    uint32_t pad2_;
+    uint32_t ticket_p;        // work queue of k_triplets_pool (light middles)
 };
 
 // One doublet record in the arena: two float4.
@@ -970,7 +978,7 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
             // launch does not end on a few warps that drew a heavy middle last.
             if (nB == 0u)
                 a.seed_cnt[m] = 0u;
-            else if ((unsigned long long)nB * nT >= TRIPLET_HEAVY_WORK)
+            else if (!pool_is_light(nB, nT))
                 a.active_list[atomicAdd(&a.ctrl->n_heavy, 1u)] = m;
             else
                 a.active_list[a.n_sp - 1u - atomicAdd(&a.ctrl->n_light, 1u)] = m;
@@ -1025,6 +1033,7 @@ struct TripletArgs {
     uint32_t list_cap;      // triplets of one 32-row block kept in shared memory
     const uint32_t* active_list;  // work list written by k_doublets (heavy first)
     uint32_t n_sp;
+    uint32_t heavy_only;          // 1: the light middles are k_triplets_pool's
 };
 
 // One triplet of the current row block (shared memory, 16 bytes).
@@ -1164,7 +1173,7 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
 
     // Work items: the active middles k_doublets listed, heavy ones first (the launch then does
     // not end on a few warps that drew a heavy middle last), middles without work never drawn.
-    const uint32_t n_heavy = a.ctrl->n_heavy, n_work = n_heavy + a.ctrl->n_light;
+    const uint32_t n_heavy = a.ctrl->n_heavy, n_work = n_heavy + (a.heavy_only ? 0u : a.ctrl->n_light);
     while (true) {
         uint32_t m = 0;
         if (lane == 0) m = atomicAdd(&a.ctrl->ticket, 1u);

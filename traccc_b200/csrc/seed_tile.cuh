@@ -451,7 +451,7 @@ k_doublets_tile(const DevCfg cfg, const TileArgs a) {
         }
         {
             // work list of k_triplets: heavy middles from the front, light ones from the back
-            const bool heavy = aB != 0u && (unsigned long long)aB * aT >= TRIPLET_HEAVY_WORK;
+            const bool heavy = aB != 0u && !pool_is_light(aB, aT);
             const bool light = aB != 0u && !heavy;
             const uint32_t mh = __ballot_sync(FULL, heavy), ml = __ballot_sync(FULL, light);
             uint32_t bh = 0, bl = 0;
