@@ -223,6 +223,59 @@ def ref_run(xyz, var_z=None, var_r=None, finder=None, grid=None, filt=None) -> d
     return {k: v[:ns].copy() for k, v in out.items()}
 
 
+REF_TPE_LIB_PATH = os.path.join(_HERE, "_ref", "libtraccc_ref_tpe.so")
+_ref_tpe = None
+
+
+def ref_tpe_lib():
+    """oracle/_ref/libtraccc_ref_tpe.so: the reference's seed_to_bound_param_vector,
+    host::track_params_estimation and device::estimate_track_params compiled verbatim
+    (oracle/ref_tpe.cpp). None when it was never built and cannot be built here."""
+    global _ref_tpe
+    if _ref_tpe is None:
+        if not os.path.exists(REF_TPE_LIB_PATH):
+            if os.path.isdir("/root/reference/core/include/traccc"):
+                subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+            else:
+                return None
+        R = C.CDLL(REF_TPE_LIB_PATH)
+        R.ref_tpe_run.restype = C.c_int
+        R.ref_tpe_run.argtypes = [C.POINTER(TpeCfg), C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
+                                  C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_int, C.c_void_p]
+        _ref_tpe = R
+    return _ref_tpe
+
+
+def ref_estimate_params(bottom, middle, top, xyz, bfield, tpe=None, sp_meas_index=None,
+                        meas_local=None, meas_surface=None, device_variant=False):
+    """The reference's own parameter estimation (host algorithm, or its device function run on
+    the host) for the given seeds. Returns BOUND_PARAMS_DTYPE records, or None when oracle/_ref is
+    not available."""
+    R = ref_tpe_lib()
+    if R is None:
+        return None
+    tpe = tpe or default_configs()[3]
+    b = np.ascontiguousarray(bottom, np.uint32)
+    m = np.ascontiguousarray(middle, np.uint32)
+    t = np.ascontiguousarray(top, np.uint32)
+    xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+    n = xyz.shape[0]
+    bf = np.ascontiguousarray(bfield, np.float32)
+    smi = None if sp_meas_index is None else np.ascontiguousarray(sp_meas_index, np.uint32)
+    if meas_local is None:
+        ml = np.zeros((n, 2), np.float32)
+        ms = np.zeros(n, np.uint64)
+    else:
+        ml = np.ascontiguousarray(meas_local, np.float32).reshape(-1, 2)
+        ms = np.ascontiguousarray(meas_surface, np.uint64)
+    out = np.zeros(len(b), dtype=BOUND_PARAMS_DTYPE)
+    got = R.ref_tpe_run(C.byref(tpe), n, _ptr(xyz), _ptr(smi), ml.shape[0], _ptr(ml), _ptr(ms), len(b),
+                        _ptr(b), _ptr(m), _ptr(t), _ptr(bf), 1 if device_variant else 0, _ptr(out))
+    assert got == len(b)
+    return out
+
+
 REF_CUDA_LIB_PATH = os.path.join(_HERE, "_ref", "libtraccc_ref_cuda.so")
 _ref_cuda = None
 

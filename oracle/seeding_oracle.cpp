@@ -764,6 +764,60 @@ inline float perp2(float x, float y) {
     return std::sqrt(x * x + y * y);
 }
 
+// 4x4 determinant / inverse by cofactor expansion, m[col][row] — the "hard-coded" 4x4 forms of the
+// array plugin's transform3 (restated from the published implementation; the library is absent).
+inline float det44(const float (&m)[4][4]) {
+        return m[0][3] * m[1][2] * m[2][1] * m[3][0] - m[0][2] * m[1][3] * m[2][1] * m[3][0] -
+               m[0][3] * m[1][1] * m[2][2] * m[3][0] + m[0][1] * m[1][3] * m[2][2] * m[3][0] +
+               m[0][2] * m[1][1] * m[2][3] * m[3][0] - m[0][1] * m[1][2] * m[2][3] * m[3][0] -
+               m[0][3] * m[1][2] * m[2][0] * m[3][1] + m[0][2] * m[1][3] * m[2][0] * m[3][1] +
+               m[0][3] * m[1][0] * m[2][2] * m[3][1] - m[0][0] * m[1][3] * m[2][2] * m[3][1] -
+               m[0][2] * m[1][0] * m[2][3] * m[3][1] + m[0][0] * m[1][2] * m[2][3] * m[3][1] +
+               m[0][3] * m[1][1] * m[2][0] * m[3][2] - m[0][1] * m[1][3] * m[2][0] * m[3][2] -
+               m[0][3] * m[1][0] * m[2][1] * m[3][2] + m[0][0] * m[1][3] * m[2][1] * m[3][2] +
+               m[0][1] * m[1][0] * m[2][3] * m[3][2] - m[0][0] * m[1][1] * m[2][3] * m[3][2] -
+               m[0][2] * m[1][1] * m[2][0] * m[3][3] + m[0][1] * m[1][2] * m[2][0] * m[3][3] +
+               m[0][2] * m[1][0] * m[2][1] * m[3][3] - m[0][0] * m[1][2] * m[2][1] * m[3][3] -
+               m[0][1] * m[1][0] * m[2][2] * m[3][3] + m[0][0] * m[1][1] * m[2][2] * m[3][3];
+}
+inline void inverse44(const float (&m)[4][4], float (&i)[4][4]) {
+        i[0][0] = m[1][2] * m[2][3] * m[3][1] - m[1][3] * m[2][2] * m[3][1] + m[1][3] * m[2][1] * m[3][2] -
+                  m[1][1] * m[2][3] * m[3][2] - m[1][2] * m[2][1] * m[3][3] + m[1][1] * m[2][2] * m[3][3];
+        i[0][1] = m[0][3] * m[2][2] * m[3][1] - m[0][2] * m[2][3] * m[3][1] - m[0][3] * m[2][1] * m[3][2] +
+                  m[0][1] * m[2][3] * m[3][2] + m[0][2] * m[2][1] * m[3][3] - m[0][1] * m[2][2] * m[3][3];
+        i[0][2] = m[0][2] * m[1][3] * m[3][1] - m[0][3] * m[1][2] * m[3][1] + m[0][3] * m[1][1] * m[3][2] -
+                  m[0][1] * m[1][3] * m[3][2] - m[0][2] * m[1][1] * m[3][3] + m[0][1] * m[1][2] * m[3][3];
+        i[0][3] = m[0][3] * m[1][2] * m[2][1] - m[0][2] * m[1][3] * m[2][1] - m[0][3] * m[1][1] * m[2][2] +
+                  m[0][1] * m[1][3] * m[2][2] + m[0][2] * m[1][1] * m[2][3] - m[0][1] * m[1][2] * m[2][3];
+        i[1][0] = m[1][3] * m[2][2] * m[3][0] - m[1][2] * m[2][3] * m[3][0] - m[1][3] * m[2][0] * m[3][2] +
+                  m[1][0] * m[2][3] * m[3][2] + m[1][2] * m[2][0] * m[3][3] - m[1][0] * m[2][2] * m[3][3];
+        i[1][1] = m[0][2] * m[2][3] * m[3][0] - m[0][3] * m[2][2] * m[3][0] + m[0][3] * m[2][0] * m[3][2] -
+                  m[0][0] * m[2][3] * m[3][2] - m[0][2] * m[2][0] * m[3][3] + m[0][0] * m[2][2] * m[3][3];
+        i[1][2] = m[0][3] * m[1][2] * m[3][0] - m[0][2] * m[1][3] * m[3][0] - m[0][3] * m[1][0] * m[3][2] +
+                  m[0][0] * m[1][3] * m[3][2] + m[0][2] * m[1][0] * m[3][3] - m[0][0] * m[1][2] * m[3][3];
+        i[1][3] = m[0][2] * m[1][3] * m[2][0] - m[0][3] * m[1][2] * m[2][0] + m[0][3] * m[1][0] * m[2][2] -
+                  m[0][0] * m[1][3] * m[2][2] - m[0][2] * m[1][0] * m[2][3] + m[0][0] * m[1][2] * m[2][3];
+        i[2][0] = m[1][1] * m[2][3] * m[3][0] - m[1][3] * m[2][1] * m[3][0] + m[1][3] * m[2][0] * m[3][1] -
+                  m[1][0] * m[2][3] * m[3][1] - m[1][1] * m[2][0] * m[3][3] + m[1][0] * m[2][1] * m[3][3];
+        i[2][1] = m[0][3] * m[2][1] * m[3][0] - m[0][1] * m[2][3] * m[3][0] - m[0][3] * m[2][0] * m[3][1] +
+                  m[0][0] * m[2][3] * m[3][1] + m[0][1] * m[2][0] * m[3][3] - m[0][0] * m[2][1] * m[3][3];
+        i[2][2] = m[0][1] * m[1][3] * m[3][0] - m[0][3] * m[1][1] * m[3][0] + m[0][3] * m[1][0] * m[3][1] -
+                  m[0][0] * m[1][3] * m[3][1] - m[0][1] * m[1][0] * m[3][3] + m[0][0] * m[1][1] * m[3][3];
+        i[2][3] = m[0][3] * m[1][1] * m[2][0] - m[0][1] * m[1][3] * m[2][0] - m[0][3] * m[1][0] * m[2][1] +
+                  m[0][0] * m[1][3] * m[2][1] + m[0][1] * m[1][0] * m[2][3] - m[0][0] * m[1][1] * m[2][3];
+        i[3][0] = m[1][2] * m[2][1] * m[3][0] - m[1][1] * m[2][2] * m[3][0] - m[1][2] * m[2][0] * m[3][1] +
+                  m[1][0] * m[2][2] * m[3][1] + m[1][1] * m[2][0] * m[3][2] - m[1][0] * m[2][1] * m[3][2];
+        i[3][1] = m[0][1] * m[2][2] * m[3][0] - m[0][2] * m[2][1] * m[3][0] + m[0][2] * m[2][0] * m[3][1] -
+                  m[0][0] * m[2][2] * m[3][1] - m[0][1] * m[2][0] * m[3][2] + m[0][0] * m[2][1] * m[3][2];
+        i[3][2] = m[0][2] * m[1][1] * m[3][0] - m[0][1] * m[1][2] * m[3][0] - m[0][2] * m[1][0] * m[3][1] +
+                  m[0][0] * m[1][2] * m[3][1] + m[0][1] * m[1][0] * m[3][2] - m[0][0] * m[1][1] * m[3][2];
+        i[3][3] = m[0][1] * m[1][2] * m[2][0] - m[0][2] * m[1][1] * m[2][0] + m[0][2] * m[1][0] * m[2][1] -
+                  m[0][0] * m[1][2] * m[2][1] - m[0][1] * m[1][0] * m[2][2] + m[0][0] * m[1][1] * m[2][2];
+    const float s = 1.f / det44(m);
+    for (int c = 0; c < 4; ++c)
+        for (int r = 0; r < 4; ++r) i[c][r] *= s;
+}
+
 // seed_to_bound_param_vector — core/include/traccc/seeding/track_params_estimation_helper.hpp:47-129
 // + covariance of host::track_params_estimation::operator() —
 // core/src/seeding/track_params_estimation.cpp:64-86 (== device/.../impl/estimate_track_params.ipp:60-87).
@@ -777,10 +831,28 @@ void estimate_params(const b200seed_tpe_cfg& cfg, const Sp& spB, const Sp& spM, 
     V3 newZAxis = normalize(bfield);
     V3 newYAxis = normalize(cross(newZAxis, relVec));
     V3 newXAxis = cross(newYAxis, newZAxis);
-    // transform3(translation, x, y, z)::point_to_local == R^T (p - t)
+    // transform3 trans(translation, x, y, z): columns x, y, z, t of a 4x4 matrix and its inverse by
+    // cofactor expansion; point_to_local(p) = rotate(inverse, p) + translation column of the inverse
+    // (:81-85). Rounds differently from R^T (p - t): q/p of a stiff track is ill-conditioned in the
+    // local coordinates (B = v2 - A u2 cancels ~300-fold), the two forms differ by up to 4e-4 there.
+    float tm[4][4], ti[4][4];
+    for (int r = 0; r < 3; ++r) {
+        tm[0][r] = newXAxis.v[r];
+        tm[1][r] = newYAxis.v[r];
+        tm[2][r] = newZAxis.v[r];
+        tm[3][r] = p0.v[r];
+    }
+    tm[0][3] = tm[1][3] = tm[2][3] = 0.f;
+    tm[3][3] = 1.f;
+    inverse44(tm, ti);
+    auto rotate = [](const float (&m)[4][4], const V3& v) {
+        return V3{{m[0][0] * v.v[0] + m[1][0] * v.v[1] + m[2][0] * v.v[2],
+                   m[0][1] * v.v[0] + m[1][1] * v.v[1] + m[2][1] * v.v[2],
+                   m[0][2] * v.v[0] + m[1][2] * v.v[1] + m[2][2] * v.v[2]}};
+    };
     auto to_local = [&](const V3& p) {
-        const V3 d = sub(p, p0);
-        return V3{{dot(newXAxis, d), dot(newYAxis, d), dot(newZAxis, d)}};
+        const V3 rg = rotate(ti, p);
+        return V3{{rg.v[0] + ti[3][0], rg.v[1] + ti[3][1], rg.v[2] + ti[3][2]}};
     };
     const V3 local1 = to_local(p1);
     const V3 local2 = to_local(p2);
@@ -800,10 +872,8 @@ void estimate_params(const b200seed_tpe_cfg& cfg, const Sp& spB, const Sp& spM, 
         local2.v[2] / (2.f * R * std::asin(perp2(local2.v[0], local2.v[1]) / (2.f * R)));
     V3 transDirection{{1.f, A, perp2(1.f, A) * invTanTheta}};
     const V3 nd = normalize(transDirection);
-    // transform3::rotate == R * v
-    V3 direction{{newXAxis.v[0] * nd.v[0] + newYAxis.v[0] * nd.v[1] + newZAxis.v[0] * nd.v[2],
-                  newXAxis.v[1] * nd.v[0] + newYAxis.v[1] * nd.v[1] + newZAxis.v[1] * nd.v[2],
-                  newXAxis.v[2] * nd.v[0] + newYAxis.v[2] * nd.v[1] + newZAxis.v[2] * nd.v[2]}};
+    // transform3::rotate(trans._data, v)
+    const V3 direction = rotate(tm, nd);
     const float phi = std::atan2(direction.v[1], direction.v[0]);
     const float theta = std::atan2(perp2(direction.v[0], direction.v[1]), direction.v[2]);
     float qOverPt = 1.f / (R * norm(bfield));

@@ -1,7 +1,13 @@
 #!/usr/bin/env python
-"""Regenerates tests/golden/*.npz: small seeded events with the oracle's outputs (grid,
-doublet counts, triplets, seeds, parameters). The inputs are stored too, so the fixtures
-do not depend on the event generator staying bit-stable.
+"""Regenerates tests/golden/*.npz: small seeded events with
+  * the outputs of the REFERENCE'S OWN CODE run here (oracle/_ref: host::seeding_algorithm and
+    host::track_params_estimation compiled verbatim from /root/reference): ref_sd_* and ref_params —
+    these are what the oracle and the CUDA path are held to;
+  * the oracle's intermediate dumps (grid, doublet lists, triplets), which the reference's code
+    does not expose.
+The generator refuses to write a fixture when the oracle's seeds / parameters differ from the
+reference code's. The inputs are stored too, so the fixtures do not depend on the event generator
+staying bit-stable. Needs /root/reference (or a built oracle/_ref).
 
     python tests/golden/make_golden.py
 """
@@ -27,8 +33,19 @@ def main():
         ev = toy_detector.generate_event(kw.pop("n_particles"), kw.pop("seed"), **kw)
         r = oracle.run(ev.xyz, ev.var_z, ev.var_r, dump=True, sp_meas_index=ev.meas_index,
                        meas_local=ev.meas_local, meas_surface=ev.meas_surface, bfield=ev.bfield)
+        rs = oracle.ref_run(ev.xyz, ev.var_z, ev.var_r)
+        assert rs is not None, "oracle/_ref is missing and /root/reference is absent"
+        rp = oracle.ref_estimate_params(rs["bottom"], rs["middle"], rs["top"], ev.xyz, ev.bfield,
+                                        sp_meas_index=ev.meas_index, meas_local=ev.meas_local,
+                                        meas_surface=ev.meas_surface)
+        for k in ("bottom", "middle", "top", "quality"):
+            assert np.array_equal(rs[k].view(np.uint32), r.seeds[k].view(np.uint32)), (name, k)
+        assert np.array_equal(rp["vec"].view(np.uint32), r.params["vec"].view(np.uint32)), name
+        assert np.array_equal(rp["cov"].view(np.uint32), r.params["cov"].view(np.uint32)), name
         np.savez_compressed(
             os.path.join(HERE, name + ".npz"),
+            ref_sd_b=rs["bottom"], ref_sd_m=rs["middle"], ref_sd_t=rs["top"], ref_sd_q=rs["quality"],
+            ref_params=rp,
             xyz=ev.xyz, var_z=ev.var_z, var_r=ev.var_r, meas_index=ev.meas_index,
             meas_local=ev.meas_local, meas_surface=ev.meas_surface, bfield=ev.bfield,
             bin_offsets=r.bin_offsets, bin_entries=r.bin_entries,

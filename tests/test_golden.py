@@ -1,6 +1,8 @@
-"""Committed golden vectors (tests/golden/*.npz, made by tests/golden/make_golden.py from the
-oracle after it was pinned on the reference's known answers): the oracle must keep
-reproducing them on CPU, and the CUDA path must reproduce them on the GPU."""
+"""Committed golden vectors (tests/golden/*.npz, made by tests/golden/make_golden.py): seeds and
+track parameters are outputs of the REFERENCE'S OWN CODE run in the build container (ref_sd_*,
+ref_params: host::seeding_algorithm / host::track_params_estimation compiled verbatim), the
+intermediate dumps are the oracle's. The oracle must keep reproducing them on CPU, and the CUDA
+path must reproduce them on the GPU (where /root/reference does not exist)."""
 import glob
 import os
 
@@ -33,6 +35,11 @@ def test_oracle_reproduces_golden(path):
     assert np.array_equal(r.seeds["quality"].view(np.uint32), g["sd_q"].view(np.uint32))
     assert rel_close(r.params["vec"], g["params"]["vec"], 1e-6).all()
     assert [r.counters[k] for k in oracle.COUNTER_NAMES] == g["counters"].tolist()
+    # the reference code's own outputs, bit for bit
+    for k, gk in (("bottom", "ref_sd_b"), ("middle", "ref_sd_m"), ("top", "ref_sd_t"), ("quality", "ref_sd_q")):
+        assert np.array_equal(r.seeds[k].view(np.uint32), g[gk].view(np.uint32)), k
+    assert np.array_equal(r.params["vec"].view(np.uint32), g["ref_params"]["vec"].view(np.uint32))
+    assert np.array_equal(r.params["cov"].view(np.uint32), g["ref_params"]["cov"].view(np.uint32))
 
 
 @pytest.mark.gpu
@@ -47,11 +54,14 @@ def test_cuda_reproduces_golden(path):
                  np.ascontiguousarray(g["meas_local"]), np.ascontiguousarray(g["meas_surface"]),
                  g["bfield"])
     assert res["counters"]["overflow"] == 0
-    for k, gk in (("bottom", "sd_b"), ("middle", "sd_m"), ("top", "sd_t")):
+    # against the reference code's own outputs: seeds bit for bit, parameters within 1e-5
+    for k, gk in (("bottom", "ref_sd_b"), ("middle", "ref_sd_m"), ("top", "ref_sd_t")):
         assert np.array_equal(res[k], g[gk])
-    assert np.array_equal(res["quality"].view(np.uint32), g["sd_q"].view(np.uint32))
-    assert np.array_equal(res["params"]["surface_link"], g["params"]["surface_link"])
-    assert rel_close(res["params"]["vec"], g["params"]["vec"], 1e-5).all()
+    assert np.array_equal(res["quality"].view(np.uint32), g["ref_sd_q"].view(np.uint32))
+    assert np.array_equal(res["params"]["surface_link"], g["ref_params"]["surface_link"])
+    assert rel_close(res["params"]["vec"], g["ref_params"]["vec"], 1e-5).all()
+    diag = np.arange(6) * 7
+    assert rel_close(res["params"]["cov"][:, diag], g["ref_params"]["cov"][:, diag], 1e-5).all()
     names = oracle.COUNTER_NAMES
     c = dict(zip(names, g["counters"].tolist()))
     for k in ("n_valid", "n_active_middles", "n_mid_bot", "n_mid_top", "pair_tests", "triplet_tests",

@@ -95,11 +95,12 @@ def _check_event(ev, finder=None, filt=None, grid=None, dump=True, stage_cap=0):
         print(f"seed {i}: gpu=({s['bottom'][i]},{s['middle'][i]},{s['top'][i]},{s['quality'][i]}) "
               f"cpu=({r['bottom'][i]},{r['middle'][i]},{r['top'][i]},{r['quality'][i]})")
     assert len(bad) == 0, f"{len(bad)} of {n_ref} seeds differ"
-    # (4b) and against the reference's own host code (oracle/_ref, when it was built)
+    # (4b) and against the reference's own host code compiled verbatim (oracle/_ref travels to
+    #      the GPU box; its absence is a failure, not a skip)
     ref_code = oracle.ref_run(ev.xyz, ev.var_z, ev.var_r, finder=of, grid=og, filt=ofl)
-    if ref_code is not None:
-        for k in ("bottom", "middle", "top", "quality"):
-            assert np.array_equal(s[k].view(np.uint32), ref_code[k].view(np.uint32)), k
+    assert ref_code is not None, "oracle/_ref/libtraccc_ref_seeding.so is missing: run `make -C oracle ref`"
+    for k in ("bottom", "middle", "top", "quality"):
+        assert np.array_equal(s[k].view(np.uint32), ref_code[k].view(np.uint32)), k
     # (5) track parameters within 1e-5 relative; surface link and local position exact
     if n_ref:
         p, q = got["params"], ref.params
@@ -111,6 +112,17 @@ def _check_event(ev, finder=None, filt=None, grid=None, dump=True, stage_cap=0):
         off = np.ones(36, bool)
         off[diag] = False
         assert not p["cov"][:, off].any()
+        # (5b) and within 1e-5 of the reference's own parameter-estimation code (host algorithm
+        #      and device function, oracle/ref_tpe.cpp)
+        for dv in (False, True):
+            rp = oracle.ref_estimate_params(r["bottom"], r["middle"], r["top"], ev.xyz, ev.bfield,
+                                            sp_meas_index=ev.meas_index, meas_local=ev.meas_local,
+                                            meas_surface=ev.meas_surface, device_variant=dv)
+            assert rp is not None, "oracle/_ref/libtraccc_ref_tpe.so is missing: run `make -C oracle ref`"
+            assert np.array_equal(p["surface_link"], rp["surface_link"])
+            assert np.array_equal(p["vec"][:, :2], rp["vec"][:, :2])
+            assert rel_close(p["vec"], rp["vec"]).all()
+            assert rel_close(p["cov"][:, diag], rp["cov"][:, diag]).all()
     return got, ref
 
 

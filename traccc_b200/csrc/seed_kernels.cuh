@@ -1852,6 +1852,60 @@ __device__ __forceinline__ V3 v3normalize(V3 a) {
 }
 __device__ __forceinline__ float perp2(float x, float y) { return sqrt_rn(x * x + y * y); }
 
+// 4x4 determinant / inverse by cofactor expansion, m[col][row] — the "hard-coded" 4x4 forms of the
+// array plugin's transform3 (restated from the published implementation; the library is absent).
+__device__ __forceinline__ float det44(const float (&m)[4][4]) {
+        return m[0][3] * m[1][2] * m[2][1] * m[3][0] - m[0][2] * m[1][3] * m[2][1] * m[3][0] -
+               m[0][3] * m[1][1] * m[2][2] * m[3][0] + m[0][1] * m[1][3] * m[2][2] * m[3][0] +
+               m[0][2] * m[1][1] * m[2][3] * m[3][0] - m[0][1] * m[1][2] * m[2][3] * m[3][0] -
+               m[0][3] * m[1][2] * m[2][0] * m[3][1] + m[0][2] * m[1][3] * m[2][0] * m[3][1] +
+               m[0][3] * m[1][0] * m[2][2] * m[3][1] - m[0][0] * m[1][3] * m[2][2] * m[3][1] -
+               m[0][2] * m[1][0] * m[2][3] * m[3][1] + m[0][0] * m[1][2] * m[2][3] * m[3][1] +
+               m[0][3] * m[1][1] * m[2][0] * m[3][2] - m[0][1] * m[1][3] * m[2][0] * m[3][2] -
+               m[0][3] * m[1][0] * m[2][1] * m[3][2] + m[0][0] * m[1][3] * m[2][1] * m[3][2] +
+               m[0][1] * m[1][0] * m[2][3] * m[3][2] - m[0][0] * m[1][1] * m[2][3] * m[3][2] -
+               m[0][2] * m[1][1] * m[2][0] * m[3][3] + m[0][1] * m[1][2] * m[2][0] * m[3][3] +
+               m[0][2] * m[1][0] * m[2][1] * m[3][3] - m[0][0] * m[1][2] * m[2][1] * m[3][3] -
+               m[0][1] * m[1][0] * m[2][2] * m[3][3] + m[0][0] * m[1][1] * m[2][2] * m[3][3];
+}
+__device__ __forceinline__ void inverse44(const float (&m)[4][4], float (&i)[4][4]) {
+        i[0][0] = m[1][2] * m[2][3] * m[3][1] - m[1][3] * m[2][2] * m[3][1] + m[1][3] * m[2][1] * m[3][2] -
+                  m[1][1] * m[2][3] * m[3][2] - m[1][2] * m[2][1] * m[3][3] + m[1][1] * m[2][2] * m[3][3];
+        i[0][1] = m[0][3] * m[2][2] * m[3][1] - m[0][2] * m[2][3] * m[3][1] - m[0][3] * m[2][1] * m[3][2] +
+                  m[0][1] * m[2][3] * m[3][2] + m[0][2] * m[2][1] * m[3][3] - m[0][1] * m[2][2] * m[3][3];
+        i[0][2] = m[0][2] * m[1][3] * m[3][1] - m[0][3] * m[1][2] * m[3][1] + m[0][3] * m[1][1] * m[3][2] -
+                  m[0][1] * m[1][3] * m[3][2] - m[0][2] * m[1][1] * m[3][3] + m[0][1] * m[1][2] * m[3][3];
+        i[0][3] = m[0][3] * m[1][2] * m[2][1] - m[0][2] * m[1][3] * m[2][1] - m[0][3] * m[1][1] * m[2][2] +
+                  m[0][1] * m[1][3] * m[2][2] + m[0][2] * m[1][1] * m[2][3] - m[0][1] * m[1][2] * m[2][3];
+        i[1][0] = m[1][3] * m[2][2] * m[3][0] - m[1][2] * m[2][3] * m[3][0] - m[1][3] * m[2][0] * m[3][2] +
+                  m[1][0] * m[2][3] * m[3][2] + m[1][2] * m[2][0] * m[3][3] - m[1][0] * m[2][2] * m[3][3];
+        i[1][1] = m[0][2] * m[2][3] * m[3][0] - m[0][3] * m[2][2] * m[3][0] + m[0][3] * m[2][0] * m[3][2] -
+                  m[0][0] * m[2][3] * m[3][2] - m[0][2] * m[2][0] * m[3][3] + m[0][0] * m[2][2] * m[3][3];
+        i[1][2] = m[0][3] * m[1][2] * m[3][0] - m[0][2] * m[1][3] * m[3][0] - m[0][3] * m[1][0] * m[3][2] +
+                  m[0][0] * m[1][3] * m[3][2] + m[0][2] * m[1][0] * m[3][3] - m[0][0] * m[1][2] * m[3][3];
+        i[1][3] = m[0][2] * m[1][3] * m[2][0] - m[0][3] * m[1][2] * m[2][0] + m[0][3] * m[1][0] * m[2][2] -
+                  m[0][0] * m[1][3] * m[2][2] - m[0][2] * m[1][0] * m[2][3] + m[0][0] * m[1][2] * m[2][3];
+        i[2][0] = m[1][1] * m[2][3] * m[3][0] - m[1][3] * m[2][1] * m[3][0] + m[1][3] * m[2][0] * m[3][1] -
+                  m[1][0] * m[2][3] * m[3][1] - m[1][1] * m[2][0] * m[3][3] + m[1][0] * m[2][1] * m[3][3];
+        i[2][1] = m[0][3] * m[2][1] * m[3][0] - m[0][1] * m[2][3] * m[3][0] - m[0][3] * m[2][0] * m[3][1] +
+                  m[0][0] * m[2][3] * m[3][1] + m[0][1] * m[2][0] * m[3][3] - m[0][0] * m[2][1] * m[3][3];
+        i[2][2] = m[0][1] * m[1][3] * m[3][0] - m[0][3] * m[1][1] * m[3][0] + m[0][3] * m[1][0] * m[3][1] -
+                  m[0][0] * m[1][3] * m[3][1] - m[0][1] * m[1][0] * m[3][3] + m[0][0] * m[1][1] * m[3][3];
+        i[2][3] = m[0][3] * m[1][1] * m[2][0] - m[0][1] * m[1][3] * m[2][0] - m[0][3] * m[1][0] * m[2][1] +
+                  m[0][0] * m[1][3] * m[2][1] + m[0][1] * m[1][0] * m[2][3] - m[0][0] * m[1][1] * m[2][3];
+        i[3][0] = m[1][2] * m[2][1] * m[3][0] - m[1][1] * m[2][2] * m[3][0] - m[1][2] * m[2][0] * m[3][1] +
+                  m[1][0] * m[2][2] * m[3][1] + m[1][1] * m[2][0] * m[3][2] - m[1][0] * m[2][1] * m[3][2];
+        i[3][1] = m[0][1] * m[2][2] * m[3][0] - m[0][2] * m[2][1] * m[3][0] + m[0][2] * m[2][0] * m[3][1] -
+                  m[0][0] * m[2][2] * m[3][1] - m[0][1] * m[2][0] * m[3][2] + m[0][0] * m[2][1] * m[3][2];
+        i[3][2] = m[0][2] * m[1][1] * m[3][0] - m[0][1] * m[1][2] * m[3][0] - m[0][2] * m[1][0] * m[3][1] +
+                  m[0][0] * m[1][2] * m[3][1] + m[0][1] * m[1][0] * m[3][2] - m[0][0] * m[1][1] * m[3][2];
+        i[3][3] = m[0][1] * m[1][2] * m[2][0] - m[0][2] * m[1][1] * m[2][0] + m[0][2] * m[1][0] * m[2][1] -
+                  m[0][0] * m[1][2] * m[2][1] - m[0][1] * m[1][0] * m[2][2] + m[0][0] * m[1][1] * m[2][2];
+    const float s = 1.f / det44(m);
+    for (int c = 0; c < 4; ++c)
+        for (int r = 0; r < 4; ++r) i[c][r] *= s;
+}
+
 // Inhomogeneous field on a regular grid: the reference's cuda::inhom_global_bfield_backend_t =
 // covfie affine< linear< clamp< strided< device array of float3 >>>>
 // (device/cuda/src/utils/magnetic_field_types.hpp:27-32), sampled at the bottom spacepoint
@@ -1929,9 +1983,22 @@ k_estimate_params(const b200seed_tpe_cfg cfg, const uint32_t* __restrict__ n_see
     const V3 newZ = v3normalize(bfield);
     const V3 newY = v3normalize(v3cross(newZ, relVec));
     const V3 newX = v3cross(newY, newZ);
-    const V3 d1 = v3sub(p1, p0), d2 = v3sub(p2, p0);
-    const V3 local1{v3dot(newX, d1), v3dot(newY, d1), v3dot(newZ, d1)};
-    const V3 local2{v3dot(newX, d2), v3dot(newY, d2), v3dot(newZ, d2)};
+    // transform3(translation = p0, x, y, z): 4x4 matrix and its cofactor-expansion inverse;
+    // point_to_local(p) = rotate(inverse, p) + translation column of the inverse
+    // (track_params_estimation_helper.hpp:78-85; the array plugin's transform3)
+    float tm[4][4], ti[4][4];
+    tm[0][0] = newX.x, tm[0][1] = newX.y, tm[0][2] = newX.z, tm[0][3] = 0.f;
+    tm[1][0] = newY.x, tm[1][1] = newY.y, tm[1][2] = newY.z, tm[1][3] = 0.f;
+    tm[2][0] = newZ.x, tm[2][1] = newZ.y, tm[2][2] = newZ.z, tm[2][3] = 0.f;
+    tm[3][0] = p0.x, tm[3][1] = p0.y, tm[3][2] = p0.z, tm[3][3] = 1.f;
+    inverse44(tm, ti);
+    auto to_local = [&](const V3& p) {
+        return V3{(ti[0][0] * p.x + ti[1][0] * p.y + ti[2][0] * p.z) + ti[3][0],
+                  (ti[0][1] * p.x + ti[1][1] * p.y + ti[2][1] * p.z) + ti[3][1],
+                  (ti[0][2] * p.x + ti[1][2] * p.y + ti[2][2] * p.z) + ti[3][2]};
+    };
+    const V3 local1 = to_local(p1);
+    const V3 local2 = to_local(p2);
     const float den1 = local1.x * local1.x + local1.y * local1.y;
     const float den2 = local2.x * local2.x + local2.y * local2.y;
     const float u1 = local1.x / den1, v1 = local1.y / den1;
