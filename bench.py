@@ -49,6 +49,10 @@ def parse_args():
     ap.add_argument("--pool-workers", type=int, default=8,
                     help="host worker threads of the end-to-end leg (2 events in flight each; "
                          "they sleep on blocking-sync events, so ranks x workers may exceed the cores)")
+    ap.add_argument("--e2e-records", default="diag", choices=["diag", "full"],
+                    help="parameter records of the end-to-end leg: 56-byte diagonal records "
+                         "(b200seed_event_io::params_diag; the covariance of this path is diagonal) or "
+                         "the full 176-byte records")
     ap.add_argument("--particles", type=int, default=N_PARTICLES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true",
@@ -391,14 +395,16 @@ def run_b200(args):
     #      inside the timed region; S native worker threads with two events in flight each ----
     PW = max(1, args.pool_workers)
     pool = seeding.EventPool(finder, grid, filt, device=local, n_workers=PW)
-    ios, outs = pool.make_batch(events)
+    DIAG = args.e2e_records == "diag"
+    rec_bytes = 56 if DIAG else 176
+    ios, outs = pool.make_batch(events, diag=DIAG)
     h2d = sum(e.xyz.nbytes + e.var_z.nbytes + e.var_r.nbytes + e.meas_index.nbytes + e.meas_local.nbytes
               + e.meas_surface.nbytes for e in events)
     d2h_box = [0]
 
     def step_e2e():
         pool.process(ios)
-        d2h_box[0] = sum(C.sizeof(_lib.Counters) + int(io.n_seeds) * (16 + 176) for io in ios)
+        d2h_box[0] = sum(C.sizeof(_lib.Counters) + int(io.n_seeds) * (16 + rec_bytes) for io in ios)
 
     def timed_wall(step_fn, k, w):
         for _ in range(w):
@@ -421,6 +427,14 @@ def run_b200(args):
     chk = seeding.EventPool.result(ios[0], outs[0])
     ref0 = d_out[0].to_host()
     assert chk["n_seeds"] == len(ref0["bottom"]) and np.array_equal(chk["top"], ref0["top"])
+    par0 = tpes[0].to_host(d_par[0], chk["n_seeds"])
+    got0 = seeding.expand_params(chk["params_diag"]) if DIAG else chk["params"]
+    assert np.array_equal(got0.view(np.uint8), par0.view(np.uint8)), "pool parameters != device path"
+    # the other record form, a few steps, for the record (not the headline)
+    ios2, outs2 = pool.make_batch(events, diag=not DIAG)
+    e2e_other_s = timed_wall(lambda: pool.process(ios2), max(2, args.steps // 4), 1)
+    e2e_other = world * E * max(2, args.steps // 4) / e2e_other_s
+    del ios2, outs2
 
     # ---- per-kernel device times (CUDA events on the launching stream) for the roofline ----
     algs[0].set_timing(True)
@@ -499,7 +513,9 @@ def run_b200(args):
                 "e2e": {"value": e2e_ev_per_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h_box[0],
                         "how": f"b200seed_pool_process from pinned host buffers: {PW} native worker threads, "
-                               f"2 algorithm instances/streams each"},
+                               f"2 algorithm instances/streams each; parameters as {rec_bytes}-byte "
+                               f"{'diagonal (b200seed_bound_params_diag)' if DIAG else 'full'} records",
+                        "other_record_form": {"bytes_per_record": 176 if DIAG else 56, "value": e2e_other}},
                 "roofline": roof, "clocks": clocks,
                 "event_counters_mean": c_mean}
 

@@ -127,6 +127,17 @@ typedef struct b200seed_bound_params {
     float cov[36];
 } b200seed_bound_params;
 
+/* Compact form of b200seed_bound_params. On this path the covariance is diagonal
+ * (core/src/seeding/track_params_estimation.cpp:64-86 and estimate_track_params.ipp:60-87 only set
+ * the (j, j) elements of a zero-initialised matrix), so 30 of the 36 floats of every record are
+ * structural zeros: 56 bytes instead of 176 to move over PCIe. b200seed_expand_params() restores
+ * the full records on the host. */
+typedef struct b200seed_bound_params_diag {
+    uint64_t surface_link;
+    float vec[6];
+    float cov_diag[6];
+} b200seed_bound_params_diag;
+
 /* Device-side counters of one event. Written by b200seed_run when d_counters != NULL;
  * they replace the reference's D->H size reads (triplet_seeding_algorithm.cpp:64-224)
  * for logging and for the parity tests. */
@@ -263,6 +274,17 @@ int b200seed_estimate_params_inhom(b200seed_handle* h, void* stream, const uint3
                                    const b200seed_field_grid* field,
                                    b200seed_bound_params* d_params);
 
+/* b200seed_estimate_params with the 56-byte diagonal output records (homogeneous field). */
+int b200seed_estimate_params_diag(b200seed_handle* h, void* stream, const uint32_t* d_n_seeds,
+                                  uint32_t seed_capacity, const uint32_t* d_bottom,
+                                  const uint32_t* d_middle, const uint32_t* d_top,
+                                  const float* d_xyz, const uint32_t* d_sp_meas_index_1,
+                                  const float* d_meas_local, const uint64_t* d_meas_surface,
+                                  const float bfield[3], b200seed_bound_params_diag* d_params);
+/* HOST helper: n diagonal records -> full 176-byte records (off-diagonal elements zero). */
+void b200seed_expand_params(const b200seed_bound_params_diag* in, uint32_t n,
+                            b200seed_bound_params* out);
+
 /* ------------------------------------------------------------------------ */
 /* The step before the path: spacepoint formation       */
 /* ------------------------------------------------------------------------ */
@@ -350,6 +372,9 @@ typedef struct b200seed_event_io {
     uint32_t n_seeds;
     int32_t status;
     b200seed_counters counters;
+    /* the parameters as 56-byte diagonal records (may be NULL). When set, the parameters cross
+     * PCIe in this form (a third of the bytes); `params` may be set as well (both are filled). */
+    b200seed_bound_params_diag* params_diag;
 } b200seed_event_io;
 
 typedef struct b200seed_pool b200seed_pool;

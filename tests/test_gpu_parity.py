@@ -480,3 +480,24 @@ def test_parity_pooled_triplet_kernel(monkeypatch):
     finder = seedfinder_config(maxSeedsPerSpM=12)
     _check_event(toy_detector.generate_event(1500, 41), finder=finder, grid=spacepoint_grid_config(finder))
     _check_event(toy_detector.generate_event(10000, 43), dump=False)
+
+
+def test_diagonal_parameter_records():
+    """b200seed_event_io::params_diag: the parameters leave the device as 56-byte diagonal
+    records (a third of the PCIe bytes); b200seed_expand_params restores the full records,
+    bit for bit what the 176-byte path delivers."""
+    from traccc_b200 import seeding, toy_detector
+    events = [toy_detector.generate_event(400 + 200 * i, 70 + i) for i in range(5)]
+    pool = seeding.EventPool(n_workers=2)
+    ios_f, outs_f = pool.make_batch(events)
+    ios_d, outs_d = pool.make_batch(events, diag=True)
+    pool.process(ios_f)
+    pool.process(ios_d)
+    for io_f, of, io_d, od in zip(ios_f, outs_f, ios_d, outs_d):
+        full = seeding.EventPool.result(io_f, of)
+        diag = seeding.EventPool.result(io_d, od)
+        assert full["n_seeds"] == diag["n_seeds"] > 0
+        for k in ("bottom", "middle", "top", "quality"):
+            assert np.array_equal(full[k], diag[k])
+        exp = seeding.expand_params(diag["params_diag"])
+        assert np.array_equal(exp.view(np.uint8), full["params"].view(np.uint8))

@@ -101,7 +101,8 @@ class EventIO(C.Structure):
                 ("meas_surface", C.c_void_p), ("bfield", C.c_float * 3),
                 ("seed_capacity", C.c_uint32), ("bottom", C.c_void_p), ("middle", C.c_void_p),
                 ("top", C.c_void_p), ("quality", C.c_void_p), ("params", C.c_void_p),
-                ("n_seeds", C.c_uint32), ("status", C.c_int32), ("counters", Counters)]
+                ("n_seeds", C.c_uint32), ("status", C.c_int32), ("counters", Counters),
+                ("params_diag", C.c_void_p)]
 
 
 class FieldGrid(C.Structure):
@@ -127,6 +128,7 @@ EXPORTS = (
     "b200seed_pool_last_error", "b200seed_pool_destroy",
     "b200seed_workspace_bytes", "b200seed_run", "b200seed_estimate_params", "b200seed_run_host",
     "b200seed_form_spacepoints", "b200seed_run_n_on_device", "b200seed_estimate_params_inhom",
+    "b200seed_estimate_params_diag", "b200seed_expand_params",
     "b200seed_workspace_layout", "b200seed_set_triplet_dump", "b200seed_set_timing",
     "b200seed_get_timings", "b200seed_launches_per_event", "b200seed_measure_fp32_peak",
     "b200seed_version")
@@ -172,6 +174,10 @@ def lib() -> C.CDLL:
     L.b200seed_form_spacepoints.argtypes = [vp, vp, u32, vp, vp, vp, vp, u32, vp, vp, vp, vp, vp, vp]
     L.b200seed_estimate_params.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp, vp, vp,
                                            C.POINTER(C.c_float * 3), vp]
+    L.b200seed_estimate_params_diag.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp, vp, vp,
+                                                C.POINTER(C.c_float * 3), vp]
+    L.b200seed_expand_params.argtypes = [vp, u32, vp]
+    L.b200seed_expand_params.restype = None
     L.b200seed_estimate_params_inhom.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp, vp, vp,
                                                  C.POINTER(FieldGrid), vp]
     L.b200seed_run_host.argtypes = [vp, vp, u32, vp, vp, vp, vp, u32, vp, vp,

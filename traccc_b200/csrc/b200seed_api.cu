@@ -986,11 +986,12 @@ int estimate_impl(b200seed_handle* h, void* stream, const uint32_t* d_n_seeds,
                   uint32_t seed_capacity, const uint32_t* d_bottom, const uint32_t* d_middle,
                   const uint32_t* d_top, const float* d_xyz, const uint32_t* d_sp_meas_index_1,
                   const float* d_meas_local, const uint64_t* d_meas_surface, const float bfield[3],
-                  const b200seed_field_grid& fg, b200seed_bound_params* d_params) {
+                  const b200seed_field_grid& fg, b200seed_bound_params* d_params,
+                  b200seed_bound_params_diag* d_params_diag = nullptr) {
     if (!h) return B200SEED_EINVAL;
     if (seed_capacity == 0) return B200SEED_OK;
     if (!d_xyz) return B200SEED_OK;  // no spacepoints => no seeds (…estimation_algorithm.cpp:49-51)
-    if (!d_n_seeds || !d_bottom || !d_middle || !d_top || !bfield || !d_params)
+    if (!d_n_seeds || !d_bottom || !d_middle || !d_top || !bfield || (!d_params && !d_params_diag))
         return fail(h, B200SEED_EINVAL, "b200seed_estimate_params: null pointer");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     CUDA_TRY(h, cudaSetDevice(h->device));
@@ -998,7 +999,7 @@ int estimate_impl(b200seed_handle* h, void* stream, const uint32_t* d_n_seeds,
         KernelTimer t(h, s, "estimate_params");
         k_estimate_params<<<(seed_capacity + 127) / 128, 128, 0, s>>>(
             h->tpe, d_n_seeds, seed_capacity, d_bottom, d_middle, d_top, d_xyz, d_sp_meas_index_1,
-            d_meas_local, d_meas_surface, bfield[0], bfield[1], bfield[2], fg, d_params);
+            d_meas_local, d_meas_surface, bfield[0], bfield[1], bfield[2], fg, d_params, d_params_diag);
     }
     CUDA_TRY(h, cudaGetLastError());
     return B200SEED_OK;
@@ -1016,6 +1017,29 @@ int b200seed_estimate_params(b200seed_handle* h, void* stream, const uint32_t* d
     b200seed_field_grid none{};
     return estimate_impl(h, stream, d_n_seeds, seed_capacity, d_bottom, d_middle, d_top, d_xyz,
                          d_sp_meas_index_1, d_meas_local, d_meas_surface, bfield, none, d_params);
+}
+
+int b200seed_estimate_params_diag(b200seed_handle* h, void* stream, const uint32_t* d_n_seeds,
+                                  uint32_t seed_capacity, const uint32_t* d_bottom,
+                                  const uint32_t* d_middle, const uint32_t* d_top,
+                                  const float* d_xyz, const uint32_t* d_sp_meas_index_1,
+                                  const float* d_meas_local, const uint64_t* d_meas_surface,
+                                  const float bfield[3], b200seed_bound_params_diag* d_params) {
+    b200seed_field_grid none{};
+    return estimate_impl(h, stream, d_n_seeds, seed_capacity, d_bottom, d_middle, d_top, d_xyz,
+                         d_sp_meas_index_1, d_meas_local, d_meas_surface, bfield, none, nullptr, d_params);
+}
+
+void b200seed_expand_params(const b200seed_bound_params_diag* in, uint32_t n, b200seed_bound_params* out) {
+    for (uint32_t i = 0; i < n; ++i) {
+        b200seed_bound_params& o = out[i];
+        std::memset(&o, 0, sizeof(o));
+        o.surface_link = in[i].surface_link;
+        for (int k = 0; k < 6; ++k) {
+            o.vec[k] = in[i].vec[k];
+            o.cov[k * 7] = in[i].cov_diag[k];
+        }
+    }
 }
 
 int b200seed_estimate_params_inhom(b200seed_handle* h, void* stream, const uint32_t* d_n_seeds,
@@ -1054,6 +1078,8 @@ struct HostEvent {
     uint32_t* h_top = nullptr;
     float* h_quality = nullptr;
     b200seed_bound_params* h_params = nullptr;
+    b200seed_bound_params_diag* h_params_diag = nullptr;  // when set, the parameters cross PCIe as
+                                                          // 56-byte diagonal records
     // device staging of the outputs (set by submit)
     uint32_t *d_b = nullptr, *d_m = nullptr, *d_t = nullptr;
     float* d_q = nullptr;
@@ -1078,7 +1104,8 @@ int host_submit(b200seed_handle* h, cudaStream_t s, HostEvent& e) {
     e.submitted = false;
     if (e.n_sp == 0) return B200SEED_OK;
     if (!e.h_xyz) return fail(h, B200SEED_EINVAL, "b200seed_run_host: h_xyz is null");
-    const bool want_params = e.h_params != nullptr;
+    const bool diag = e.h_params_diag != nullptr;
+    const bool want_params = e.h_params != nullptr || diag;
     const uint32_t n_sp = e.n_sp, n_meas = e.n_meas, seed_capacity = e.seed_capacity;
 
     // device staging: inputs | outputs | workspace
@@ -1093,7 +1120,9 @@ int host_submit(b200seed_handle* h, cudaStream_t s, HostEvent& e) {
                  o_ml = take(size_t(n_meas) * 8), o_ms = take(size_t(n_meas) * 8),
                  o_b = take(size_t(seed_capacity) * 4), o_m = take(size_t(seed_capacity) * 4),
                  o_t = take(size_t(seed_capacity) * 4), o_q = take(size_t(seed_capacity) * 4),
-                 o_p = take(want_params ? size_t(seed_capacity) * sizeof(b200seed_bound_params) : 0),
+                 o_p = take(want_params ? size_t(seed_capacity) * (diag ? sizeof(b200seed_bound_params_diag)
+                                                                         : sizeof(b200seed_bound_params))
+                                        : 0),
                  o_n = take(256), o_c = take(sizeof(b200seed_counters));
     const size_t ws_bytes = b200seed_workspace_bytes(h, n_sp);
     const size_t o_ws = take(ws_bytes);
@@ -1141,8 +1170,11 @@ int host_submit(b200seed_handle* h, cudaStream_t s, HostEvent& e) {
                           e.d_m, e.d_t, e.d_q, d_n, d_c);
     if (rc != B200SEED_OK) return rc;
     if (want_params) {
-        rc = b200seed_estimate_params(h, s, d_n, seed_capacity, e.d_b, e.d_m, e.d_t, d_xyz, d_smi,
-                                      d_ml, d_ms, e.bfield, e.d_p);
+        rc = diag ? b200seed_estimate_params_diag(h, s, d_n, seed_capacity, e.d_b, e.d_m, e.d_t, d_xyz, d_smi,
+                                                  d_ml, d_ms, e.bfield,
+                                                  reinterpret_cast<b200seed_bound_params_diag*>(e.d_p))
+                  : b200seed_estimate_params(h, s, d_n, seed_capacity, e.d_b, e.d_m, e.d_t, d_xyz, d_smi,
+                                             d_ml, d_ms, e.bfield, e.d_p);
         if (rc != B200SEED_OK) return rc;
     }
     // the counters struct carries n_seeds: one small read-back, then the sized copies
@@ -1169,11 +1201,16 @@ int host_finish(b200seed_handle* h, cudaStream_t s, HostEvent& e, uint32_t* h_n_
         if (e.h_middle) CUDA_TRY(h, cudaMemcpyAsync(e.h_middle, e.d_m, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
         if (e.h_top) CUDA_TRY(h, cudaMemcpyAsync(e.h_top, e.d_t, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
         if (e.h_quality) CUDA_TRY(h, cudaMemcpyAsync(e.h_quality, e.d_q, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
-        if (e.h_params)
+        if (e.h_params_diag)
+            CUDA_TRY(h, cudaMemcpyAsync(e.h_params_diag, e.d_p, size_t(n) * sizeof(b200seed_bound_params_diag),
+                                        cudaMemcpyDeviceToHost, s));
+        else if (e.h_params)
             CUDA_TRY(h, cudaMemcpyAsync(e.h_params, e.d_p, size_t(n) * sizeof(b200seed_bound_params),
                                         cudaMemcpyDeviceToHost, s));
         CUDA_TRY(h, host_wait_point(h, s));
         CUDA_TRY(h, cudaEventSynchronize(h->ev_host));
+        // both forms requested: the full records are expanded on the host
+        if (e.h_params_diag && e.h_params) b200seed_expand_params(e.h_params_diag, n, e.h_params);
     }
     if (const uint32_t ovf = h->h_pinned->overflow) {
         *h->h_sticky = 0u;  // reported here
@@ -1203,6 +1240,7 @@ HostEvent host_event_of(const b200seed_event_io& io) {
     e.bfield[0] = io.bfield[0], e.bfield[1] = io.bfield[1], e.bfield[2] = io.bfield[2];
     e.h_bottom = io.bottom, e.h_middle = io.middle, e.h_top = io.top, e.h_quality = io.quality;
     e.h_params = io.params;
+    e.h_params_diag = io.params_diag;
     return e;
 }
 

@@ -1955,7 +1955,8 @@ k_estimate_params(const b200seed_tpe_cfg cfg, const uint32_t* __restrict__ n_see
                   const float* __restrict__ xyz, const uint32_t* __restrict__ sp_meas,
                   const float* __restrict__ meas_local, const uint64_t* __restrict__ meas_surface,
                   const float bx, const float by, const float bz, const b200seed_field_grid fg,
-                  b200seed_bound_params* __restrict__ out) {
+                  b200seed_bound_params* __restrict__ out,
+                  b200seed_bound_params_diag* __restrict__ out_diag) {
     // Records are 176 B: written one per lane they would cost 32 sectors per store
     // instruction. Each warp builds its 32 records (5632 contiguous bytes) in shared memory
     // and streams them out as float4 rows.
@@ -2020,32 +2021,52 @@ k_estimate_params(const b200seed_tpe_cfg cfg, const uint32_t* __restrict__ n_see
     const uint32_t mi = sp_meas ? sp_meas[ib] : ib;
 
     // the record of this lane inside the warp's staging buffer (same layout as the output)
+    const float sigma_qopt = cfg.initial_sigma_qopt * sinf(theta);
+    const float sigma_pt_rel = cfg.initial_sigma_pt_rel * qop;
+    const float sigma_theta = qop / tanf(theta);
+    float var[6];
+    float var_theta = 0.f;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        float v = cfg.initial_sigma[j] * cfg.initial_sigma[j];
+        if (j == 4) {
+            v += sigma_qopt * sigma_qopt;
+            v += sigma_pt_rel * sigma_pt_rel;
+            v += var_theta * sigma_theta * sigma_theta;
+        }
+        v *= cfg.initial_inflation[j];
+        if (j == 3) var_theta = v;
+        var[j] = v;
+    }
+    const uint64_t link = meas_surface ? meas_surface[mi] : 0ull;
+    const float loc0 = meas_local ? meas_local[2 * size_t(mi)] : 0.f;
+    const float loc1 = meas_local ? meas_local[2 * size_t(mi) + 1] : 0.f;
+    const uint32_t nrec = (n - i0 < 32u) ? (n - i0) : 32u;
+    if (out_diag) {
+        // 56-byte diagonal records: 14 floats per lane, streamed out as float2 rows
+        b200seed_bound_params_diag* o = reinterpret_cast<b200seed_bound_params_diag*>(rec + lane * 14);
+        o->surface_link = link;
+        o->vec[0] = loc0, o->vec[1] = loc1, o->vec[2] = phi, o->vec[3] = theta, o->vec[4] = qop;
+        o->vec[5] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) o->cov_diag[j] = var[j];
+        __syncwarp();
+        const float2* s2 = reinterpret_cast<const float2*>(rec);
+        float2* d2 = reinterpret_cast<float2*>(out_diag + i0);
+        for (uint32_t k = lane; k < nrec * 7u; k += 32) d2[k] = s2[k];
+        return;
+    }
     b200seed_bound_params* o = reinterpret_cast<b200seed_bound_params*>(rec + lane * 44);
-    o->surface_link = meas_surface ? meas_surface[mi] : 0ull;
-    o->vec[0] = meas_local ? meas_local[2 * size_t(mi)] : 0.f;
-    o->vec[1] = meas_local ? meas_local[2 * size_t(mi) + 1] : 0.f;
+    o->surface_link = link;
+    o->vec[0] = loc0;
+    o->vec[1] = loc1;
     o->vec[2] = phi;
     o->vec[3] = theta;
     o->vec[4] = qop;
     o->vec[5] = 0.f;
-    float var_theta = 0.f;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
-        float var = cfg.initial_sigma[j] * cfg.initial_sigma[j];
-        if (j == 4) {
-            const float sigma_qopt = cfg.initial_sigma_qopt * sinf(theta);
-            var += sigma_qopt * sigma_qopt;
-            const float sigma_pt_rel = cfg.initial_sigma_pt_rel * qop;
-            var += sigma_pt_rel * sigma_pt_rel;
-            const float sigma_theta = qop / tanf(theta);
-            var += var_theta * sigma_theta * sigma_theta;
-        }
-        var *= cfg.initial_inflation[j];
-        if (j == 3) var_theta = var;
-        o->cov[j * 6 + j] = var;
-    }
+    for (int j = 0; j < 6; ++j) o->cov[j * 6 + j] = var[j];
     __syncwarp();
-    const uint32_t nrec = (n - i0 < 32u) ? (n - i0) : 32u;
     float* dst = reinterpret_cast<float*>(out + i0);
     if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
         const float4* s4 = reinterpret_cast<const float4*>(rec);

@@ -23,6 +23,18 @@ from ._lib import (B200SeedError, Counters, EventIO, WsLayout, seedfilter_config
 
 BOUND_PARAMS_DTYPE = np.dtype([("surface_link", "<u8"), ("vec", "<f4", (6,)),
                                ("cov", "<f4", (36,))])
+# b200seed_bound_params_diag: the same record with the (diagonal) covariance as six floats
+BOUND_PARAMS_DIAG_DTYPE = np.dtype([("surface_link", "<u8"), ("vec", "<f4", (6,)),
+                                    ("cov_diag", "<f4", (6,))])
+
+
+def expand_params(diag: np.ndarray) -> np.ndarray:
+    """b200seed_expand_params: 56-byte diagonal records -> full 176-byte records (host)."""
+    diag = np.ascontiguousarray(diag)
+    out = np.zeros(len(diag), dtype=BOUND_PARAMS_DTYPE)
+    _lib.lib().b200seed_expand_params(diag.ctypes.data_as(C.c_void_p), len(diag),
+                                      out.ctypes.data_as(C.c_void_p))
+    return out
 
 
 @dataclass
@@ -544,7 +556,7 @@ class EventPool:
             self.lib.b200seed_pool_destroy(p)
             self.p = None
 
-    def make_batch(self, events, with_params: bool = True):
+    def make_batch(self, events, with_params: bool = True, diag: bool = False):
         """Pinned host buffers + the b200seed_event_io array for a list of ToyEvent-like
         objects. Returns (io_array, outputs) where outputs[i] holds the pinned result tensors
         (and, under "_inputs", the pinned inputs): the caller owns the batch, the pool keeps
@@ -563,7 +575,10 @@ class EventPool:
                    "top": torch.empty(cap, dtype=torch.int32, pin_memory=True),
                    "quality": torch.empty(cap, dtype=torch.float32, pin_memory=True),
                    "params": torch.empty(cap * BOUND_PARAMS_DTYPE.itemsize, dtype=torch.uint8,
-                                         pin_memory=True) if with_params else None}
+                                         pin_memory=True) if (with_params and not diag) else None,
+                   # diag: the parameters cross PCIe as 56-byte diagonal records
+                   "params_diag": torch.empty(cap * BOUND_PARAMS_DIAG_DTYPE.itemsize, dtype=torch.uint8,
+                                              pin_memory=True) if (with_params and diag) else None}
             io = ios[i]
             io.n_spacepoints, io.n_measurements = n, int(e.meas_local.shape[0])
             io.xyz, io.var_z, io.var_r = inp[0].data_ptr(), inp[1].data_ptr(), inp[2].data_ptr()
@@ -575,7 +590,8 @@ class EventPool:
             io.bottom, io.middle, io.top = (out["bottom"].data_ptr(), out["middle"].data_ptr(),
                                             out["top"].data_ptr())
             io.quality = out["quality"].data_ptr()
-            io.params = out["params"].data_ptr() if with_params else None
+            io.params = out["params"].data_ptr() if out["params"] is not None else None
+            io.params_diag = out["params_diag"].data_ptr() if out["params_diag"] is not None else None
             out["_inputs"] = inp   # the pinned input buffers live as long as the caller's batch
             outs.append(out)
         return ios, outs
@@ -597,4 +613,7 @@ class EventPool:
         if out["params"] is not None:
             res["params"] = out["params"][: ns * BOUND_PARAMS_DTYPE.itemsize].numpy().view(
                 BOUND_PARAMS_DTYPE)
+        if out.get("params_diag") is not None:
+            res["params_diag"] = out["params_diag"][: ns * BOUND_PARAMS_DIAG_DTYPE.itemsize].numpy().view(
+                BOUND_PARAMS_DIAG_DTYPE)
         return res
