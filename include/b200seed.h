@@ -158,6 +158,9 @@ typedef struct b200seed_counters {
                                     depends on how middles are grouped, not only on the event */
     uint32_t n_fallback_middles; /* middles the group kernel handed to the warp-per-middle kernel */
     uint32_t reserved_;
+    uint64_t triplet_visited;    /* (mid-bottom, mid-top) pairs inside the conservative cotTheta
+                                    windows == combinations the triplet kernel actually evaluated
+                                    (triplet_tests is what the reference evaluates) */
 } b200seed_counters;
 
 #define B200SEED_OVF_DOUBLETS 1u /* doublet arena too small: raise max_doublets */
@@ -199,7 +202,7 @@ int b200seed_get_axes(const b200seed_handle* h, uint32_t* n_phi, float* phi_min,
                       uint32_t* n_z, float* z_min, float* z_max);
 
 /* Doublet arena capacity (entries per direction). 0 selects the default policy
- * max(2^20, 4e-3 * max_spacepoints^2). */
+ * max(2^20, 5e-3 * max_spacepoints^2). */
 int b200seed_set_max_doublets(b200seed_handle* h, uint64_t max_doublets);
 
 /* Tuning knob: mid-bottom doublets of one middle staged in shared memory by the doublet

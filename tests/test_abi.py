@@ -32,7 +32,7 @@ def test_struct_layouts():
     assert C.sizeof(seedfilter_config) == 56
     assert seedfilter_config.compatSeedLimit.offset == 16
     assert C.sizeof(track_params_estimation_config) == 56
-    assert C.sizeof(_lib.Counters) == 64
+    assert C.sizeof(_lib.Counters) == 72
     assert seedfinder_config.maxSeedsPerSpM.offset == 64 and seedfinder_config.neighbor_scope.offset == 124
 
 

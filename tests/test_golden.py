@@ -111,7 +111,7 @@ def test_cuda_reproduces_next_row_goldens():
     seeds = seeding.seed_collection(i32(g["sd_b"]), i32(g["sd_m"]), i32(g["sd_t"]),
                                     torch.zeros(n, dtype=torch.float32, device=dev),
                                     torch.tensor([n], dtype=torch.int32, device=dev),
-                                    torch.zeros(64, dtype=torch.uint8, device=dev))
+                                    torch.zeros(128, dtype=torch.uint8, device=dev))
     sp = seeding.spacepoint_collection(torch.from_numpy(g["xyz"]).to(dev), None, None, i32(g["meas_index"]))
     ms = seeding.measurement_collection(torch.from_numpy(g["meas_local"]).to(dev),
                                         torch.from_numpy(g["meas_surface"].view(np.int64)).to(dev))

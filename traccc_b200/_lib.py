@@ -86,7 +86,7 @@ class Counters(C.Structure):
                 ("n_mid_top", C.c_uint32), ("n_triplets", C.c_uint32), ("n_seeds", C.c_uint32),
                 ("overflow", C.c_uint32), ("pair_tests", C.c_uint64), ("triplet_tests", C.c_uint64),
                 ("pair_visited", C.c_uint64), ("n_fallback_middles", C.c_uint32),
-                ("reserved_", C.c_uint32)]
+                ("reserved_", C.c_uint32), ("triplet_visited", C.c_uint64)]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -95,6 +95,7 @@ struct Control {
     uint32_t n_fallback;      // middles handed back to the warp-per-middle kernel
     uint32_t ticket_f;        // work queue of that pass
     uint32_t ticket_p;        // work queue of k_triplets_pool (light middles)
+    unsigned long long triplet_visited;  // (mid-bottom, mid-top) pairs inside the cotTheta windows
 };
 
 // One doublet record in the arena: two float4.
@@ -1145,7 +1146,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B200_TRIPLET_MIN_CTAS)
 k_triplets(const DevCfg cfg, const TripletArgs a) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ uint32_t s_ntrip;
-    __shared__ unsigned long long s_tests;
+    __shared__ unsigned long long s_tests, s_visited;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t ltmask = lanemask_lt();
     unsigned char* base = s_raw + triplet_smem_per_warp(a.list_cap, DENSE) * warp;
@@ -1163,13 +1164,13 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
     uint8_t* aux = reinterpret_cast<uint8_t*>(ord + a.list_cap);     // bonus count, later rank
     if (threadIdx.x == 0) {
         s_ntrip = 0;
-        s_tests = 0ull;
+        s_tests = s_visited = 0ull;
     }
     __syncthreads();
     const uint32_t n_valid = a.ctrl->n_valid;
     const uint32_t K = cfg.maxSeedsPerSpM;
     uint32_t acc_trip = 0;
-    unsigned long long acc_tests = 0ull;
+    unsigned long long acc_tests = 0ull, acc_visited = 0ull;
 
     // Work items: the active middles k_doublets listed, heavy ones first (the launch then does
     // not end on a few warps that drew a heavy middle last), middles without work never drawn.
@@ -1567,6 +1568,7 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
 
             // ---- evaluate the (row, mid-top) pairs inside the windows, 32 at a time ----
             const uint32_t base_n = nlist;
+            acc_visited += total;
 #ifndef B200_PREFILTER_MIN_PAIRS
 #define B200_PREFILTER_MIN_PAIRS 512u
 #endif
@@ -1720,11 +1722,13 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
     if (lane == 0) {
         atomicAdd(&s_ntrip, acc_trip);
         atomicAdd(&s_tests, acc_tests);
+        atomicAdd(&s_visited, acc_visited);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         if (s_ntrip) atomicAdd(&a.ctrl->n_triplets, s_ntrip);
         if (s_tests) atomicAdd(&a.ctrl->triplet_tests, s_tests);
+        if (s_visited) atomicAdd(&a.ctrl->triplet_visited, s_visited);
     }
 }
 
@@ -1814,6 +1818,7 @@ k_seed_gather(const uint32_t n_sp, const uint32_t K, const Control* __restrict__
                     c.pair_visited = ctrl->pair_visited;
                     c.n_fallback_middles = ctrl->n_fallback;
                     c.reserved_ = 0u;
+                    c.triplet_visited = ctrl->triplet_visited;
                     *counters = c;
                 }
             }

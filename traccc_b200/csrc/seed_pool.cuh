@@ -81,7 +81,7 @@ k_triplets_pool(const DevCfg cfg, const TripletArgs a) {
     const uint32_t n_valid = a.ctrl->n_valid;
     const bool has_var = a.ctrl->has_variance != 0u;
     uint32_t acc_trip = 0;
-    unsigned long long acc_tests = 0ull;
+    unsigned long long acc_tests = 0ull, acc_visited = 0ull;
     const uint32_t n_light = a.ctrl->n_light;
 
     // order of a spacepoint among the doublet partners of member j in the reference (canon_key
@@ -439,6 +439,7 @@ k_triplets_pool(const DevCfg cfg, const TripletArgs a) {
             const uint32_t incl = warp_incl_scan(wdt, lane);
             const uint32_t excl = incl - wdt;
             const uint32_t total = __shfl_sync(FULL, incl, 31);
+            acc_visited += total;
             // emit the pairs of this block in slices that fit the queue (row-major order)
             uint32_t e0 = 0;
             do {
@@ -480,6 +481,7 @@ k_triplets_pool(const DevCfg cfg, const TripletArgs a) {
     if (lane == 0) {
         atomicAdd(&s_ntrip, acc_trip);
         atomicAdd(&s_tests, acc_tests);
+        if (acc_visited) atomicAdd(&a.ctrl->triplet_visited, acc_visited);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
