@@ -276,6 +276,68 @@ def ref_estimate_params(bottom, middle, top, xyz, bfield, tpe=None, sp_meas_inde
     return out
 
 
+REF_ADAPTER_LIB_PATH = os.path.join(_HERE, "_ref", "libtraccc_ref_adapter.so")
+_ref_adapter = None
+
+
+def ref_adapter_lib():
+    """oracle/_ref/libtraccc_ref_adapter.so (oracle/ref_adapter.cu): the drop-in classes of
+    include/traccc_b200/traccc_adapter.hpp compiled against the reference's real EDM types, next
+    to the reference's own CUDA algorithm. None when it was never built."""
+    global _ref_adapter
+    if _ref_adapter is None:
+        if not os.path.exists(REF_ADAPTER_LIB_PATH):
+            if os.path.isdir("/root/reference/device/cuda/src/seeding"):
+                subprocess.check_call(["make", "-C", _HERE, "ref_adapter"], stdout=subprocess.DEVNULL)
+            if not os.path.exists(REF_ADAPTER_LIB_PATH):
+                return None
+        R = C.CDLL(REF_ADAPTER_LIB_PATH)
+        R.ref_adapter_run.restype = C.c_long
+        R.ref_adapter_run.argtypes = [C.c_int, C.POINTER(FinderCfg), C.POINTER(GridCfg), C.POINTER(FilterCfg),
+                                      C.POINTER(TpeCfg), C.c_uint32] + [C.c_void_p] * 4 + [
+                                      C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32] + \
+                                     [C.c_void_p] * 5
+        _ref_adapter = R
+    return _ref_adapter
+
+
+def ref_adapter_run(which, ev, finder=None, grid=None, filt=None, tpe=None, resizable_input=False):
+    """which = 0: traccc::cuda::triplet_seeding_algorithm (the reference's CUDA code);
+    which = 1: traccc::b200::triplet_seeding_algorithm + seed_parameter_estimation_algorithm —
+    both through the reference's EDM buffers / views on the GPU. Returns seed columns (+ params)."""
+    R = ref_adapter_lib()
+    if R is None:
+        return None
+    d = default_configs()
+    finder = finder or d[0]
+    if grid is None:
+        grid = GridCfg()
+        lib().oracle_grid_cfg_from_finder(C.byref(finder), C.byref(grid))
+    filt = filt or d[2]
+    tpe = tpe or d[3]
+    xyz = np.ascontiguousarray(ev.xyz, np.float32)
+    n = xyz.shape[0]
+    cap = max(1, n * max(1, int(finder.maxSeedsPerSpM)))
+    out = {k: np.empty(cap, np.uint32) for k in ("bottom", "middle", "top")}
+    out["quality"] = np.empty(cap, np.float32)
+    params = np.zeros(cap, dtype=BOUND_PARAMS_DTYPE)
+    vz = np.ascontiguousarray(ev.var_z, np.float32)
+    vr = np.ascontiguousarray(ev.var_r, np.float32)
+    smi = np.ascontiguousarray(ev.meas_index, np.uint32)
+    ml = np.ascontiguousarray(ev.meas_local, np.float32)
+    ms = np.ascontiguousarray(ev.meas_surface, np.uint64)
+    bf = np.ascontiguousarray(ev.bfield, np.float32)
+    ns = R.ref_adapter_run(which, C.byref(finder), C.byref(grid), C.byref(filt), C.byref(tpe), n, _ptr(xyz),
+                           _ptr(vz), _ptr(vr), _ptr(smi), ml.shape[0], _ptr(ml), _ptr(ms), _ptr(bf),
+                           1 if resizable_input else 0, cap, _ptr(out["bottom"]), _ptr(out["middle"]),
+                           _ptr(out["top"]), _ptr(out["quality"]), _ptr(params))
+    if ns < 0:
+        raise RuntimeError("ref_adapter_run failed")
+    res = {k: v[:ns].copy() for k, v in out.items()}
+    res["params"] = params[:ns].copy()
+    return res
+
+
 REF_CUDA_LIB_PATH = os.path.join(_HERE, "_ref", "libtraccc_ref_cuda.so")
 _ref_cuda = None
 
