@@ -227,6 +227,35 @@ def test_stage2_predecision_never_contradicts_the_exact_cut(cfg):
         assert np.array_equal(fast[decided], exact[decided])
 
 
+@pytest.mark.parametrize("cfg", [{}, dict(minPt=1.0), dict(impactMax=3.0)])
+def test_stage2_bounded_variant_is_the_guarded_one(cfg):
+    """doublet_stage2_fast_bounded (no magnitude guards; used when DevCfg::fast_bounded says every
+    valid spacepoint lies far inside the minimum helix radius) must give exactly the answers of
+    doublet_stage2_fast for coordinates inside that bound (r <= rMax + |beam| + 1), including
+    axis-parallel chords, identical points and NaNs."""
+    finder = seedfinder_config(**cfg)
+    finder.setup()
+    dc = _devcfg(finder, spacepoint_grid_config(finder), seedfilter_config())
+    rng = np.random.default_rng(23)
+    n = 300000
+    r1 = rng.uniform(0.0, 201.0, n)
+    r2 = rng.uniform(0.0, 201.0, n)
+    phi = rng.uniform(-np.pi, np.pi, n)
+    dphi = rng.normal(0, 0.3, n)
+    xy = np.stack([r1 * np.cos(phi), r1 * np.sin(phi), r2 * np.cos(phi + dphi), r2 * np.sin(phi + dphi)], 1)
+    xy = xy.astype(np.float32)
+    xy[:1000, 2] = xy[:1000, 0]          # dx == 0
+    xy[1000:2000, 3] = xy[1000:2000, 1]  # dy == 0
+    xy[2000:3000, 2:] = xy[2000:3000, :2]
+    xy[3000:3010, 0] = np.nan
+    exact, fast = _stage2(dc, xy)
+    fb = np.zeros(len(xy), np.int32)
+    _lib.lib().b200seed_host_probe_stage2_bounded(dc, len(xy), _p(np.ascontiguousarray(xy)), _p(fb))
+    assert np.array_equal(fb, fast)
+    decided = fb != 2
+    assert np.array_equal(fb[decided], exact[decided])
+
+
 def test_triplet_prefilter_is_conservative_at_the_cut_boundaries():
     """triplet_certainly_rejected (division-free) against the exact triplet_is_compatible on
     combinations pushed onto the helix-diameter / impact-parameter boundaries: accepted triplets

@@ -212,6 +212,9 @@ def lib() -> C.CDLL:
     if hasattr(L, "b200seed_host_probe_stage2"):   # test-only probe; older A/B builds lack it
         L.b200seed_host_probe_stage2.argtypes = [vp, u32, vp, vp, vp]
         L.b200seed_host_probe_stage2.restype = None
+    if hasattr(L, "b200seed_host_probe_stage2_bounded"):
+        L.b200seed_host_probe_stage2_bounded.argtypes = [vp, u32, vp, vp]
+        L.b200seed_host_probe_stage2_bounded.restype = None
     L.b200seed_host_probe_cell_window.argtypes = [vp, C.POINTER(seedfinder_config), u32, u32, vp, vp,
                                                   vp, vp, vp]
     L.b200seed_host_probe_cell_window.restype = None

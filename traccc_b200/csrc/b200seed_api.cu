@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "../../include/b200seed.h"
+#include "../../include/b200seed_probes.h"
 #include "seed_kernels.cuh"
 #include "seed_tile.cuh"
 #include "seed_pool.cuh"
@@ -786,10 +787,9 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
     }
     {
         KernelTimer t(h, s, "bin_scatter");
-        k_bin_scatter<<<nblk, BIN_THREADS, 0, s>>>(h->dev, L.g, n_sp, d_xyz, d_var_z, d_var_r, bin_of,
-                                                   blk_hist, nblk, sp4, var2, sorted_index,
-                                                   sorted_bin, cell_off, cell_cnt, csp4, ccanon,
-                                                   d_n_sp, ctrl);
+        k_bin_scatter<<<nblk, BIN_THREADS, h->nbins * sizeof(uint32_t), s>>>(
+            h->dev, L.g, n_sp, d_xyz, d_var_z, d_var_r, bin_of, blk_hist, nblk, sp4, var2, sorted_index,
+            sorted_bin, cell_off, cell_cnt, csp4, ccanon, d_n_sp, ctrl, h->nbins);
     }
     {
         DoubletArgs a{};
@@ -1498,6 +1498,13 @@ void b200seed_host_probe_stage2(const void* devcfg, uint32_t n, const float* xy,
         const float* q = xy + 4 * size_t(i);
         exact[i] = doublet_stage2(d, q[0], q[1], q[2], q[3]) ? 1 : 0;
         fast[i] = doublet_stage2_fast(d, q[0], q[1], q[2], q[3]);
+    }
+}
+void b200seed_host_probe_stage2_bounded(const void* devcfg, uint32_t n, const float* xy, int32_t* fast) {
+    const DevCfg& d = *static_cast<const DevCfg*>(devcfg);
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* q = xy + 4 * size_t(i);
+        fast[i] = doublet_stage2_fast_bounded(d, q[0], q[1], q[2], q[3]);
     }
 }
 // Pruning index: for n (middle, other) pairs, whether the other spacepoint's cell lies inside

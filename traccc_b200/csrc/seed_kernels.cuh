@@ -343,19 +343,33 @@ k_bin_scatter(const DevCfg cfg, const CellGrid g, const uint32_t n_sp_max,
               uint32_t* __restrict__ sorted_index, uint32_t* __restrict__ sorted_bin,
               const uint32_t* __restrict__ cell_off, uint32_t* __restrict__ cell_cur,
               float4* __restrict__ csp4, uint32_t* __restrict__ ccanon,
-              const uint32_t* __restrict__ n_sp_dev, Control* __restrict__ ctrl) {
-    __shared__ uint32_t s_bin[BIN_THREADS];
+              const uint32_t* __restrict__ n_sp_dev, Control* __restrict__ ctrl, const uint32_t nbins) {
+    // rank among the earlier spacepoints of this block that fall into the same bin: ascending
+    // original index inside every bin, like the CPU's push_back loop
+    // (core/src/seeding/spacepoint_binning.cpp:40-50). Inside a warp: __match_any_sync + popc of
+    // the lower lanes; across the warps of the block: a shared-memory histogram (dynamic, nbins
+    // words) that the warps update one after the other, in order.
+    extern __shared__ uint32_t s_hist[];
     const uint32_t n_sp = dev_count(n_sp_max, n_sp_dev);
     const uint32_t i = blockIdx.x * BIN_THREADS + threadIdx.x;
     const uint32_t bin = (i < n_sp) ? bin_of[i] : INVALID_BIN;
-    s_bin[threadIdx.x] = bin;
+    const uint32_t lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5;
+    for (uint32_t b = threadIdx.x; b < nbins; b += BIN_THREADS) s_hist[b] = 0u;
+    const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+    const uint32_t in_warp = __popc(peers & ((1u << lane_) - 1u));
+    const uint32_t leader = __ffs(int(peers)) - 1u;
+    uint32_t before = 0;
     __syncthreads();
+    for (uint32_t w = 0; w < BIN_THREADS / 32; ++w) {
+        if (warp_ == w && bin != INVALID_BIN && lane_ == leader) {
+            before = s_hist[bin];  // one leader per distinct bin: no conflict inside the warp
+            s_hist[bin] = before + __popc(peers);
+        }
+        __syncthreads();
+    }
+    before = __shfl_sync(0xffffffffu, before, leader);
     if (bin == INVALID_BIN) return;
-    // rank among the earlier spacepoints of this block that fall into the same bin:
-    // ascending original index inside every bin, like the CPU's push_back loop
-    // (core/src/seeding/spacepoint_binning.cpp:40-50).
-    uint32_t rank = 0;
-    for (uint32_t t = 0; t < threadIdx.x; ++t) rank += (s_bin[t] == bin) ? 1u : 0u;
+    const uint32_t rank = before + in_warp;
     const uint32_t pos = blk_scan[size_t(bin) * nblk + blockIdx.x] + rank;
     const float x = __ldg(xyz + 3 * size_t(i));
     const float y = __ldg(xyz + 3 * size_t(i) + 1);
@@ -646,6 +660,7 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
     __syncthreads();
     const uint32_t n_valid = a.ctrl->n_valid;
     const bool has_var = a.ctrl->has_variance != 0u;
+    const bool bounded = cfg.fast_bounded != 0u;  // the pre-decision needs no magnitude guards
     const CellGrid g = a.g;
     unsigned long long pairs = 0ull, visited = 0ull;  // per lane
     uint32_t acc_active = 0, acc_nb = 0, acc_nt = 0;
@@ -756,7 +771,8 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
                         if (st != 0) {
                             // division-free pre-decision; the exact reference chain only for
                             // the few pairs inside its uncertainty band
-                            int d = doublet_stage2_fast(cfg, M.x, M.y, P.x, P.y);
+                            int d = bounded ? doublet_stage2_fast_bounded(cfg, M.x, M.y, P.x, P.y)
+                                            : doublet_stage2_fast(cfg, M.x, M.y, P.x, P.y);
                             if (d == 2) d = doublet_stage2(cfg, M.x, M.y, P.x, P.y) ? 1 : 0;
                             if (d == 0) st = 0;
                         }
