@@ -346,6 +346,69 @@ def extras(args, rank, world, local, dev, finder, grid, filt, events):
         out["muons100"] = {"workload": "configs[0]: 100 single muons (10 GeV), one event on one stream",
                            **{k: r0[k] for k in ("spacepoints", "seeds", "overflow", "ms_per_event",
                                                  "events_per_s_one_stream", "kernel_ms")}}
+        # the same event as a CUDA graph (b200seed_run / b200seed_estimate_params never touch the
+        # host between their launches, so the whole event is capturable): launch overhead removed
+        try:
+            sps0 = seeding.spacepoint_collection.from_event(mu[0], dev)
+            meas0 = seeding.measurement_collection.from_event(mu[0], dev)
+            seeds0 = alg(sps0)
+            par0 = tpe(mu[0].bfield, meas0, sps0, seeds0)
+            torch.cuda.synchronize()
+            cs = torch.cuda.Stream(device=dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(cs):
+                with torch.cuda.graph(g, stream=cs):
+                    alg(sps0, out=seeds0, stream=cs)
+                    tpe(mu[0].bfield, meas0, sps0, seeds0, out=par0, stream=cs)
+            n_before = seeds0.size()
+            ts = []
+            for _ in range(20):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                with torch.cuda.stream(cs):
+                    e0.record(cs)
+                    g.replay()
+                    e1.record(cs)
+                e1.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            assert seeds0.size() == n_before == r0["seeds"]
+            out["muons100"]["cuda_graph_ms_per_event"] = float(np.median(ts))
+            out["muons100"]["cuda_graph_events_per_s"] = 1e3 / float(np.median(ts))
+            del g
+        except Exception as exc:      # an extra must never break the bench line
+            out["muons100"]["cuda_graph"] = f"unavailable: {type(exc).__name__}: {exc}"
+        # ... and many such events in flight (8 streams x 8 events)
+        try:
+            S8 = 8
+            st8 = [torch.cuda.Stream(device=dev) for _ in range(S8)]
+            a8 = [seeding.triplet_seeding_algorithm(finder, grid, filt, device=local) for _ in range(S8)]
+            t8 = [seeding.seed_parameter_estimation_algorithm(device=local) for _ in range(S8)]
+            sp8 = [seeding.spacepoint_collection.from_event(e, dev) for e in mu]
+            me8 = [seeding.measurement_collection.from_event(e, dev) for e in mu]
+            NE = 64
+            o8 = [a8[i % S8](sp8[i % 10], stream=st8[i % S8]) for i in range(NE)]
+            p8 = [t8[i % S8](mu[i % 10].bfield, me8[i % 10], sp8[i % 10], o8[i], stream=st8[i % S8]) for i in range(NE)]
+            torch.cuda.synchronize()
+            best = 1e9
+            for _ in range(5):
+                main = torch.cuda.current_stream()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(main)
+                for s_ in st8:
+                    s_.wait_event(e0)
+                for i in range(NE):
+                    a8[i % S8](sp8[i % 10], out=o8[i], stream=st8[i % S8])
+                    t8[i % S8](mu[i % 10].bfield, me8[i % 10], sp8[i % 10], o8[i], out=p8[i], stream=st8[i % S8])
+                for s_ in st8:
+                    ev_ = torch.cuda.Event()
+                    ev_.record(s_)
+                    main.wait_event(ev_)
+                e1.record(main)
+                e1.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            out["muons100"]["events_per_s_8_streams"] = NE / (best * 1e-3)
+            del a8, t8, o8, p8
+        except Exception as exc:
+            out["muons100"]["events_per_s_8_streams"] = f"unavailable: {type(exc).__name__}: {exc}" 
         # configs[2]: occupancy sweep
         out["sweep"] = []
         for n_p, seed, reps in ((1000, 201, 10), (5000, 202, 8), (20000, 203, 5), (50000, 204, 3)):

@@ -535,3 +535,58 @@ def test_stress_event_full_size():
     same = mid[1:] == mid[:-1]
     assert (np.diff(s["quality"])[same] <= 0).all()
     assert np.isfinite(a["params"]["vec"]).all()
+
+
+def test_event_is_stream_capturable():
+    """b200seed_run + b200seed_estimate_params never touch the host between their launches (every
+    size the reference reads back stays on the device), so a whole event can be captured into a
+    CUDA graph and replayed: same seeds and parameters as the eager call, also after the input
+    buffers were overwritten with another event of the same size."""
+    import torch
+    from traccc_b200 import (seedfilter_config, seedfinder_config, seeding, spacepoint_grid_config,
+                             toy_detector)
+    ev1 = toy_detector.generate_event(300, 81)
+    ev2 = toy_detector.generate_event(300, 82)
+    n = min(ev1.n_spacepoints, ev2.n_spacepoints)
+    finder = seedfinder_config()
+    sa = seeding.triplet_seeding_algorithm(finder, spacepoint_grid_config(finder), seedfilter_config())
+    tp = seeding.seed_parameter_estimation_algorithm()
+
+    def cut(ev):
+        import copy
+        e = copy.copy(ev)
+        e.xyz, e.var_z, e.var_r = ev.xyz[:n].copy(), ev.var_z[:n].copy(), ev.var_r[:n].copy()
+        e.meas_index = np.arange(n, dtype=np.uint32)
+        e.meas_local, e.meas_surface = ev.meas_local[:n].copy(), ev.meas_surface[:n].copy()
+        return e
+
+    e1, e2 = cut(ev1), cut(ev2)
+    sps = seeding.spacepoint_collection.from_event(e1)
+    meas = seeding.measurement_collection.from_event(e1)
+    seeds = sa(sps)
+    par = tp(e1.bfield, meas, sps, seeds)
+    torch.cuda.synchronize()
+    eager1 = (seeds.to_host(), tp.to_host(par, seeds.size()).copy())
+    cs = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(cs):
+        with torch.cuda.graph(g, stream=cs):
+            sa(sps, out=seeds, stream=cs)
+            tp(e1.bfield, meas, sps, seeds, out=par, stream=cs)
+    for ev, want in ((e2, None), (e1, eager1)):
+        sps.xyz.copy_(torch.from_numpy(ev.xyz))
+        meas.local_position.copy_(torch.from_numpy(ev.meas_local))
+        meas.surface_link.copy_(torch.from_numpy(ev.meas_surface.view(np.int64)))
+        torch.cuda.synchronize()
+        g.replay()
+        torch.cuda.synchronize()
+        got = (seeds.to_host(), tp.to_host(par, seeds.size()).copy())
+        if want is None:
+            ref = oracle.run(ev.xyz, ev.var_z, ev.var_r, dump=False)
+            want_s = ref.seeds
+        else:
+            want_s = want[0]
+            assert np.array_equal(got[1].view(np.uint8), want[1].view(np.uint8))
+        for k in ("bottom", "middle", "top"):
+            assert np.array_equal(got[0][k], want_s[k]), k
+        assert np.array_equal(got[0]["quality"].view(np.uint32), want_s["quality"].view(np.uint32))
