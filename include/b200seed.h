@@ -167,7 +167,8 @@ typedef struct b200seed_counters {
 #define B200SEED_OVF_SEEDS 2u    /* seed_capacity too small                     */
 #define B200SEED_OVF_DUMP 4u     /* debug triplet dump buffer too small         */
 #define B200SEED_OVF_TRIPLETS 8u /* one mid-bottom doublet has more triplets than the
-                                    shared-memory list holds (pathological)       */
+                                    shared-memory list holds AND the doublet arena has no
+                                    room left for them: raise max_doublets        */
 
 /* Error codes */
 #define B200SEED_OK 0
@@ -211,6 +212,12 @@ int b200seed_set_max_doublets(b200seed_handle* h, uint64_t max_doublets);
  * spacepoints, 512 above). Values whose shared-memory footprint (80 bytes * cap per CTA) exceeds
  * the device's opt-in limit are rejected with B200SEED_EINVAL. Results do not depend on it. */
 int b200seed_set_stage_cap(b200seed_handle* h, uint32_t cap);
+
+/* Tuning knob: accepted triplets of one middle kept in shared memory before they are merged into
+ * its top-N (0 = automatic: 96 up to 80k spacepoints, 128 above). A single mid-bottom doublet with
+ * more accepted triplets than this takes a slow path through global memory (the unused tail of
+ * the doublet arena). Results do not depend on it. */
+int b200seed_set_triplet_list_cap(b200seed_handle* h, uint32_t cap);
 
 /* Truncation check for the asynchronous entry points (b200seed_run, b200seed_run_n_on_device):
  * after the caller has synchronised the stream, returns B200SEED_EOVERFLOW (and the B200SEED_OVF_*

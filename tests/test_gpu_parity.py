@@ -23,7 +23,7 @@ def _physics_counters(c):
     return {k: v for k, v in c.items() if k not in ("pair_visited", "n_fallback_middles", "reserved_", "triplet_visited")}
 
 
-def _run_gpu(ev, finder=None, filt=None, grid=None, dump=True, max_doublets=0, stage_cap=0):
+def _run_gpu(ev, finder=None, filt=None, grid=None, dump=True, max_doublets=0, stage_cap=0, list_cap=0):
     import torch
     from traccc_b200 import (seedfilter_config, seedfinder_config, seeding,
                              spacepoint_grid_config)
@@ -31,7 +31,8 @@ def _run_gpu(ev, finder=None, filt=None, grid=None, dump=True, max_doublets=0, s
     grid = grid or spacepoint_grid_config(finder)
     filt = filt or seedfilter_config()
     sa = seeding.triplet_seeding_algorithm(finder, grid, filt, triplet_dump=(4_000_000 if dump else 0),
-                                           max_doublets=max_doublets, stage_cap=stage_cap)
+                                           max_doublets=max_doublets, stage_cap=stage_cap,
+                                           list_cap=list_cap)
     tp = seeding.seed_parameter_estimation_algorithm()
     sps = seeding.spacepoint_collection.from_event(ev)
     meas = seeding.measurement_collection.from_event(ev)
@@ -46,8 +47,8 @@ def _run_gpu(ev, finder=None, filt=None, grid=None, dump=True, max_doublets=0, s
     return res, (finder, grid, filt)
 
 
-def _check_event(ev, finder=None, filt=None, grid=None, dump=True, stage_cap=0):
-    got, (finder, grid, filt) = _run_gpu(ev, finder, filt, grid, dump, stage_cap=stage_cap)
+def _check_event(ev, finder=None, filt=None, grid=None, dump=True, stage_cap=0, list_cap=0):
+    got, (finder, grid, filt) = _run_gpu(ev, finder, filt, grid, dump, stage_cap=stage_cap, list_cap=list_cap)
     of, og, ofl = oracle_cfgs(finder, grid, filt)
     ref = oracle.run(ev.xyz, ev.var_z, ev.var_r, finder=of, grid=og, filt=ofl, dump=dump,
                      sp_meas_index=ev.meas_index, meas_local=ev.meas_local,
@@ -590,3 +591,66 @@ def test_event_is_stream_capturable():
         for k in ("bottom", "middle", "top"):
             assert np.array_equal(got[0][k], want_s[k]), k
         assert np.array_equal(got[0]["quality"].view(np.uint32), want_s["quality"].view(np.uint32))
+
+
+def _rays_event(n_rays=24, n_tops=40, seed=3, variances=0.0):
+    """Straight tracks with one bottom, one middle and n_tops tightly spaced top spacepoints on the
+    same ray: every (bottom, middle) doublet has up to n_tops accepted triplets — far more than any
+    toy-detector event (four barrel layers allow ~10)."""
+    from traccc_b200 import toy_detector
+    rng = np.random.default_rng(seed)
+    pts = []
+    for k in range(n_rays):
+        phi = -3.0 + 6.0 * k / n_rays + rng.uniform(-0.01, 0.01)
+        cot = rng.uniform(-1.0, 1.0)
+        z0 = rng.uniform(-50, 50)
+        for r in [40.0, 80.0] + [101.0 + 1.0 * i for i in range(n_tops)]:
+            r_ = r + rng.uniform(-0.05, 0.05)
+            pts.append([r_ * np.cos(phi), r_ * np.sin(phi), z0 + cot * r_])
+    xyz = np.array(pts, np.float32)
+    n = len(xyz)
+    var = (rng.uniform(0, variances, (2, n)) if variances > 0 else np.zeros((2, n))).astype(np.float32)
+    return toy_detector.ToyEvent(xyz, var[0], var[1], np.arange(n, dtype=np.uint32)[::-1].copy(),
+                                 rng.uniform(-1, 1, (n, 2)).astype(np.float32),
+                                 rng.integers(1, 1 << 40, n).astype(np.uint64), np.zeros(n, np.uint32), n_rays,
+                                 np.array([0.0, 0.0, 5.9958e-4], np.float32))
+
+
+@pytest.mark.parametrize("list_cap", [0, 16, 32])
+def test_parity_rows_that_outgrow_the_triplet_list(list_cap):
+    """A mid-bottom doublet with more accepted triplets than the shared-memory list of k_triplets
+    holds: the middle is handed to the slow path (triplets_slow_middles: the last CTA redoes it row
+    by row through the unused tail of the doublet arena). Forced with rows of 40 triplets against
+    lists of 16 / 32 entries (0: the default 96, the fast path on the same event). Triplet sets with
+    curvature and weights, seeds and parameters must be the oracle's, without any overflow flag;
+    also with non-zero variances and maxSeedsPerSpM = 12."""
+    from traccc_b200 import seedfinder_config, spacepoint_grid_config
+    got, ref = _check_event(_rays_event(), list_cap=list_cap)
+    per_row = np.unique(np.stack([ref.triplets["m"], ref.triplets["b"]], 1), axis=0, return_counts=True)[1]
+    assert per_row.max() >= 40
+    _check_event(_rays_event(n_rays=40, n_tops=60, seed=4, variances=0.01), list_cap=list_cap)
+    finder = seedfinder_config(maxSeedsPerSpM=12)
+    _check_event(_rays_event(seed=5), finder=finder, grid=spacepoint_grid_config(finder), list_cap=list_cap)
+
+
+def test_parity_big_rows_dense_variant():
+    """The same hand-over inside k_triplets<1> (events above 80k spacepoints use it): an ordinary
+    20k-particle event plus rays whose rows outgrow a 16-entry list."""
+    from traccc_b200 import toy_detector
+    ev = toy_detector.generate_event(20000, 45)
+    rays = _rays_event(n_rays=30, n_tops=50, seed=6)
+    import copy
+    big = copy.copy(ev)
+    big.xyz = np.concatenate([ev.xyz, rays.xyz])
+    n = len(big.xyz)
+    big.var_z = np.zeros(n, np.float32)
+    big.var_r = np.zeros(n, np.float32)
+    big.meas_index = np.arange(n, dtype=np.uint32)
+    big.meas_local = np.zeros((n, 2), np.float32)
+    big.meas_surface = np.arange(n, dtype=np.uint64)
+    a, _ = _run_gpu(big, dump=False)
+    b, _ = _run_gpu(big, dump=False, list_cap=16)
+    assert a["counters"]["overflow"] == 0 and b["counters"]["overflow"] == 0
+    assert _physics_counters(a["counters"]) == _physics_counters(b["counters"])
+    for k in ("bottom", "middle", "top", "quality"):
+        assert np.array_equal(a["seeds"][k], b["seeds"][k])

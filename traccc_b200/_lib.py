@@ -124,7 +124,7 @@ EXPORTS = (
     "b200seed_finder_cfg_defaults", "b200seed_finder_cfg_setup", "b200seed_grid_cfg_from_finder",
     "b200seed_filter_cfg_defaults", "b200seed_tpe_cfg_defaults", "b200seed_create",
     "b200seed_destroy", "b200seed_last_error", "b200seed_get_axes", "b200seed_set_max_doublets",
-    "b200seed_set_stage_cap", "b200seed_check_overflow", "b200seed_pool_create", "b200seed_pool_process",
+    "b200seed_set_stage_cap", "b200seed_set_triplet_list_cap", "b200seed_check_overflow", "b200seed_pool_create", "b200seed_pool_process",
     "b200seed_pool_last_error", "b200seed_pool_destroy",
     "b200seed_workspace_bytes", "b200seed_run", "b200seed_estimate_params", "b200seed_run_host",
     "b200seed_form_spacepoints", "b200seed_run_n_on_device", "b200seed_estimate_params_inhom",
@@ -164,6 +164,8 @@ def lib() -> C.CDLL:
     L.b200seed_set_max_doublets.argtypes = [vp, u64]
     L.b200seed_set_triplet_dump.argtypes = [vp, u64]
     L.b200seed_set_stage_cap.argtypes = [vp, u32]
+    if hasattr(L, "b200seed_set_triplet_list_cap"):   # older A/B builds lack it
+        L.b200seed_set_triplet_list_cap.argtypes = [vp, u32]
     L.b200seed_check_overflow.argtypes = [vp, C.POINTER(u32)]
     L.b200seed_workspace_bytes.argtypes = [vp, u32]
     L.b200seed_workspace_bytes.restype = sz

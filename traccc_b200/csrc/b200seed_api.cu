@@ -44,7 +44,7 @@ inline size_t align_up(size_t v, size_t a) {
 struct Layout {
     size_t control, cell_cnt, bin_of, blk_hist, bin_off, cell_off, sorted_index, sorted_bin, sp4,
         var2, csp4, ccanon, cnt, off, seed_cnt, seed_b, seed_t, seed_w, arena_b, arena_t,
-        dump, gather_state, spill_list, active_list, group_list, fallback_list, total;
+        dump, gather_state, spill_list, active_list, group_list, fallback_list, slow_list, total;
     size_t zero_bytes;  // control block, cell populations, look-back state: cleared per event
     uint32_t nblk;
     uint64_t max_doublets, max_dump;
@@ -69,6 +69,7 @@ struct b200seed_handle {
     uint64_t max_doublets_user = 0;
     uint64_t max_dump = 0;
     uint32_t stage_cap_user = 0;
+    uint32_t list_cap_user = 0;
     // doublet search: 2 = warp-per-middle k_doublets<0> (default: the faster one),
     // 0 = k_doublets_tile (groups of middles, cp.async.bulk staging), 1 = the same with 16-byte
     // cp.async (B200SEED_DOUBLETS=warp|tile|ldgsts, read at b200seed_create)
@@ -220,6 +221,7 @@ Layout make_layout(const b200seed_handle* h, uint32_t max_sp) {
     L.seed_b = take(n * K * 4);
     L.seed_t = take(n * K * 4);
     L.seed_w = take(n * K * 4);
+    L.slow_list = take(2 * n * 4);
     L.arena_b = take(L.max_doublets * sizeof(DoubletRec));
     L.arena_t = take(L.max_doublets * sizeof(DoubletRec));
     L.dump = take(L.max_dump * sizeof(TripletDumpRec));
@@ -639,6 +641,18 @@ int b200seed_set_stage_cap(b200seed_handle* h, uint32_t cap) {
     return B200SEED_OK;
 }
 
+int b200seed_set_triplet_list_cap(b200seed_handle* h, uint32_t cap) {
+    if (!h) return B200SEED_EINVAL;
+    // (the per-warp shared-memory block must stay 16-byte aligned: 27 bytes per entry)
+    if (cap != 0 && (cap < 16 || cap > 1024 || (cap & 15u)))
+        return fail(h, B200SEED_EINVAL, "triplet list cap must be 0 or a multiple of 16 in [16, 1024]");
+    if (cap != 0 && triplet_smem_per_warp(cap, true) * WARPS_PER_CTA + 1024 >
+                        size_t(h->smem_optin > 0 ? h->smem_optin : 0))
+        return fail(h, B200SEED_EINVAL, "triplet list cap needs more shared memory than a CTA can have");
+    h->list_cap_user = cap;
+    return B200SEED_OK;
+}
+
 int b200seed_set_triplet_dump(b200seed_handle* h, uint64_t max_triplets) {
     if (!h) return B200SEED_EINVAL;
     if (max_triplets > 0xFFFF0000ull) return fail(h, B200SEED_EINVAL, "max_triplets too large");
@@ -857,8 +871,9 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
         // find an empty list and exit)
         k_doublets<1><<<grid_s, WARPS_PER_CTA * 32, smem, s>>>(h->dev, a);
     }
+    TripletArgs ta{};  // also read by k_seed_gather (slow path of the triplet search)
     {
-        TripletArgs a{};
+        TripletArgs& a = ta;
         a.sp4 = sp4;
         a.var2 = var2;
         a.sorted_bin = sorted_bin;
@@ -875,7 +890,10 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
         a.seed_w = seed_w;
         a.dump = L.max_dump ? reinterpret_cast<TripletDumpRec*>(at(L.dump)) : nullptr;
         a.max_dump = uint32_t(L.max_dump);
-        a.list_cap = triplet_list_cap(n_sp);
+        a.list_cap = h->list_cap_user ? h->list_cap_user : triplet_list_cap(n_sp);
+        a.scratch_t = reinterpret_cast<DoubletRec*>(at(L.arena_t));
+        a.max_doublets = uint32_t(L.max_doublets);
+        a.slow_list = reinterpret_cast<uint32_t*>(at(L.slow_list));
         a.active_list = reinterpret_cast<const uint32_t*>(at(L.active_list));
         a.n_sp = n_sp;
         const bool dense = n_sp > 80000u;
@@ -897,6 +915,8 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
             if (pgrid > pmax) pgrid = pmax;
             k_triplets_pool<<<pgrid, POOL_WARPS * 32, psmem, s>>>(h->dev, a);
         }
+
+
     }
     {
         // exclusive scan of the per-middle seed counts fused into the gather (single pass,
@@ -905,7 +925,7 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
         unsigned long long* gs = reinterpret_cast<unsigned long long*>(at(L.gather_state));
         k_seed_gather<<<nblk, BIN_THREADS, 0, s>>>(
             n_sp, K, ctrl, seed_cnt, seed_b, seed_t, seed_w, sorted_index, seed_capacity, d_bottom,
-            d_middle, d_top, d_quality, d_n_seeds, d_counters, d_n_sp, gs + 1, gs, h->h_sticky);
+            d_middle, d_top, d_quality, d_n_seeds, d_counters, d_n_sp, gs + 1, gs, h->h_sticky, h->dev, ta);
     }
     CUDA_TRY(h, cudaGetLastError());
     return B200SEED_OK;

@@ -96,6 +96,10 @@ struct Control {
     uint32_t ticket_f;        // work queue of that pass
     uint32_t ticket_p;        // work queue of k_triplets_pool (light middles)
     unsigned long long triplet_visited;  // (mid-bottom, mid-top) pairs inside the cotTheta windows
+    uint32_t n_slow;          // middles handed to the slow path (a row outgrew the triplet list)
+    uint32_t ticket_q;        // its work queue
+    uint32_t slow_done;       // set by k_seed_gather's tile 0 when they are finished
+    uint32_t pad3_;
 };
 
 // One doublet record in the arena: two float4.
@@ -1051,6 +1055,10 @@ struct TripletArgs {
     const uint32_t* active_list;  // work list written by k_doublets (heavy first)
     uint32_t n_sp;
     uint32_t heavy_only;          // 1: the light middles are k_triplets_pool's
+    DoubletRec* scratch_t;        // the mid-top arena again, writable: its unused tail holds the
+                                  // triplets of a row that outgrows the shared-memory list
+    uint32_t max_doublets;
+    uint32_t* slow_list;          // [2 * n_sp] (middle, first row k_triplets did not finish)
 };
 
 // One triplet of the current row block (shared memory, 16 bytes).
@@ -1062,6 +1070,7 @@ struct __align__(16) BlockTriplet {
 };
 
 constexpr uint32_t TCOT_CAP = 256;  // cotTheta of the first mid-tops of a middle kept in smem
+constexpr uint32_t HANDED_OVER = 0xFFFFFFF0u;  // row cursor of a middle given to the slow path
 
 // cotTheta of mid-top t: shared-memory copy for the first TCOT_CAP, the arena otherwise
 struct TopCot {
@@ -1143,6 +1152,265 @@ __host__ __device__ inline size_t triplet_smem_per_warp(uint32_t list_cap, bool 
     // + 64 pending (row, mid-top) pairs of k_triplets<DENSE>'s pre-filter
     return size_t(list_cap) * (16 + 4 + 4 + 2 + 1) + MAX_TOPK * 5 * 4 + TCOT_CAP * 4 +
            (dense ? 64 * 4 : 0);
+}
+
+// One triplet of a mid-bottom row that outgrows the shared-memory list: a 32-byte slot in the unused
+// tail of the mid-top arena (global memory).
+struct __align__(16) BigRowTriplet {
+    uint32_t key;     // canon_key of the top spacepoint, later the position of the bottom one
+    float curvature;  // later: radius of the bottom spacepoint
+    float weight;     // -impact * impactWeightFactor, later the final weight
+    float rT;         // radius of the top spacepoint, later the sorter sum
+    uint32_t pos_t;
+    uint32_t ord;     // slot q holds the list index of the q-th triplet in the reference's order
+    uint32_t aux;     // compatible-seed count, later the rank in the top-K (0xFF: none)
+    uint32_t pad_;
+};
+static_assert(sizeof(BigRowTriplet) == sizeof(DoubletRec), "one arena slot per triplet");
+
+// The slow path of the triplet search: a middle one of whose mid-bottom doublets produced more
+// accepted triplets than the shared-memory list of k_triplets holds. k_triplets hands such a
+// middle over (with the row it stopped at); this kernel redoes it from the first row, row by
+// row, with the same steps as k_triplets' flush — exact cuts against ALL mid-tops of the middle (the
+// cotTheta window is only a pruning), reference order inside the row, compatible-seed bonus, final
+// weight / single-seed cut, merge into the middle's top-K — with the row's triplets in global memory
+// (nt slots from the unused tail of the mid-top arena, allocated once per middle), then makes the
+// final per-middle selection. It runs inside k_seed_gather (tile 0 does it before any tile reads the
+// per-middle seed counts; one load of n_slow per CTA otherwise), because everywhere else it cost
+// the common path: as a call inside k_triplets' row loop +36 %, after that loop +13 %, from the last
+// CTA of k_triplets +4 % (64 registers instead of 62, spills around the call), as its own empty
+// launch -2 % throughput. Warp per handed-over middle.
+__device__ __noinline__ void triplets_slow_middles(const DevCfg& cfg, const TripletArgs& a,
+                                                   uint32_t* smem /* >= 5 * MAX_TOPK words per warp */) {
+    const uint32_t n_slow = *reinterpret_cast<volatile uint32_t*>(&a.ctrl->n_slow);
+    const uint32_t warp = threadIdx.x >> 5;
+    // the kernel's dynamic shared memory is free by now: the per-warp top-K lives there
+    float* top_w = reinterpret_cast<float*>(smem + size_t(warp) * 5 * MAX_TOPK);
+    float* top_s = top_w + MAX_TOPK;
+    float* top_rb = top_s + MAX_TOPK;
+    uint32_t* top_b = reinterpret_cast<uint32_t*>(top_rb + MAX_TOPK);
+    uint32_t* top_t = top_b + MAX_TOPK;
+    const uint32_t n_valid = a.ctrl->n_valid;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t ltmask = lanemask_lt();
+    const uint32_t K = cfg.maxSeedsPerSpM;
+    uint32_t found = 0;
+  while (true) {
+    uint32_t tk = 0;
+    if (lane == 0) tk = atomicAdd(&a.ctrl->ticket_q, 1u);
+    tk = __shfl_sync(0xffffffffu, tk, 0);
+    if (tk >= n_slow) break;
+    const uint32_t m = a.slow_list[2 * tk], row_begin = a.slow_list[2 * tk + 1];
+    const uint32_t nb = a.cnt_b[m], nt = a.cnt_t[m];
+    const DoubletRec* LB = a.arena_b + a.off_b[m];
+    const DoubletRec* LT = a.arena_t + a.off_t[m];
+    const float4 M = __ldg(a.sp4 + m);
+    const float2 VM = __ldg(a.var2 + m);
+    const float rM = M.w, varZM = VM.x, varRM = VM.y;
+    const uint32_t walk_r0 = circular_remap(cfg.nPhi, __ldg(a.sorted_bin + m) % cfg.nPhi, -int(cfg.scope0));
+    uint32_t ntop = 0;  // the whole middle is redone: nothing of k_triplets' top-K was kept
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&a.ctrl->cursor[1], nt);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base > a.max_doublets || nt > a.max_doublets - base) {
+        // no room left in the arena either: the rest of the middle is lost and the event is flagged
+        // (an error for the caller, B200SEED_EOVERFLOW); what was found so far is kept
+        if (lane == 0) atomicOr(&a.ctrl->overflow, B200SEED_OVF_TRIPLETS);
+    } else {
+    BigRowTriplet* S = reinterpret_cast<BigRowTriplet*>(a.scratch_t + base);
+    auto tie_key = [&](uint32_t pos) -> unsigned long long {
+        const uint32_t pb = __ldg(a.sorted_bin + pos) % cfg.nPhi;
+        const uint32_t w = (pb + cfg.nPhi - walk_r0) % cfg.nPhi;
+        return (unsigned long long)w * n_valid + pos;
+    };
+    auto before = [&](float w1, float s1, uint32_t b1, uint32_t t1, float w2, float s2, uint32_t b2,
+                      uint32_t t2) -> bool {
+        if (w1 != w2 || s1 != s2) return seed_before(w1, s1, w2, s2);
+        const unsigned long long k1 = tie_key(b1), k2 = tie_key(b2);
+        return (k1 != k2) ? (k1 < k2) : (tie_key(t1) < tie_key(t2));
+    };
+    for (uint32_t row = 0; row < nb; ++row) {
+        // (0) the exact cuts against every mid-top
+        const float4 ba = __ldg(&LB[row].a);
+        const float4 bb = __ldg(&LB[row].b);
+        LinCircle lb;
+        lb.cotTheta = ba.x, lb.iDeltaR = ba.y, lb.Er = ba.z, lb.U = ba.w;
+        lb.V = bb.x, lb.Zo = bb.y;
+        float is2, s2;
+        triplet_row_constants(cfg, lb.cotTheta, is2, s2);
+        uint32_t n = 0;
+        for (uint32_t p0 = 0; p0 < nt; p0 += 32) {
+            const uint32_t tt = p0 + lane;
+            bool ok = false;
+            BigRowTriplet e{};
+            if (tt < nt) {
+                const float4 ta = __ldg(&LT[tt].a);
+                const float4 tb = __ldg(&LT[tt].b);
+                LinCircle lt;
+                lt.cotTheta = ta.x, lt.iDeltaR = ta.y, lt.Er = ta.z, lt.U = ta.w;
+                lt.V = tb.x, lt.Zo = 0.f;
+                float curvature = 0.f, impact = 0.f;
+                ok = triplet_is_compatible(cfg, rM, varRM, varZM, lb, lt, is2, s2, curvature, impact);
+                e.key = __float_as_uint(tb.y);
+                e.curvature = curvature;
+                e.weight = -impact * cfg.impactWeightFactor;
+                e.rT = tb.z;
+                e.pos_t = __float_as_uint(tb.w);
+            }
+            const uint32_t mk = __ballot_sync(0xffffffffu, ok);
+            if (ok) S[n + __popc(mk & ltmask)] = e;
+            n += __popc(mk);
+        }
+        __syncwarp();
+        if (n == 0) continue;
+        // (1) reference order inside the row: slot rank(i) holds i (the keys are unique)
+        for (uint32_t i = lane; i < n; i += 32) {
+            const uint32_t key = S[i].key;
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < n; ++j) rank += (S[j].key < key) ? 1u : 0u;
+            S[rank].ord = i;
+        }
+        __syncwarp();
+        // (2) compatible-seed bonus (triplet_finding.hpp:107-179)
+        for (uint32_t i = lane; i < n; i += 32) {
+            const float c_rT = S[i].rT, c_curv = S[i].curvature;
+            const float lower = c_curv - cfg.deltaInvHelixDiameter;
+            const float upper = c_curv + cfg.deltaInvHelixDiameter;
+            float compat[MAX_COMPAT];
+            uint32_t ncompat = 0;
+            for (uint32_t q = 0; q < n; ++q) {
+                const uint32_t j = S[q].ord;
+                if (j == i) continue;
+                const float o_rT = S[j].rT, o_curv = S[j].curvature;
+                const float deltaR = c_rT - o_rT;
+                if (absf(deltaR) < cfg.filterDeltaRMin) continue;
+                if (o_curv < lower) continue;
+                if (o_curv > upper) continue;
+                bool newCompSeed = true;
+#pragma unroll
+                for (uint32_t c = 0; c < MAX_COMPAT; ++c)
+                    if (c < ncompat && absf(compat[c] - o_rT) < cfg.filterDeltaRMin) newCompSeed = false;
+                if (newCompSeed) {
+#pragma unroll
+                    for (uint32_t c = 0; c < MAX_COMPAT; ++c)
+                        if (c == ncompat) compat[c] = o_rT;
+                    ++ncompat;
+                }
+                if (ncompat >= cfg.compatSeedLimit) break;
+            }
+            S[i].aux = ncompat;
+        }
+        __syncwarp();
+        // (3) final weight, single-seed cut, sorter sum; optional dump
+        const uint32_t pos_b = __float_as_uint(bb.w);
+        const float rB = bb.z;
+        const float4 PB = __ldg(a.sp4 + pos_b);
+        for (uint32_t i = lane; i < n; i += 32) {
+            BigRowTriplet cur = S[i];
+            float w = cur.weight;  // the reference adds compatSeedWeight one at a time (:171)
+            for (uint32_t q = cur.aux; q > 0; --q) w += cfg.compatSeedWeight;
+            if (a.dump && row >= row_begin) {  // earlier rows were dumped by k_triplets
+                const uint32_t d = atomicAdd(&a.ctrl->dump_cursor, 1u);
+                if (d < a.max_dump) {
+                    TripletDumpRec r;
+                    r.pos_b = pos_b, r.pos_m = m, r.pos_t = cur.pos_t, r.mb_idx = row;
+                    r.mt_idx = cur.key, r.curvature = cur.curvature, r.weight = w;
+                    r.z_vertex = bb.y;
+                    a.dump[d] = r;
+                } else {
+                    atomicOr(&a.ctrl->overflow, B200SEED_OVF_DUMP);
+                }
+            }
+            w += seed_weight_increase(cfg, rB, cur.rT);
+            const bool keep = single_seed_cut(cfg, rB, w);
+            const float4 PT = __ldg(a.sp4 + cur.pos_t);
+            cur.weight = w;
+            cur.rT = sorter_sum(PB.y, PB.z, PT.y, PT.z);
+            cur.curvature = rB;
+            cur.key = keep ? pos_b : 0xFFFFFFFFu;
+            cur.aux = 0xFFu;
+            S[i] = cur;
+        }
+        __syncwarp();
+        // (4) merge into the per-middle top-K (triplet_sorter's order; full ties: order of discovery)
+        uint32_t nkept = 0;
+        for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            uint32_t rank = 0xFFu;
+            if (i < n) {
+                const BigRowTriplet c = S[i];
+                bool in = (c.key != 0xFFFFFFFFu);
+                if (in && ntop == K)
+                    in = before(c.weight, c.rT, c.key, c.pos_t, top_w[K - 1], top_s[K - 1], top_b[K - 1],
+                                top_t[K - 1]);
+                if (in) {
+                    rank = 0;
+                    for (uint32_t q = 0; q < ntop; ++q)
+                        rank += before(top_w[q], top_s[q], top_b[q], top_t[q], c.weight, c.rT, c.key, c.pos_t)
+                                    ? 1u : 0u;
+                    for (uint32_t j = 0; j < n && rank < K; ++j) {
+                        if (j == i) continue;
+                        const uint32_t o_key = S[j].key;
+                        if (o_key != 0xFFFFFFFFu &&
+                            before(S[j].weight, S[j].rT, o_key, S[j].pos_t, c.weight, c.rT, c.key, c.pos_t))
+                            ++rank;
+                    }
+                    if (rank >= K) rank = 0xFFu;
+                }
+            }
+            __syncwarp();                       // everybody has read the list entries it ranks against
+            if (i < n) S[i].aux = rank;
+            nkept += __popc(__ballot_sync(0xffffffffu, rank != 0xFFu));
+        }
+        __syncwarp();
+        if (nkept) {
+            float ew = 0.f, es = 0.f, erb = 0.f;
+            uint32_t eb = 0, et = 0, npos = 0xFFu;
+            if (lane < ntop) {
+                ew = top_w[lane], es = top_s[lane], erb = top_rb[lane];
+                eb = top_b[lane], et = top_t[lane];
+                npos = lane;
+                for (uint32_t j = 0; j < n; ++j) {
+                    if (S[j].aux == 0xFFu) continue;
+                    npos += before(S[j].weight, S[j].rT, S[j].key, S[j].pos_t, ew, es, eb, et) ? 1u : 0u;
+                }
+            }
+            __syncwarp();
+            if (npos < K) {
+                top_w[npos] = ew, top_s[npos] = es, top_rb[npos] = erb;
+                top_b[npos] = eb, top_t[npos] = et;
+            }
+            for (uint32_t i = lane; i < n; i += 32) {
+                const BigRowTriplet c = S[i];
+                if (c.aux != 0xFFu) {
+                    top_w[c.aux] = c.weight, top_s[c.aux] = c.rT, top_rb[c.aux] = c.curvature;
+                    top_b[c.aux] = c.key, top_t[c.aux] = c.pos_t;
+                }
+            }
+            ntop = (ntop + nkept < K) ? (ntop + nkept) : K;
+        }
+        __syncwarp();
+        if (row >= row_begin) found += n;  // earlier rows were counted by k_triplets
+    }
+    }  // arena room
+    // ---- final per-middle selection (seed_filtering.cpp:84-122) ----
+    {
+        const bool keep = lane < ntop && (lane == 0 || cut_per_middle_sp(cfg, top_rb[lane], top_w[lane]));
+        const uint32_t km = __ballot_sync(0xffffffffu, keep);
+        const float w_ = keep ? top_w[lane] : 0.f;
+        const uint32_t b_ = keep ? top_b[lane] : 0u, t_ = keep ? top_t[lane] : 0u;
+        __syncwarp();
+        if (keep) {
+            const uint32_t o = __popc(km & ltmask);
+            a.seed_b[size_t(m) * K + o] = b_;
+            a.seed_t[size_t(m) * K + o] = t_;
+            a.seed_w[size_t(m) * K + o] = w_;
+        }
+        if (lane == 0) a.seed_cnt[m] = __popc(km);
+    }
+    __syncwarp();
+  }
+    if (lane == 0 && found) atomicAdd(&a.ctrl->n_triplets, found);
 }
 
 // Warp per middle spacepoint (atomic ticket queue). For every block of 32 mid-bottom doublets
@@ -1712,13 +1980,24 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
                     nlist = base_n;
                     continue;
                 }
-                // a single row with more triplets than the list holds: keep the first
-                // list_cap and flag the event (cannot happen for list_cap >= nt).
-                if (lane == 0) atomicOr(&a.ctrl->overflow, B200SEED_OVF_TRIPLETS);
-                nlist = a.list_cap;
+                // a single row with more triplets than the list holds: the slow path
+                // (triplets_slow_middles) redoes this middle row by row through global memory;
+                // rows before row0 were already counted and dumped here. The row loop ends through
+                // its normal exit (no rows left), the final selection below is skipped.
+                if (lane == 0) {
+                    const uint32_t e = atomicAdd(&a.ctrl->n_slow, 1u);
+                    a.slow_list[2 * e] = m;
+                    a.slow_list[2 * e + 1] = row0;
+                }
+                nlist = 0;
+                row0 = HANDED_OVER - nrows;
             }
             row0 += nrows;
             rows = 32;
+        }
+        if (row0 == HANDED_OVER) {
+            __syncwarp();
+            continue;
         }
         // ---- final per-middle selection (seed_filtering.cpp:84-122) ----
         {
@@ -1763,12 +2042,32 @@ k_seed_gather(const uint32_t n_sp, const uint32_t K, const Control* __restrict__
               uint32_t* __restrict__ out_t, float* __restrict__ out_q, uint32_t* __restrict__ out_n,
               b200seed_counters* __restrict__ counters, const uint32_t* __restrict__ n_sp_dev,
               unsigned long long* __restrict__ status, unsigned long long* __restrict__ ticket_ctr,
-              uint32_t* __restrict__ sticky_overflow) {
+              uint32_t* __restrict__ sticky_overflow, const __grid_constant__ DevCfg cfg,
+              const __grid_constant__ TripletArgs ta) {
     __shared__ uint32_t s_tile, s_warp[BIN_THREADS / 32], s_prefix;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_tile = uint32_t(atomicAdd(ticket_ctr, 1ull));
     __syncthreads();
     const uint32_t tile = s_tile;
+    // Middles the triplet kernel handed over (a mid-bottom doublet with more accepted triplets than
+    // its shared-memory list holds; none for ordinary events): the CTA that drew tile 0 — it is
+    // running, tiles are handed out in the order the CTAs start — finishes them first, the others
+    // wait for it before they read the per-middle seed counts.
+    if (ta.ctrl->n_slow != 0u) {
+        __shared__ uint32_t s_top[(BIN_THREADS / 32) * 5 * MAX_TOPK];
+        volatile uint32_t* done = &ta.ctrl->slow_done;
+        if (tile == 0) {
+            triplets_slow_middles(cfg, ta, s_top);
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) *done = 1u;
+        } else {
+            if (threadIdx.x == 0)
+                while (*done == 0u) __nanosleep(200);
+            __syncthreads();
+            __threadfence();
+        }
+    }
     const uint32_t m = tile * BIN_THREADS + threadIdx.x;
     const uint32_t n_valid = ctrl->n_valid;
     const uint32_t n = (m < n_valid) ? seed_cnt[m] : 0u;
@@ -1817,24 +2116,26 @@ k_seed_gather(const uint32_t n_sp, const uint32_t K, const Control* __restrict__
                 *out_n = nout;
                 // a truncated event is never silent: the handle's host-mapped word collects the
                 // overflow bits even when the caller passed no counters record
-                const uint32_t ovf = ctrl->overflow | (all > seed_capacity ? B200SEED_OVF_SEEDS : 0u);
+                // (volatile: the slow path above may have updated the block from another SM)
+                const volatile Control* vc = ctrl;
+                const uint32_t ovf = vc->overflow | (all > seed_capacity ? B200SEED_OVF_SEEDS : 0u);
                 if (ovf != 0u && sticky_overflow) atomicOr_system(sticky_overflow, ovf);
                 if (counters) {
                     b200seed_counters c;
                     c.n_spacepoints = dev_count(n_sp, n_sp_dev);
                     c.n_valid = n_valid;
-                    c.n_active_middles = ctrl->n_active;
-                    c.n_mid_bot = ctrl->n_mid_bot;
-                    c.n_mid_top = ctrl->n_mid_top;
-                    c.n_triplets = ctrl->n_triplets;
+                    c.n_active_middles = vc->n_active;
+                    c.n_mid_bot = vc->n_mid_bot;
+                    c.n_mid_top = vc->n_mid_top;
+                    c.n_triplets = vc->n_triplets;
                     c.n_seeds = nout;
                     c.overflow = ovf;
-                    c.pair_tests = ctrl->pair_tests;
-                    c.triplet_tests = ctrl->triplet_tests;
-                    c.pair_visited = ctrl->pair_visited;
-                    c.n_fallback_middles = ctrl->n_fallback;
+                    c.pair_tests = vc->pair_tests;
+                    c.triplet_tests = vc->triplet_tests;
+                    c.pair_visited = vc->pair_visited;
+                    c.n_fallback_middles = vc->n_fallback;
                     c.reserved_ = 0u;
-                    c.triplet_visited = ctrl->triplet_visited;
+                    c.triplet_visited = vc->triplet_visited;
                     *counters = c;
                 }
             }

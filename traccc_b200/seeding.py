@@ -182,7 +182,7 @@ class triplet_seeding_algorithm:
 
     def __init__(self, finder_config: seedfinder_config, grid_config: spacepoint_grid_config,
                  filter_config: seedfilter_config, device: int = 0, stream=None,
-                 max_doublets: int = 0, triplet_dump: int = 0, stage_cap: int = 0):
+                 max_doublets: int = 0, triplet_dump: int = 0, stage_cap: int = 0, list_cap: int = 0):
         self._hd = _Handle(finder_config, grid_config, filter_config, None, device)
         self.lib = self._hd.lib
         self.h = self._hd.h
@@ -197,6 +197,8 @@ class triplet_seeding_algorithm:
             _lib.check(self.lib.b200seed_set_triplet_dump(self.h, int(triplet_dump)), self.h)
         if stage_cap:
             _lib.check(self.lib.b200seed_set_stage_cap(self.h, int(stage_cap)), self.h)
+        if list_cap:
+            _lib.check(self.lib.b200seed_set_triplet_list_cap(self.h, int(list_cap)), self.h)
 
     # --- introspection -------------------------------------------------------------
     def axes(self):
