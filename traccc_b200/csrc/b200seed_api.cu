@@ -214,7 +214,7 @@ Layout make_layout(const b200seed_handle* h, uint32_t max_sp) {
     L.cnt = take(2 * n * 4);
     L.off = take(2 * n * 4);
     L.spill_list = take(n * 4);
-    L.active_list = take(n * 4);
+    L.active_list = take(n * 4 * WORK_CLASSES);
     L.group_list = take(n * 4);
     L.fallback_list = take(n * 4);
     L.seed_cnt = take(n * 4);
@@ -1594,3 +1594,16 @@ void b200seed_host_probe_triplet_prefilter(const void* devcfg, uint32_t n, const
 }
 
 }  // extern "C"
+
+#ifdef B200_TAIL_PROBE
+// debug build only (tools/tail_probe.py)
+extern "C" int b200seed_debug_tail_probe(unsigned long long* out, int reset) {
+    if (out) cudaMemcpyFromSymbol(out, b200seed::g_tail_probe, sizeof(b200seed::g_tail_probe));
+    if (reset) {
+        void* p = nullptr;
+        cudaGetSymbolAddress(&p, b200seed::g_tail_probe);
+        cudaMemset(p, 0, sizeof(b200seed::g_tail_probe));
+    }
+    return 0;
+}
+#endif

@@ -47,6 +47,17 @@ constexpr int SCAN_ITEMS = 4;
 #define B200_WARPS_PER_CTA 8
 #endif
 constexpr int WARPS_PER_CTA = B200_WARPS_PER_CTA;
+#ifdef B200_TAIL_PROBE
+// Debug build only (tools/tail_probe.py): time (globaltimer, ns) at which every warp of the two
+// search kernels drew its first ticket and ran out of tickets, and for k_triplets the start and
+// the sizes of its last middle; read back by b200seed_debug_tail_probe.
+__device__ unsigned long long g_tail_probe[2][4][16384];
+__device__ __forceinline__ unsigned long long probe_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
 constexpr int MAX_TOPK = 16;        // upper bound on maxSeedsPerSpM
 constexpr int MAX_COMPAT = 8;       // upper bound on compatSeedLimit
 // k_triplets hands its middles out longest jobs first: "heavy" = nMidBot * nMidTop at or above
@@ -66,6 +77,17 @@ __host__ __device__ inline bool pool_is_light(uint32_t nB, uint32_t nT) {
     return nT <= POOL_NT && nB <= POOL_NB && (unsigned long long)nB * nT < TRIPLET_HEAVY_WORK;
 }
 
+// Work list of the triplet kernels: WORK_CLASSES lists of n_sp entries each, filled by the doublet
+// kernels and drawn class by class — longest jobs first, so that a launch does not end on a few
+// warps that drew a long middle last, and its final tickets are the shortest jobs (the time a warp
+// spends on a middle follows its number of mid-bottom rows). Classes 0-3: the heavy middles
+// (see pool_is_light), 4-7: the light ones.
+constexpr uint32_t WORK_CLASSES = 8, WORK_HEAVY_CLASSES = 4;
+__host__ __device__ inline uint32_t work_class(uint32_t nB, uint32_t nT) {
+    if (!pool_is_light(nB, nT)) return (nB < 192u ? 1u : 0u) + (nB < 96u ? 1u : 0u) + (nB < 48u ? 1u : 0u);
+    return 4u + (nB < 32u ? 1u : 0u) + (nB < 16u ? 1u : 0u) + (nB < 8u ? 1u : 0u);
+}
+
 // Small control block at the start of the workspace, zeroed at the start of each event.
 struct Control {
     uint32_t cursor[2];       // doublet arena bump pointers (bottom / top)
@@ -83,8 +105,7 @@ struct Control {
     uint32_t ticket_d;        // k_doublets work queue
     uint32_t n_spill;         // middles handed to k_doublets<true> (lists longer than the staging area)
     uint32_t ticket_s;        // its work queue
-    uint32_t n_heavy;         // active middles with much triplet work (front of active_list)
-    uint32_t n_light;         // the other active middles (back of active_list)
+    uint32_t pad0_[2];
     uint32_t has_variance;    // set by k_bin_scatter if any z / radius variance is non-zero
     uint32_t pad_;
     unsigned long long pair_visited;  // candidates actually loaded by k_doublets
@@ -100,7 +121,35 @@ struct Control {
     uint32_t ticket_q;        // its work queue
     uint32_t slow_done;       // set by k_seed_gather's tile 0 when they are finished
     uint32_t pad3_;
+    uint32_t n_cls[WORK_CLASSES];  // entries in each class of the work list
 };
+
+// Start of every class in ticket order (s_pre[WORK_CLASSES] = all): once per CTA, before a
+// __syncthreads().
+__device__ __forceinline__ void work_prefix(const Control* ctrl, uint32_t* s_pre) {
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (uint32_t c = 0; c < WORK_CLASSES; ++c) {
+            s_pre[c] = acc;
+            acc += ctrl->n_cls[c];
+        }
+        s_pre[WORK_CLASSES] = acc;
+    }
+}
+// The middle behind ticket t (t < s_pre[WORK_CLASSES])
+__device__ __forceinline__ uint32_t work_item(const uint32_t* list, uint32_t n_sp, const uint32_t* s_pre,
+                                              uint32_t t) {
+    uint32_t c = 0;
+#pragma unroll
+    for (uint32_t k = 1; k < WORK_CLASSES; ++k) c += (t >= s_pre[k]) ? 1u : 0u;
+    return __ldg(list + size_t(c) * n_sp + (t - s_pre[c]));
+}
+// Append middle m (lane-level; nB != 0)
+__device__ __forceinline__ void work_push(uint32_t* list, uint32_t n_sp, Control* ctrl, uint32_t m,
+                                          uint32_t nB, uint32_t nT) {
+    const uint32_t c = work_class(nB, nT);
+    list[size_t(c) * n_sp + atomicAdd(&ctrl->n_cls[c], 1u)] = m;
+}
 
 // One doublet record in the arena: two float4.
 //   a = {cotTheta, iDeltaR, Er, U}     b = {V, Zo, radius(other), bits(sorted pos of other)}
@@ -676,6 +725,15 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
         if (lane == 0)
             m = atomicAdd(SPILL ? &a.ctrl->ticket_s : (LISTED ? &a.ctrl->ticket_f : &a.ctrl->ticket_d), 1u);
         m = __shfl_sync(0xffffffffu, m, 0);
+#ifdef B200_TAIL_PROBE
+        if (MODE == 0 && lane == 0) {
+            const uint32_t w = blockIdx.x * WARPS_PER_CTA + warp;
+            if (w < 16384u) {
+                if (g_tail_probe[0][0][w] == 0ull) g_tail_probe[0][0][w] = probe_now();
+                if (m >= n_work) g_tail_probe[0][1][w] = probe_now();
+            }
+        }
+#endif
         if (m >= n_work) break;
         if (SPILL) m = a.spill_list[m];
         if (LISTED) m = a.fallback_list[m];
@@ -999,10 +1057,8 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
             // launch does not end on a few warps that drew a heavy middle last.
             if (nB == 0u)
                 a.seed_cnt[m] = 0u;
-            else if (!pool_is_light(nB, nT))
-                a.active_list[atomicAdd(&a.ctrl->n_heavy, 1u)] = m;
             else
-                a.active_list[a.n_sp - 1u - atomicAdd(&a.ctrl->n_light, 1u)] = m;
+                work_push(a.active_list, a.n_sp, a.ctrl, m, nB, nT);
         }
         if (nB) {
             ++acc_active;
@@ -1431,6 +1487,7 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ uint32_t s_ntrip;
     __shared__ unsigned long long s_tests, s_visited;
+    __shared__ uint32_t s_pre[WORK_CLASSES + 1];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t ltmask = lanemask_lt();
     unsigned char* base = s_raw + triplet_smem_per_warp(a.list_cap, DENSE) * warp;
@@ -1450,22 +1507,41 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
         s_ntrip = 0;
         s_tests = s_visited = 0ull;
     }
+    work_prefix(a.ctrl, s_pre);
     __syncthreads();
     const uint32_t n_valid = a.ctrl->n_valid;
     const uint32_t K = cfg.maxSeedsPerSpM;
     uint32_t acc_trip = 0;
     unsigned long long acc_tests = 0ull, acc_visited = 0ull;
 
-    // Work items: the active middles k_doublets listed, heavy ones first (the launch then does
-    // not end on a few warps that drew a heavy middle last), middles without work never drawn.
-    const uint32_t n_heavy = a.ctrl->n_heavy, n_work = n_heavy + (a.heavy_only ? 0u : a.ctrl->n_light);
+    // Work items: the active middles k_doublets listed, longest jobs first (see work_class),
+    // middles without work never drawn.
+    const uint32_t n_work = s_pre[a.heavy_only ? WORK_HEAVY_CLASSES : WORK_CLASSES];
     while (true) {
         uint32_t m = 0;
         if (lane == 0) m = atomicAdd(&a.ctrl->ticket, 1u);
         m = __shfl_sync(0xffffffffu, m, 0);
+#ifdef B200_TAIL_PROBE
+        if (!DENSE && lane == 0) {
+            const uint32_t w = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+            if (w < 16384u) {
+                if (g_tail_probe[1][0][w] == 0ull) g_tail_probe[1][0][w] = probe_now();
+                if (m >= n_work) g_tail_probe[1][1][w] = probe_now();
+            }
+        }
+#endif
         if (m >= n_work) break;
-        m = __ldg(a.active_list + (m < n_heavy ? m : a.n_sp - 1u - (m - n_heavy)));
+        m = work_item(a.active_list, a.n_sp, s_pre, m);
         const uint32_t nb = a.cnt_b[m], nt = a.cnt_t[m];
+#ifdef B200_TAIL_PROBE
+        if (!DENSE && lane == 0) {
+            const uint32_t w = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+            if (w < 16384u) {
+                g_tail_probe[1][2][w] = probe_now();
+                g_tail_probe[1][3][w] = ((unsigned long long)nb << 32) | nt;
+            }
+        }
+#endif
         acc_tests += (unsigned long long)nb * nt;
         const DoubletRec* LB = a.arena_b + a.off_b[m];
         const DoubletRec* LT = a.arena_t + a.off_t[m];

@@ -62,6 +62,7 @@ k_triplets_pool(const DevCfg cfg, const TripletArgs a) {
     extern __shared__ __align__(16) unsigned char s_pool_raw[];
     __shared__ uint32_t s_ntrip;
     __shared__ unsigned long long s_tests;
+    __shared__ uint32_t s_pre[WORK_CLASSES + 1];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t ltmask = lanemask_lt();
     constexpr uint32_t FULL = 0xffffffffu;
@@ -77,12 +78,13 @@ k_triplets_pool(const DevCfg cfg, const TripletArgs a) {
         s_ntrip = 0;
         s_tests = 0ull;
     }
+    work_prefix(a.ctrl, s_pre);
     __syncthreads();
     const uint32_t n_valid = a.ctrl->n_valid;
     const bool has_var = a.ctrl->has_variance != 0u;
     uint32_t acc_trip = 0;
     unsigned long long acc_tests = 0ull, acc_visited = 0ull;
-    const uint32_t n_light = a.ctrl->n_light;
+    const uint32_t n_heavy = s_pre[WORK_HEAVY_CLASSES], n_light = s_pre[WORK_CLASSES] - n_heavy;
 
     // order of a spacepoint among the doublet partners of member j in the reference (canon_key
     // of the doublet kernels); only evaluated for full ties in the seed ranking
@@ -107,7 +109,7 @@ k_triplets_pool(const DevCfg cfg, const TripletArgs a) {
         // ---- members ----
         uint32_t my_nb = 0, my_nt = 0;
         if (lane < G) {
-            const uint32_t m = __ldg(a.active_list + (a.n_sp - 1u - (t0 + lane)));  // light: from the back
+            const uint32_t m = work_item(a.active_list, a.n_sp, s_pre, n_heavy + t0 + lane);  // light classes
             my_nb = a.cnt_b[m];
             my_nt = a.cnt_t[m];
             W.mpos[lane] = m;

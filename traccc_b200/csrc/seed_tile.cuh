@@ -450,19 +450,8 @@ k_doublets_tile(const DevCfg cfg, const TileArgs a) {
             if (aB == 0u) a.seed_cnt[m] = 0u;
         }
         {
-            // work list of k_triplets: heavy middles from the front, light ones from the back
-            const bool heavy = aB != 0u && !pool_is_light(aB, aT);
-            const bool light = aB != 0u && !heavy;
-            const uint32_t mh = __ballot_sync(FULL, heavy), ml = __ballot_sync(FULL, light);
-            uint32_t bh = 0, bl = 0;
-            if (lane == 0) {
-                if (mh) bh = atomicAdd(&a.ctrl->n_heavy, uint32_t(__popc(mh)));
-                if (ml) bl = atomicAdd(&a.ctrl->n_light, uint32_t(__popc(ml)));
-            }
-            bh = __shfl_sync(FULL, bh, 0);
-            bl = __shfl_sync(FULL, bl, 0);
-            if (heavy) a.active_list[bh + __popc(mh & ltmask)] = m;
-            if (light) a.active_list[a.n_sp - 1u - (bl + __popc(ml & ltmask))] = m;
+            // work list of k_triplets (see work_class)
+            if (aB != 0u) work_push(a.active_list, a.n_sp, a.ctrl, m, aB, aT);
         }
         acc_active += __popc(actmask);
         acc_nb += (actmask ? totB : 0u);
