@@ -827,7 +827,13 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
         a.cap_t = a.cap_b / 2;
         const size_t smem = size_t(WARPS_PER_CTA) * doublet_smem_words(a.cap_b, a.cap_t) * 4;
         uint32_t grid = (n_sp + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-        const uint32_t max_grid = uint32_t(h->num_sms) * (32 / WARPS_PER_CTA) * 2;
+        // One wave: as many CTAs as can be resident (the warps draw tickets, so more CTAs only
+        // start, find the queue empty and leave — with several events in flight they take slots
+        // other events' kernels could use: 2x the resident CTAs cost 2.6 % of the event rate).
+#ifndef B200_DOUBLET_GRID_X2
+#define B200_DOUBLET_GRID_X2 2
+#endif
+        const uint32_t max_grid = uint32_t(h->num_sms) * (32 / WARPS_PER_CTA) * B200_DOUBLET_GRID_X2 / 2;
         if (grid > max_grid) grid = max_grid;
         KernelTimer t(h, s, "doublets");
         a.spill_list = reinterpret_cast<uint32_t*>(at(L.spill_list));
@@ -899,7 +905,10 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
         const bool dense = n_sp > 80000u;
         const size_t smem = triplet_smem_per_warp(a.list_cap, dense) * WARPS_PER_CTA;
         uint32_t grid = (n_sp + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-        const uint32_t max_grid = uint32_t(h->num_sms) * (32 / WARPS_PER_CTA) * 3 / 2;
+#ifndef B200_TRIPLET_GRID_X2
+#define B200_TRIPLET_GRID_X2 2
+#endif
+        const uint32_t max_grid = uint32_t(h->num_sms) * (32 / WARPS_PER_CTA) * B200_TRIPLET_GRID_X2 / 2;
         if (grid > max_grid) grid = max_grid;
         KernelTimer t(h, s, "triplets");
         a.heavy_only = h->triplet_pool ? 1u : 0u;
