@@ -464,6 +464,27 @@ def test_parity_group_kernel(mode, monkeypatch):
     assert got["counters"]["n_fallback_middles"] < got["counters"]["n_valid"]
 
 
+@pytest.mark.parametrize("order", ["cost", "grid"])
+def test_parity_doublet_ticket_order(order, monkeypatch):
+    """k_doublets draws its tickets in cost order (k_cell_scan classifies every (bin, r row) by the
+    populations of the rows below / above it, k_bin_scatter lays the middles out class by class;
+    automatic from 16k spacepoints on) or in grid order: forced either way with
+    B200SEED_DOUBLET_ORDER, the binning, doublet and triplet sets, seeds and parameters must be the
+    oracle's — small and ragged events, 7 z bins, spacepoints outside the grid, an empty event."""
+    from traccc_b200 import seedfinder_config, spacepoint_grid_config, toy_detector
+    monkeypatch.setenv("B200SEED_DOUBLET_ORDER", order)
+    _check_event(toy_detector.generate_event(3, 1))
+    _check_event(toy_detector.generate_event(1000, 3))
+    _check_event(toy_detector.generate_event(1000, 4, shuffle=True, variances=0.05))
+    _check_event(toy_detector.generate_event(3000, 5, eta_max=1.0))
+    finder = seedfinder_config(cotThetaMax=7.0)      # 7 z bins
+    _check_event(toy_detector.generate_event(1500, 23), finder=finder, grid=spacepoint_grid_config(finder))
+    finder = seedfinder_config(zMin=-400.0, zMax=900.0, rMax=150.0)   # spacepoints outside the grid
+    _check_event(toy_detector.generate_event(1200, 37), finder=finder, grid=spacepoint_grid_config(finder))
+    got, _ = _check_event(toy_detector.generate_event(10000, 31), dump=False)
+    assert got["counters"]["overflow"] == 0
+
+
 def test_parity_pooled_triplet_kernel(monkeypatch):
     """k_triplets_pool (eight light middles per warp, one pair queue and one triplet list for all of
     them; B200SEED_TRIPLETS=pool, off by default — DESIGN.md §5) against the oracle: triplet sets

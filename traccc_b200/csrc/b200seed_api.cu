@@ -44,7 +44,7 @@ inline size_t align_up(size_t v, size_t a) {
 struct Layout {
     size_t control, cell_cnt, bin_of, blk_hist, bin_off, cell_off, sorted_index, sorted_bin, sp4,
         var2, csp4, ccanon, cnt, off, seed_cnt, seed_b, seed_t, seed_w, arena_b, arena_t,
-        dump, gather_state, spill_list, active_list, group_list, fallback_list, slow_list, total;
+        dump, gather_state, spill_list, active_list, group_list, fallback_list, slow_list, seg_info, mid_order, total;
     size_t zero_bytes;  // control block, cell populations, look-back state: cleared per event
     uint32_t nblk;
     uint64_t max_doublets, max_dump;
@@ -74,6 +74,10 @@ struct b200seed_handle {
     // 0 = k_doublets_tile (groups of middles, cp.async.bulk staging), 1 = the same with 16-byte
     // cp.async (B200SEED_DOUBLETS=warp|tile|ldgsts, read at b200seed_create)
     int doublet_mode = 2;
+    // k_doublets<0> draws its tickets in cost order (longest middles first: k_cell_scan's classes)
+    // instead of grid order: 1 = for events of at least 16k spacepoints (default), 0 / 2 = never /
+    // always (B200SEED_DOUBLET_ORDER=grid / cost, for A/B runs and the tests)
+    int ordered_tickets = 1;
     // triplet search of the light middles: 0 = k_triplets for all (default: faster),
     // 1 = k_triplets_pool (several middles per warp); B200SEED_TRIPLETS=warp|pool
     int triplet_pool = 0;
@@ -215,6 +219,8 @@ Layout make_layout(const b200seed_handle* h, uint32_t max_sp) {
     L.off = take(2 * n * 4);
     L.spill_list = take(n * 4);
     L.active_list = take(n * 4 * WORK_CLASSES);
+    L.mid_order = take(n * 4);
+    L.seg_info = take(size_t(h->nbins) * L.g.NR * 4);
     L.group_list = take(n * 4);
     L.fallback_list = take(n * 4);
     L.seed_cnt = take(n * 4);
@@ -548,6 +554,8 @@ int b200seed_create(const b200seed_finder_cfg* finder, const b200seed_grid_cfg* 
                          h->smem_optin - 1024);
     cudaFuncSetAttribute(k_doublets_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          h->smem_optin - 1024);
+    if (const char* m = std::getenv("B200SEED_DOUBLET_ORDER"))
+        h->ordered_tickets = !std::strcmp(m, "grid") ? 0 : (!std::strcmp(m, "cost") ? 2 : 1);
     if (const char* m = std::getenv("B200SEED_DOUBLETS")) {
         if (!std::strcmp(m, "tile")) h->doublet_mode = 0;
         else if (!std::strcmp(m, "ldgsts")) h->doublet_mode = 1;
@@ -768,6 +776,14 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
     uint32_t* cell_off = reinterpret_cast<uint32_t*>(at(L.cell_off));
     float4* csp4 = reinterpret_cast<float4*>(at(L.csp4));
     uint32_t* ccanon = reinterpret_cast<uint32_t*>(at(L.ccanon));
+    // ticket order of k_doublets<0> (cost classes per (bin, r row); B200SEED_DOUBLET_ORDER=grid: off)
+    // (from 16k spacepoints on: below that the launch is too short for its end to matter and the
+    // classification costs k_cell_scan / k_bin_scatter more than it saves; =cost forces it)
+    const bool ordered = h->ordered_tickets == 2 || (h->ordered_tickets == 1 && n_sp >= 16384u);
+    uint32_t* seg_info = ordered ? reinterpret_cast<uint32_t*>(at(L.seg_info)) : nullptr;
+    uint32_t* mid_order = ordered ? reinterpret_cast<uint32_t*>(at(L.mid_order)) : nullptr;
+    uint32_t row_reach = uint32_t(h->finder.deltaRMax * L.g.invRw) + 1u;  // rows a partner can be away
+    if (!(h->finder.deltaRMax >= 0.f) || row_reach > 31u) row_reach = 31u;
     // canon_key (seed_kernels.cuh) is a 32-bit word
     if (uint64_t(h->dev.scope0 + h->dev.scope1 + 1u) * n_sp > 0xFFFFFFFFull)
         return fail(h, B200SEED_EINVAL, "b200seed_run: too many spacepoints for this neighbor_scope");
@@ -797,13 +813,13 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
         k_cell_scan<<<h->nbins, 256, h->doublet_mode == 2 ? 0 : (L.g.CPB + 1) * sizeof(uint32_t), s>>>(
             cell_cnt, cell_off, bin_off, L.g.CPB, h->nbins,
             h->doublet_mode == 2 ? nullptr : reinterpret_cast<uint32_t*>(at(L.group_list)), ctrl,
-            L.g.NZc, gmax, zspan, gmax >= 4u ? gmax / 2u : 2u, n_sp);
+            L.g.NZc, gmax, zspan, gmax >= 4u ? gmax / 2u : 2u, n_sp, seg_info, row_reach);
     }
     {
         KernelTimer t(h, s, "bin_scatter");
         k_bin_scatter<<<nblk, BIN_THREADS, h->nbins * sizeof(uint32_t), s>>>(
             h->dev, L.g, n_sp, d_xyz, d_var_z, d_var_r, bin_of, blk_hist, nblk, sp4, var2, sorted_index,
-            sorted_bin, cell_off, cell_cnt, csp4, ccanon, d_n_sp, ctrl, h->nbins);
+            sorted_bin, cell_off, cell_cnt, csp4, ccanon, d_n_sp, ctrl, h->nbins, seg_info, mid_order);
     }
     {
         DoubletArgs a{};
@@ -841,6 +857,7 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
         a.seed_cnt = seed_cnt;
         a.n_sp = n_sp;
         a.fallback_list = reinterpret_cast<const uint32_t*>(at(L.fallback_list));
+        a.mid_order = mid_order;
         const uint32_t grid_s = grid < uint32_t(h->num_sms) * 4u ? grid : uint32_t(h->num_sms) * 4u;
         if (h->doublet_mode == 2) {
             k_doublets<0><<<grid, WARPS_PER_CTA * 32, smem, s>>>(h->dev, a);
@@ -1604,8 +1621,9 @@ void b200seed_host_probe_triplet_prefilter(const void* devcfg, uint32_t n, const
 
 }  // extern "C"
 
+
 #ifdef B200_TAIL_PROBE
-// debug build only (tools/tail_probe.py)
+// debug build only (tools/tail_probe.py, tools/middle_cost.py)
 extern "C" int b200seed_debug_tail_probe(unsigned long long* out, int reset) {
     if (out) cudaMemcpyFromSymbol(out, b200seed::g_tail_probe, sizeof(b200seed::g_tail_probe));
     if (reset) {
@@ -1614,5 +1632,8 @@ extern "C" int b200seed_debug_tail_probe(unsigned long long* out, int reset) {
         cudaMemset(p, 0, sizeof(b200seed::g_tail_probe));
     }
     return 0;
+}
+extern "C" int b200seed_debug_middle_cycles(uint32_t* out, uint32_t n) {
+    return int(cudaMemcpyFromSymbol(out, b200seed::g_middle_cycles, size_t(n) * 4));
 }
 #endif

@@ -48,10 +48,12 @@ constexpr int SCAN_ITEMS = 4;
 #endif
 constexpr int WARPS_PER_CTA = B200_WARPS_PER_CTA;
 #ifdef B200_TAIL_PROBE
-// Debug build only (tools/tail_probe.py): time (globaltimer, ns) at which every warp of the two
-// search kernels drew its first ticket and ran out of tickets, and for k_triplets the start and
-// the sizes of its last middle; read back by b200seed_debug_tail_probe.
+// Debug build only (tools/tail_probe.py, tools/middle_cost.py): time (globaltimer, ns) at which
+// every warp of the two search kernels drew its first ticket and ran out of tickets, for
+// k_triplets the start and the sizes of its last middle, and the SM cycles k_doublets spent on
+// every middle; read back by b200seed_debug_tail_probe / b200seed_debug_middle_cycles.
 __device__ unsigned long long g_tail_probe[2][4][16384];
+__device__ uint32_t g_middle_cycles[1 << 19];
 __device__ __forceinline__ unsigned long long probe_now() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -122,16 +124,17 @@ struct Control {
     uint32_t slow_done;       // set by k_seed_gather's tile 0 when they are finished
     uint32_t pad3_;
     uint32_t n_cls[WORK_CLASSES];  // entries in each class of the work list
+    uint32_t n_dcls[WORK_CLASSES];  // ... of k_doublets' own ticket order (mid_order)
 };
 
 // Start of every class in ticket order (s_pre[WORK_CLASSES] = all): once per CTA, before a
 // __syncthreads().
-__device__ __forceinline__ void work_prefix(const Control* ctrl, uint32_t* s_pre) {
+__device__ __forceinline__ void work_prefix(const uint32_t* n_cls, uint32_t* s_pre) {
     if (threadIdx.x == 0) {
         uint32_t acc = 0;
         for (uint32_t c = 0; c < WORK_CLASSES; ++c) {
             s_pre[c] = acc;
-            acc += ctrl->n_cls[c];
+            acc += n_cls[c];
         }
         s_pre[WORK_CLASSES] = acc;
     }
@@ -396,13 +399,17 @@ k_bin_scatter(const DevCfg cfg, const CellGrid g, const uint32_t n_sp_max,
               uint32_t* __restrict__ sorted_index, uint32_t* __restrict__ sorted_bin,
               const uint32_t* __restrict__ cell_off, uint32_t* __restrict__ cell_cur,
               float4* __restrict__ csp4, uint32_t* __restrict__ ccanon,
-              const uint32_t* __restrict__ n_sp_dev, Control* __restrict__ ctrl, const uint32_t nbins) {
+              const uint32_t* __restrict__ n_sp_dev, Control* __restrict__ ctrl, const uint32_t nbins,
+              const uint32_t* __restrict__ seg_info, uint32_t* __restrict__ mid_order) {
     // rank among the earlier spacepoints of this block that fall into the same bin: ascending
     // original index inside every bin, like the CPU's push_back loop
     // (core/src/seeding/spacepoint_binning.cpp:40-50). Inside a warp: __match_any_sync + popc of
     // the lower lanes; across the warps of the block: a shared-memory histogram (dynamic, nbins
     // words) that the warps update one after the other, in order.
     extern __shared__ uint32_t s_hist[];
+    __shared__ uint32_t s_dpre[WORK_CLASSES];  // start of every cost class in mid_order
+    // (loaded now, summed after the ranking loop: the round trip overlaps it)
+    const uint32_t dcl = (seg_info && threadIdx.x < WORK_CLASSES) ? ctrl->n_dcls[threadIdx.x] : 0u;
     const uint32_t n_sp = dev_count(n_sp_max, n_sp_dev);
     const uint32_t i = blockIdx.x * BIN_THREADS + threadIdx.x;
     const uint32_t bin = (i < n_sp) ? bin_of[i] : INVALID_BIN;
@@ -421,6 +428,18 @@ k_bin_scatter(const DevCfg cfg, const CellGrid g, const uint32_t n_sp_max,
         __syncthreads();
     }
     before = __shfl_sync(0xffffffffu, before, leader);
+    if (seg_info) {
+        if (warp_ == 0) {
+            uint32_t incl = dcl;
+#pragma unroll
+            for (int o = 1; o < int(WORK_CLASSES); o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane_ >= uint32_t(o)) incl += t;
+            }
+            if (lane_ < WORK_CLASSES) s_dpre[lane_] = incl - dcl;
+        }
+        __syncthreads();
+    }
     if (bin == INVALID_BIN) return;
     const uint32_t rank = before + in_warp;
     const uint32_t pos = blk_scan[size_t(bin) * nblk + blockIdx.x] + rank;
@@ -439,9 +458,17 @@ k_bin_scatter(const DevCfg cfg, const CellGrid g, const uint32_t n_sp_max,
     sorted_bin[pos] = bin;
     // cell-sorted copy (order inside a cell is arbitrary: nothing downstream depends on it)
     const uint32_t cell = sp_cell(cfg, g, bin, r, z);
+    // ticket order of k_doublets: the segment of this (bin, r row) inside its cost class (k_cell_scan)
+    uint32_t info = 0, row_start = 0;
+    if (seg_info) {
+        const uint32_t row = cell_row(g, r);
+        info = __ldg(seg_info + bin * g.NR + row);
+        row_start = __ldg(cell_off + size_t(bin) * g.CPB + row * g.NZc);
+    }
     const uint32_t cpos = cell_off[cell] + atomicAdd(&cell_cur[cell], 1u);
     csp4[cpos] = P;
     ccanon[cpos] = pos;
+    if (seg_info) mid_order[s_dpre[info >> 28] + (info & 0x0FFFFFFFu) + (cpos - row_start)] = pos;
 }
 
 // CTA per reference bin: cell_off[bin * CPB + c] = bin_off[bin] + exclusive scan of the
@@ -456,7 +483,8 @@ __global__ void __launch_bounds__(256)
 k_cell_scan(uint32_t* __restrict__ cell_cnt, uint32_t* __restrict__ cell_off,
             const uint32_t* __restrict__ bin_off, const uint32_t CPB, const uint32_t nbins,
             uint32_t* __restrict__ group_list, Control* __restrict__ ctrl, const uint32_t NZc,
-            const uint32_t gmax, const uint32_t zspan, const uint32_t big, const uint32_t n_sp) {
+            const uint32_t gmax, const uint32_t zspan, const uint32_t big, const uint32_t n_sp,
+            uint32_t* __restrict__ seg_info, const uint32_t row_reach) {
     __shared__ uint32_t s_warp[8];
     __shared__ uint32_t s_total;
     const uint32_t bin = blockIdx.x;
@@ -504,6 +532,40 @@ k_cell_scan(uint32_t* __restrict__ cell_cnt, uint32_t* __restrict__ cell_off,
         __syncthreads();
     }
     if (bin == nbins - 1 && threadIdx.x == 0) cell_off[size_t(nbins) * CPB] = carry;
+    if (seg_info) {
+        // Ticket order of k_doublets: the spacepoints of one (bin, r row) form a segment of the
+        // cell order and share a cost class, estimated from what can be known here — the
+        // populations of the rows below and above within deltaRMax (own row left out: it holds
+        // partners of both kinds). A middle with an empty side cannot seed and costs one scan;
+        // the more partners on the scarcer side, the more doublets, lin_circles and sorting.
+        // Longest first, so that the launch ends on its shortest jobs (see work_class).
+        __syncthreads();  // the offsets of this bin, written above by other threads of the CTA
+        if (warp == 0) {
+            const uint32_t NR = CPB / NZc;
+            const uint32_t b0 = __ldg(bin_off + bin);
+            const uint32_t start = (lane < NR) ? cell_off[size_t(bin) * CPB + lane * NZc] : carry;
+            const uint32_t next = __shfl_down_sync(0xffffffffu, start, 1);
+            const uint32_t end = (lane + 1u < NR) ? next : carry;
+            const uint32_t pop = (lane < NR) ? end - start : 0u;
+            uint32_t below = 0, above = 0;
+            for (uint32_t d = 1; d <= row_reach; ++d) {
+                const uint32_t lo = __shfl_sync(0xffffffffu, pop, (lane - d) & 31u);
+                const uint32_t hi = __shfl_sync(0xffffffffu, pop, (lane + d) & 31u);
+                if (lane >= d) below += lo;
+                if (lane + d < NR) above += hi;
+            }
+            if (lane < NR && pop != 0u) {
+                const uint32_t nb = carry - b0;  // population of the bin
+                const uint32_t sc = below < above ? below : above;
+                uint32_t c;
+                if (sc == 0u) c = ((below + above) * 4u >= nb) ? 6u : 7u;
+                else c = (sc * 8u >= nb) ? 0u : (sc * 16u >= nb) ? 1u : (sc * 32u >= nb) ? 2u
+                       : (sc * 64u >= nb) ? 3u : (sc * 256u >= nb) ? 4u : 5u;
+                const uint32_t base = atomicAdd(&ctrl->n_dcls[c], pop);
+                seg_info[bin * NR + lane] = (c << 28) | base;
+            }
+        }
+    }
     if (!group_list) return;
     // the offsets of this bin in shared memory (dynamic, CPB + 1 words)
     extern __shared__ uint32_t s_off[];
@@ -585,6 +647,7 @@ struct DoubletArgs {
     uint32_t* seed_cnt;           // [n_sp] set to 0 here for the middles without work
     uint32_t n_sp;
     const uint32_t* fallback_list;  // [n_sp] middles handed back by k_doublets_tile (MODE 2)
+    const uint32_t* mid_order;      // [n_sp] ticket order of MODE 0 (null: grid order)
 };
 
 __device__ __forceinline__ uint32_t lanemask_lt() {
@@ -733,10 +796,12 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
                 if (m >= n_work) g_tail_probe[0][1][w] = probe_now();
             }
         }
+        const long long probe_c0 = clock64();
 #endif
         if (m >= n_work) break;
         if (SPILL) m = a.spill_list[m];
         if (LISTED) m = a.fallback_list[m];
+        if (MODE == 0 && a.mid_order) m = __ldg(a.mid_order + m);  // longest middles first
 #ifdef B200_CELL_ORDER_TICKETS
         // tickets in CELL order: the warps of a CTA then work on middles of the same
         // (bin, r row, z cell) neighbourhood at the same time and share their candidate cells in L1
@@ -1060,6 +1125,9 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
             else
                 work_push(a.active_list, a.n_sp, a.ctrl, m, nB, nT);
         }
+#ifdef B200_TAIL_PROBE
+        if (MODE == 0 && lane == 0 && m < (1u << 19)) g_middle_cycles[m] = uint32_t(clock64() - probe_c0);
+#endif
         if (nB) {
             ++acc_active;
             acc_nb += nB;
@@ -1507,7 +1575,7 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
         s_ntrip = 0;
         s_tests = s_visited = 0ull;
     }
-    work_prefix(a.ctrl, s_pre);
+    work_prefix(a.ctrl->n_cls, s_pre);
     __syncthreads();
     const uint32_t n_valid = a.ctrl->n_valid;
     const uint32_t K = cfg.maxSeedsPerSpM;

@@ -78,7 +78,7 @@ k_triplets_pool(const DevCfg cfg, const TripletArgs a) {
         s_ntrip = 0;
         s_tests = 0ull;
     }
-    work_prefix(a.ctrl, s_pre);
+    work_prefix(a.ctrl->n_cls, s_pre);
     __syncthreads();
     const uint32_t n_valid = a.ctrl->n_valid;
     const bool has_var = a.ctrl->has_variance != 0u;
