@@ -42,7 +42,7 @@ inline size_t align_up(size_t v, size_t a) {
 }
 
 struct Layout {
-    size_t control, cell_cnt, bin_of, blk_hist, bin_off, cell_off, sorted_index, sorted_bin, sp4,
+    size_t control, cell_cnt, bin_tot, bin_of, blk_hist, bin_off, cell_off, sorted_index, sorted_bin, sp4,
         var2, csp4, ccanon, cnt, off, seed_cnt, seed_b, seed_t, seed_w, arena_b, arena_t,
         dump, gather_state, spill_list, active_list, group_list, fallback_list, slow_list, seg_info, mid_order, total;
     size_t zero_bytes;  // control block, cell populations, look-back state: cleared per event
@@ -202,6 +202,7 @@ Layout make_layout(const b200seed_handle* h, uint32_t max_sp) {
     };
     L.control = take(sizeof(Control));
     L.cell_cnt = take(ncells * 4);
+    L.bin_tot = take(size_t(h->nbins) * 4);
     // look-back status words of k_seed_gather (one per 256 middles) + its ticket counter
     L.gather_state = take((size_t(L.nblk) + 1) * sizeof(unsigned long long));
     L.zero_bytes = o;
@@ -716,11 +717,11 @@ int b200seed_get_timings(b200seed_handle* h, const char** names, float* ms, int 
 }
 
 int b200seed_launches_per_event(const b200seed_handle* h, int with_params) {
-    // k_bin_count, k_scan, k_cell_scan, k_bin_scatter, k_doublets<0>, k_doublets<1>, k_triplets,
+    // k_bin_count, k_cell_scan, k_bin_scatter, k_doublets<0>, k_doublets<1>, k_triplets,
     // k_seed_gather; the group kernel adds one launch (k_doublets_tile + k_doublets<2>)
     const int doublets = (h && h->doublet_mode != 2) ? 3 : 2;
     const int triplets = (h && h->triplet_pool) ? 2 : 1;
-    return 5 + doublets + triplets + (with_params ? 1 : 0);
+    return 4 + doublets + triplets + (with_params ? 1 : 0);
 }
 
 }  // extern "C"
@@ -758,6 +759,7 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
     Control* ctrl = reinterpret_cast<Control*>(at(L.control));
     uint32_t* bin_of = reinterpret_cast<uint32_t*>(at(L.bin_of));
     uint32_t* blk_hist = reinterpret_cast<uint32_t*>(at(L.blk_hist));
+    uint32_t* bin_tot = reinterpret_cast<uint32_t*>(at(L.bin_tot));
     uint32_t* bin_off = reinterpret_cast<uint32_t*>(at(L.bin_off));
     uint32_t* sorted_index = reinterpret_cast<uint32_t*>(at(L.sorted_index));
     uint32_t* sorted_bin = reinterpret_cast<uint32_t*>(at(L.sorted_bin));
@@ -794,12 +796,7 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
     {
         KernelTimer t(h, s, "bin_count");
         k_bin_count<<<nblk, BIN_THREADS, h->nbins * sizeof(uint32_t), s>>>(
-            h->dev, L.g, n_sp, d_xyz, bin_of, blk_hist, cell_cnt, h->nbins, nblk, d_n_sp);
-    }
-    {
-        KernelTimer t(h, s, "scan_bins");
-        k_scan<<<1, SCAN_THREADS, 0, s>>>(blk_hist, blk_hist, h->nbins * nblk, nullptr, &ctrl->n_valid,
-                                          bin_off, h->nbins, nblk);
+            h->dev, L.g, n_sp, d_xyz, bin_of, blk_hist, cell_cnt, h->nbins, nblk, d_n_sp, bin_tot);
     }
     {
         KernelTimer t(h, s, "cell_scan");
@@ -811,7 +808,7 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
         uint32_t zspan = uint32_t(zspan_mm * L.g.invZw + 0.5f);
         if (zspan < 1u) zspan = 1u;
         k_cell_scan<<<h->nbins, 256, h->doublet_mode == 2 ? 0 : (L.g.CPB + 1) * sizeof(uint32_t), s>>>(
-            cell_cnt, cell_off, bin_off, L.g.CPB, h->nbins,
+            cell_cnt, cell_off, bin_off, bin_tot, blk_hist, nblk, L.g.CPB, h->nbins,
             h->doublet_mode == 2 ? nullptr : reinterpret_cast<uint32_t*>(at(L.group_list)), ctrl,
             L.g.NZc, gmax, zspan, gmax >= 4u ? gmax / 2u : 2u, n_sp, seg_info, row_reach);
     }

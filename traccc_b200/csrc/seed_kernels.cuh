@@ -303,7 +303,7 @@ k_bin_count(const DevCfg cfg, const CellGrid g, const uint32_t n_sp_max,
             const float* __restrict__ xyz,
             uint32_t* __restrict__ bin_of, uint32_t* __restrict__ blk_hist,
             uint32_t* __restrict__ cell_cnt, const uint32_t nbins, const uint32_t nblk,
-            const uint32_t* __restrict__ n_sp_dev) {
+            const uint32_t* __restrict__ n_sp_dev, uint32_t* __restrict__ bin_tot) {
     extern __shared__ uint32_t s_hist[];
     for (uint32_t b = threadIdx.x; b < nbins; b += BIN_THREADS) s_hist[b] = 0;
     __syncthreads();
@@ -321,8 +321,11 @@ k_bin_count(const DevCfg cfg, const CellGrid g, const uint32_t n_sp_max,
         }
     }
     __syncthreads();
-    for (uint32_t b = threadIdx.x; b < nbins; b += BIN_THREADS)
-        blk_hist[size_t(b) * nblk + blockIdx.x] = s_hist[b];
+    for (uint32_t b = threadIdx.x; b < nbins; b += BIN_THREADS) {
+        const uint32_t c = s_hist[b];
+        blk_hist[size_t(b) * nblk + blockIdx.x] = c;
+        if (c) atomicAdd(&bin_tot[b], c);  // population of the bin (k_cell_scan sums them into bin_off)
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -481,7 +484,8 @@ k_bin_scatter(const DevCfg cfg, const CellGrid g, const uint32_t n_sp_max,
 // others from the back of group_list[n_sp].
 __global__ void __launch_bounds__(256)
 k_cell_scan(uint32_t* __restrict__ cell_cnt, uint32_t* __restrict__ cell_off,
-            const uint32_t* __restrict__ bin_off, const uint32_t CPB, const uint32_t nbins,
+            uint32_t* __restrict__ bin_off, const uint32_t* __restrict__ bin_tot,
+            uint32_t* __restrict__ blk_hist, const uint32_t nblk, const uint32_t CPB, const uint32_t nbins,
             uint32_t* __restrict__ group_list, Control* __restrict__ ctrl, const uint32_t NZc,
             const uint32_t gmax, const uint32_t zspan, const uint32_t big, const uint32_t n_sp,
             uint32_t* __restrict__ seg_info, const uint32_t row_reach) {
@@ -489,48 +493,78 @@ k_cell_scan(uint32_t* __restrict__ cell_cnt, uint32_t* __restrict__ cell_off,
     __shared__ uint32_t s_total;
     const uint32_t bin = blockIdx.x;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t carry = __ldg(bin_off + bin);
-    for (uint32_t base = 0; base < CPB; base += 256 * 4) {
-        const uint32_t idx = base + threadIdx.x * 4;
-        uint32_t v[4];
-        uint32_t sum = 0;
+    // exclusive scan of len words at p (in place) continuing from `from`; returns the end value
+    auto scan_in_place = [&](uint32_t* p, const uint32_t len, const uint32_t from, uint32_t* copy_to,
+                             const bool zero_src) -> uint32_t {
+        uint32_t run0 = from;
+        for (uint32_t base = 0; base < len; base += 256 * 4) {
+            const uint32_t idx = base + threadIdx.x * 4;
+            uint32_t v[4];
+            uint32_t sum = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            v[k] = (idx + k < CPB) ? cell_cnt[size_t(bin) * CPB + idx + k] : 0u;
-            sum += v[k];
-        }
-        uint32_t incl = sum;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
-            if (lane >= uint32_t(off)) incl += t;
-        }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            const uint32_t ws = (lane < 8) ? s_warp[lane] : 0u;
-            uint32_t wincl = ws;
-#pragma unroll
-            for (int off = 1; off < 8; off <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, wincl, off);
-                if (lane >= uint32_t(off)) wincl += t;
+            for (int k = 0; k < 4; ++k) {
+                v[k] = (idx + k < len) ? p[idx + k] : 0u;
+                sum += v[k];
             }
-            if (lane < 8) s_warp[lane] = wincl - ws;
-            if (lane == 7) s_total = wincl;
-        }
-        __syncthreads();
-        uint32_t run = carry + s_warp[warp] + incl - sum;
+            uint32_t incl = sum;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (idx + k < CPB) {
-                cell_off[size_t(bin) * CPB + idx + k] = run;
-                cell_cnt[size_t(bin) * CPB + idx + k] = 0u;
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= uint32_t(off)) incl += t;
             }
-            run += v[k];
+            if (lane == 31) s_warp[warp] = incl;
+            __syncthreads();
+            if (warp == 0) {
+                const uint32_t ws = (lane < 8) ? s_warp[lane] : 0u;
+                uint32_t wincl = ws;
+#pragma unroll
+                for (int off = 1; off < 8; off <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, wincl, off);
+                    if (lane >= uint32_t(off)) wincl += t;
+                }
+                if (lane < 8) s_warp[lane] = wincl - ws;
+                if (lane == 7) s_total = wincl;
+            }
+            __syncthreads();
+            uint32_t run = run0 + s_warp[warp] + incl - sum;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (idx + k < len) {
+                    (copy_to ? copy_to : p)[idx + k] = run;
+                    if (zero_src) p[idx + k] = 0u;
+                }
+                run += v[k];
+            }
+            run0 += s_total;
+            __syncthreads();
         }
-        carry += s_total;
-        __syncthreads();
+        return run0;
+    };
+    // Start of this bin in the grid order = populations of the bins before it (k_bin_count's
+    // totals; this used to be a single-CTA scan kernel of its own between the two).
+    uint32_t part = 0;
+    for (uint32_t b = threadIdx.x; b < bin; b += 256) part += __ldg(bin_tot + b);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) s_warp[warp] = part;
+    __syncthreads();
+    uint32_t bin_base = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) bin_base += s_warp[w];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        bin_off[bin] = bin_base;
+        if (bin == nbins - 1) {
+            const uint32_t n_valid = bin_base + __ldg(bin_tot + bin);
+            bin_off[nbins] = n_valid;
+            ctrl->n_valid = n_valid;
+        }
     }
+    // position of the first spacepoint every block of k_bin_count / k_bin_scatter has in this bin
+    scan_in_place(blk_hist + size_t(bin) * nblk, nblk, bin_base, nullptr, false);
+    // cell offsets of this bin; the populations are zeroed again (k_bin_scatter's cursors)
+    const uint32_t carry = scan_in_place(cell_cnt + size_t(bin) * CPB, CPB, bin_base,
+                                         cell_off + size_t(bin) * CPB, true);
     if (bin == nbins - 1 && threadIdx.x == 0) cell_off[size_t(nbins) * CPB] = carry;
     if (seg_info) {
         // Ticket order of k_doublets: the spacepoints of one (bin, r row) form a segment of the
