@@ -78,6 +78,9 @@ struct b200seed_handle {
     // instead of grid order: 1 = for events of at least 16k spacepoints (default), 0 / 2 = never /
     // always (B200SEED_DOUBLET_ORDER=grid / cost, for A/B runs and the tests)
     int ordered_tickets = 1;
+    // ... and the classes with a scarce side in a launch of their own (B200SEED_DOUBLET_SIDES=0: off)
+    int split_sides = 1;
+    int pdl = 1;  // ... overlapping the end of k_doublets<0> (B200SEED_PDL=0: plain stream order)
     // triplet search of the light middles: 0 = k_triplets for all (default: faster),
     // 1 = k_triplets_pool (several middles per warp); B200SEED_TRIPLETS=warp|pool
     int triplet_pool = 0;
@@ -551,10 +554,14 @@ int b200seed_create(const b200seed_finder_cfg* finder, const b200seed_grid_cfg* 
                          h->smem_optin - 1024);
     cudaFuncSetAttribute(k_doublets<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          h->smem_optin - 1024);
+    cudaFuncSetAttribute(k_doublets<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         h->smem_optin - 1024);
     cudaFuncSetAttribute(k_doublets_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          h->smem_optin - 1024);
     cudaFuncSetAttribute(k_doublets_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          h->smem_optin - 1024);
+    if (const char* m = std::getenv("B200SEED_DOUBLET_SIDES")) h->split_sides = std::strcmp(m, "0") != 0;
+    if (const char* m = std::getenv("B200SEED_PDL")) h->pdl = std::strcmp(m, "0") != 0;
     if (const char* m = std::getenv("B200SEED_DOUBLET_ORDER"))
         h->ordered_tickets = !std::strcmp(m, "grid") ? 0 : (!std::strcmp(m, "cost") ? 2 : 1);
     if (const char* m = std::getenv("B200SEED_DOUBLETS")) {
@@ -719,7 +726,9 @@ int b200seed_get_timings(b200seed_handle* h, const char** names, float* ms, int 
 int b200seed_launches_per_event(const b200seed_handle* h, int with_params) {
     // k_bin_count, k_cell_scan, k_bin_scatter, k_doublets<0>, k_doublets<1>, k_triplets,
     // k_seed_gather; the group kernel adds one launch (k_doublets_tile + k_doublets<2>)
-    const int doublets = (h && h->doublet_mode != 2) ? 3 : 2;
+    // (events of at least 16k spacepoints: + k_doublets<3> for the middles with a scarce side)
+    const bool sides = h && h->doublet_mode == 2 && h->ordered_tickets && h->split_sides && h->finder.deltaRMin >= 0.f;
+    const int doublets = (h && h->doublet_mode != 2) ? 3 : (sides ? 3 : 2);
     const int triplets = (h && h->triplet_pool) ? 2 : 1;
     return 4 + doublets + triplets + (with_params ? 1 : 0);
 }
@@ -784,6 +793,9 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
     const bool ordered = h->ordered_tickets == 2 || (h->ordered_tickets == 1 && n_sp >= 16384u);
     uint32_t* seg_info = ordered ? reinterpret_cast<uint32_t*>(at(L.seg_info)) : nullptr;
     uint32_t* mid_order = ordered ? reinterpret_cast<uint32_t*>(at(L.mid_order)) : nullptr;
+    // the classes with an (almost) empty side get their own launch, which looks at that side first
+    // (k_doublets<3>; needs deltaRMin >= 0: bottoms below, tops above the middle's row)
+    const bool split_sides = ordered && h->split_sides && h->finder.deltaRMin >= 0.f && h->doublet_mode == 2;
     uint32_t row_reach = uint32_t(h->finder.deltaRMax * L.g.invRw) + 1u;  // rows a partner can be away
     if (!(h->finder.deltaRMax >= 0.f) || row_reach > 31u) row_reach = 31u;
     // canon_key (seed_kernels.cuh) is a 32-bit word
@@ -810,7 +822,7 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
         k_cell_scan<<<h->nbins, 256, h->doublet_mode == 2 ? 0 : (L.g.CPB + 1) * sizeof(uint32_t), s>>>(
             cell_cnt, cell_off, bin_off, bin_tot, blk_hist, nblk, L.g.CPB, h->nbins,
             h->doublet_mode == 2 ? nullptr : reinterpret_cast<uint32_t*>(at(L.group_list)), ctrl,
-            L.g.NZc, gmax, zspan, gmax >= 4u ? gmax / 2u : 2u, n_sp, seg_info, row_reach);
+            L.g.NZc, gmax, zspan, gmax >= 4u ? gmax / 2u : 2u, n_sp, seg_info, row_reach, split_sides);
     }
     {
         KernelTimer t(h, s, "bin_scatter");
@@ -855,9 +867,25 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
         a.n_sp = n_sp;
         a.fallback_list = reinterpret_cast<const uint32_t*>(at(L.fallback_list));
         a.mid_order = mid_order;
+        a.split_sides = split_sides ? 1u : 0u;
         const uint32_t grid_s = grid < uint32_t(h->num_sms) * 4u ? grid : uint32_t(h->num_sms) * 4u;
         if (h->doublet_mode == 2) {
             k_doublets<0><<<grid, WARPS_PER_CTA * 32, smem, s>>>(h->dev, a);
+            if (split_sides) {
+                // no data dependence on k_doublets<0> (disjoint middles, shared atomics only): its
+                // CTAs start as soon as that launch frees slots, i.e. they fill its tail
+                cudaLaunchConfig_t lc{};
+                lc.gridDim = dim3(grid_s);
+                lc.blockDim = dim3(WARPS_PER_CTA * 32);
+                lc.dynamicSmemBytes = smem;
+                lc.stream = s;
+                cudaLaunchAttribute at1{};
+                at1.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at1.val.programmaticStreamSerializationAllowed = h->pdl ? 1 : 0;
+                lc.attrs = &at1;
+                lc.numAttrs = 1;
+                CUDA_TRY(h, cudaLaunchKernelEx(&lc, k_doublets<3>, h->dev, a));
+            }
         } else {
             TileArgs ta{};
             ta.bin_off = bin_off;

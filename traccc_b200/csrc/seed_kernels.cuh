@@ -90,6 +90,9 @@ __host__ __device__ inline uint32_t work_class(uint32_t nB, uint32_t nT) {
     return 4u + (nB < 32u ? 1u : 0u) + (nB < 16u ? 1u : 0u) + (nB < 8u ? 1u : 0u);
 }
 
+// Flag in the entries of mid_order for the classes with a scarce side: it is the lower one.
+constexpr uint32_t MID_LOWER_SCARCE = 0x80000000u;
+
 // Small control block at the start of the workspace, zeroed at the start of each event.
 struct Control {
     uint32_t cursor[2];       // doublet arena bump pointers (bottom / top)
@@ -125,6 +128,9 @@ struct Control {
     uint32_t pad3_;
     uint32_t n_cls[WORK_CLASSES];  // entries in each class of the work list
     uint32_t n_dcls[WORK_CLASSES];  // ... of k_doublets' own ticket order (mid_order)
+    uint32_t ticket_e;        // work queue of k_doublets<3> (middles with a scarce side)
+    uint32_t n_main;          // tickets of k_doublets<0>: n_valid minus those of k_doublets<3>
+    uint32_t pad4_[2];
 };
 
 // Start of every class in ticket order (s_pre[WORK_CLASSES] = all): once per CTA, before a
@@ -471,7 +477,9 @@ k_bin_scatter(const DevCfg cfg, const CellGrid g, const uint32_t n_sp_max,
     const uint32_t cpos = cell_off[cell] + atomicAdd(&cell_cur[cell], 1u);
     csp4[cpos] = P;
     ccanon[cpos] = pos;
-    if (seg_info) mid_order[s_dpre[info >> 28] + (info & 0x0FFFFFFFu) + (cpos - row_start)] = pos;
+    if (seg_info)
+        mid_order[s_dpre[info >> 28] + (info & 0x07FFFFFFu) + (cpos - row_start)] =
+            pos | ((info & (1u << 27)) ? MID_LOWER_SCARCE : 0u);
 }
 
 // CTA per reference bin: cell_off[bin * CPB + c] = bin_off[bin] + exclusive scan of the
@@ -488,7 +496,7 @@ k_cell_scan(uint32_t* __restrict__ cell_cnt, uint32_t* __restrict__ cell_off,
             uint32_t* __restrict__ blk_hist, const uint32_t nblk, const uint32_t CPB, const uint32_t nbins,
             uint32_t* __restrict__ group_list, Control* __restrict__ ctrl, const uint32_t NZc,
             const uint32_t gmax, const uint32_t zspan, const uint32_t big, const uint32_t n_sp,
-            uint32_t* __restrict__ seg_info, const uint32_t row_reach) {
+            uint32_t* __restrict__ seg_info, const uint32_t row_reach, const bool sided) {
     __shared__ uint32_t s_warp[8];
     __shared__ uint32_t s_total;
     const uint32_t bin = blockIdx.x;
@@ -558,6 +566,7 @@ k_cell_scan(uint32_t* __restrict__ cell_cnt, uint32_t* __restrict__ cell_off,
             const uint32_t n_valid = bin_base + __ldg(bin_tot + bin);
             bin_off[nbins] = n_valid;
             ctrl->n_valid = n_valid;
+            if (!sided) ctrl->n_main = n_valid;
         }
     }
     // position of the first spacepoint every block of k_bin_count / k_bin_scatter has in this bin
@@ -596,7 +605,9 @@ k_cell_scan(uint32_t* __restrict__ cell_cnt, uint32_t* __restrict__ cell_off,
                 else c = (sc * 8u >= nb) ? 0u : (sc * 16u >= nb) ? 1u : (sc * 32u >= nb) ? 2u
                        : (sc * 64u >= nb) ? 3u : (sc * 256u >= nb) ? 4u : 5u;
                 const uint32_t base = atomicAdd(&ctrl->n_dcls[c], pop);
-                seg_info[bin * NR + lane] = (c << 28) | base;
+                if (sided && c < WORK_CLASSES / 2) atomicAdd(&ctrl->n_main, pop);
+                // bit 27: the scarcer side is the lower one (only read for the classes >= 4)
+                seg_info[bin * NR + lane] = (c << 28) | ((sided && c >= 4u && below < above) ? (1u << 27) : 0u) | base;
             }
         }
     }
@@ -682,6 +693,7 @@ struct DoubletArgs {
     uint32_t n_sp;
     const uint32_t* fallback_list;  // [n_sp] middles handed back by k_doublets_tile (MODE 2)
     const uint32_t* mid_order;      // [n_sp] ticket order of MODE 0 (null: grid order)
+    uint32_t split_sides;           // the classes with a scarce side go to the MODE 3 launch
 };
 
 __device__ __forceinline__ uint32_t lanemask_lt() {
@@ -794,6 +806,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B200_DOUBLET_MIN_CTAS)
 k_doublets(const DevCfg cfg, const DoubletArgs a) {
     constexpr bool SPILL = (MODE == 1);
     constexpr bool LISTED = (MODE == 2);
+    constexpr bool SIDES = (MODE == 3);
     extern __shared__ __align__(16) uint32_t s_mem[];
     __shared__ unsigned long long s_pairs[2];
     __shared__ uint32_t s_acc[3];  // active, nb, nt
@@ -807,6 +820,10 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
         s_pairs[0] = s_pairs[1] = 0ull;
         s_acc[0] = s_acc[1] = s_acc[2] = 0u;
     }
+    // k_doublets<3> (launched behind this one with programmatic stream serialization) shares no
+    // data with this launch: its CTAs may take the slots this launch frees while its last middles
+    // are still running
+    if (MODE == 0) asm volatile("griddepcontrol.launch_dependents;");
     __syncthreads();
     const uint32_t n_valid = a.ctrl->n_valid;
     const bool has_var = a.ctrl->has_variance != 0u;
@@ -815,12 +832,18 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
     unsigned long long pairs = 0ull, visited = 0ull;  // per lane
     uint32_t acc_active = 0, acc_nb = 0, acc_nt = 0;
 
-    const uint32_t n_work = SPILL ? a.ctrl->n_spill : (LISTED ? a.ctrl->n_fallback : n_valid);
-    if ((SPILL || LISTED) && n_work == 0u) return;  // the usual case: no ticket traffic at all
+    // With a cost-ordered ticket list (mid_order) the classes whose row populations leave one side
+    // (almost) empty — the last WORK_CLASSES / 2 — belong to the MODE 3 launch.
+    // (n_main: the tickets of MODE 0, written by k_cell_scan — all valid spacepoints without the split)
+    const uint32_t n_work = SPILL ? a.ctrl->n_spill
+                                  : (LISTED ? a.ctrl->n_fallback
+                                            : (SIDES ? n_valid - a.ctrl->n_main : a.ctrl->n_main));
+    if ((SPILL || LISTED || SIDES) && n_work == 0u) return;  // the usual case: no ticket traffic at all
     while (true) {
         uint32_t m = 0;
         if (lane == 0)
-            m = atomicAdd(SPILL ? &a.ctrl->ticket_s : (LISTED ? &a.ctrl->ticket_f : &a.ctrl->ticket_d), 1u);
+            m = atomicAdd(SPILL ? &a.ctrl->ticket_s
+                                : (LISTED ? &a.ctrl->ticket_f : (SIDES ? &a.ctrl->ticket_e : &a.ctrl->ticket_d)), 1u);
         m = __shfl_sync(0xffffffffu, m, 0);
 #ifdef B200_TAIL_PROBE
         if (MODE == 0 && lane == 0) {
@@ -836,6 +859,12 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
         if (SPILL) m = a.spill_list[m];
         if (LISTED) m = a.fallback_list[m];
         if (MODE == 0 && a.mid_order) m = __ldg(a.mid_order + m);  // longest middles first
+        bool lower_scarce = false;
+        if (SIDES) {
+            m = __ldg(a.mid_order + (n_valid - n_work) + m);
+            lower_scarce = (m & MID_LOWER_SCARCE) != 0u;
+            m &= ~MID_LOWER_SCARCE;
+        }
 #ifdef B200_CELL_ORDER_TICKETS
         // tickets in CELL order: the warps of a CTA then work on middles of the same
         // (bin, r row, z cell) neighbourhood at the same time and share their candidate cells in L1
@@ -899,15 +928,35 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
         for (int pass = SPILL ? 1 : 0; run && pass < (SPILL ? 2 : 1); ++pass) {
             const bool direct = SPILL;
             uint32_t wB = 0, wT = 0;  // doublets found so far in this pass
-            for (uint32_t j0 = 0; j0 < ncombo; j0 += 32) {
+            // MODE 3: the rows of the scarce side first (bottoms sit in the rows up to the
+            // middle's own, tops from its own row upwards: deltaRMin >= 0); if they hold no
+            // partner the middle cannot seed (seed_finding.cpp:85-95) and the other, populated
+            // side is never read. All other modes: one segment, all rows.
+            uint32_t split = 0;  // rows [0, split) form the lower segment
+            if (SIDES && cfg.deltaRMin >= 0.f) {
+                const uint32_t rowM = cell_row(g, M.w);
+                const uint32_t iM = (rowM > row_lo) ? ((rowM - row_lo < nrows) ? rowM - row_lo : nrows) : 0u;
+                // lower side scarce: [0, iM] | (iM, nrows); upper side scarce: [iM, nrows) | [0, iM)
+                split = lower_scarce ? ((iM + 1u < nrows) ? iM + 1u : nrows) : iM;
+            }
+            for (uint32_t seg = 0; seg < (SIDES ? 2u : 1u); ++seg) {
+            const bool low_seg = SIDES && (lower_scarce ? seg == 0u : seg == 1u);
+            const uint32_t rbase = SIDES ? (low_seg ? 0u : split) : 0u;
+            const uint32_t nr = SIDES ? (low_seg ? split : nrows - split) : nrows;
+            if (SIDES && (nr == 0u || (seg == 1u && split != 0u && split != nrows &&
+                                       (lower_scarce ? wB == 0u : wT == 0u))))
+                continue;
+            const uint32_t ncombo_s = SIDES ? walk.nq * nr : ncombo;
+            const float inv_nr = SIDES ? 1.f / float(nr) : inv_nrows;
+            for (uint32_t j0 = 0; j0 < ncombo_s; j0 += 32) {
                 // lane j: one (neighbour bin, row) -> contiguous run of cells
                 const uint32_t j = j0 + lane;
                 uint32_t lo = 0, len = 0, wphi = 0;
-                const uint32_t jj = (j < ncombo) ? j : 0u;
-                const uint32_t q = div_small(jj, inv_nrows), ri = jj - q * nrows;
+                const uint32_t jj = (j < ncombo_s) ? j : 0u;
+                const uint32_t q = div_small(jj, inv_nr), ri = rbase + (jj - q * nr);
                 const float L = __shfl_sync(0xffffffffu, winL, ri);
                 const float U = __shfl_sync(0xffffffffu, winU, ri);
-                if (j < ncombo && ((win_mask >> ri) & 1u)) {
+                if (j < ncombo_s && ((win_mask >> ri) & 1u)) {
                     const uint32_t zb = walk.zbin(q);
                     const uint32_t base = walk.bin(cfg, q) * g.CPB + (row_lo + ri) * g.NZc;
                     lo = __ldg(a.cell_off + base + cell_z(g, zb, L));
@@ -970,6 +1019,7 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
                     wB += __popc(mB);
                     wT += __popc(mT);
                 }
+            }
             }
             if (direct) {
                 // Sort the mid-top records by (cotTheta, reference order): bucket sort between
