@@ -660,7 +660,17 @@ def run_b200(args):
 
         def search_kernel(name):
             t = kt[name] * 1e-3
-            k = ncu.get("k_" + name, {})
+            k = dict(ncu.get("k_" + name, {}))
+            if name == "doublets":
+                # the stage is three launches: all middles but the sided classes, those (k_doublets<3>)
+                # and the (normally empty) spill pass: instructions and traffic add up
+                parts = [k] + [ncu[x] for x in ("k_doublets_sides", "k_doublets_spill") if x in ncu]
+                if k.get("warp_instructions"):
+                    wi = sum(p_["warp_instructions"] for p_ in parts)
+                    k["active_lanes_per_instruction"] = sum(
+                        p_["warp_instructions"] * p_["active_lanes_per_instruction"] for p_ in parts) / wi
+                    k["warp_instructions"] = wi
+                    k["dram_bytes"] = sum(p_["dram_bytes"] for p_ in parts)
             r = {"bound": "fp32-issue", "kernel": "k_" + name, "ms_per_launch": kt[name],
                  "achieved": exe[name] / t / 1e12, "peak": fp32_peak_tops,
                  "unit": "Tops/s (non-fused fp32; EXECUTED ops, counted on the device)",

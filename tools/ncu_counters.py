@@ -31,7 +31,7 @@ out = {"source": rep.split("/")[-1]}
 md = [f"# ncu --set full counters ({rep.split('/')[-1]})", ""]
 for r in rr[2:]:
     name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "")
-    k = {"k_doublets<0>": "k_doublets", "k_doublets<1>": "k_doublets_spill", "k_doublets<2>": "k_doublets_fallback",
+    k = {"k_doublets<0>": "k_doublets", "k_doublets<1>": "k_doublets_spill", "k_doublets<2>": "k_doublets_fallback", "k_doublets<3>": "k_doublets_sides",
          "k_triplets<0>": "k_triplets", "k_triplets<1>": "k_triplets_dense"}.get(name, name.split("<")[0])
     d = {lab: val(r, key) for key, lab in keys if key in hdr}
     d["dram_bytes"] = val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")
