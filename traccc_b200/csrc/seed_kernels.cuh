@@ -838,7 +838,10 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
     const uint32_t n_work = SPILL ? a.ctrl->n_spill
                                   : (LISTED ? a.ctrl->n_fallback
                                             : (SIDES ? n_valid - a.ctrl->n_main : a.ctrl->n_main));
-    if ((SPILL || LISTED || SIDES) && n_work == 0u) return;  // the usual case: no ticket traffic at all
+    if ((SPILL || LISTED || SIDES) && n_work == 0u) {  // the usual case: no ticket traffic at all
+        if (SIDES) asm volatile("griddepcontrol.wait;" ::: "memory");  // (see the end of the kernel)
+        return;
+    }
     while (true) {
         uint32_t m = 0;
         if (lane == 0)
@@ -1237,6 +1240,11 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
             atomicAdd(&a.ctrl->n_mid_top, s_acc[2]);
         }
     }
+    // This launch started before k_doublets<0> had finished (programmatic stream serialization) and
+    // needs nothing from it — but the launches behind it do, and they only wait for this one: it
+    // must not complete first (PTX: a grid launched as a dependent has to execute
+    // griddepcontrol.wait for the stream order to hold).
+    if (SIDES) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------
