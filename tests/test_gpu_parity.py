@@ -468,7 +468,7 @@ def test_parity_group_kernel(mode, monkeypatch):
 def test_parity_doublet_ticket_order(order, monkeypatch):
     """k_doublets draws its tickets in cost order (k_cell_scan classifies every (bin, r row) by the
     populations of the rows below / above it, k_bin_scatter lays the middles out class by class;
-    automatic from 16k spacepoints on) or in grid order: forced either way with
+    automatic from 32k spacepoints on) or in grid order: forced either way with
     B200SEED_DOUBLET_ORDER, the binning, doublet and triplet sets, seeds and parameters must be the
     oracle's — small and ragged events, 7 z bins, spacepoints outside the grid, an empty event."""
     from traccc_b200 import seedfinder_config, spacepoint_grid_config, toy_detector
@@ -483,6 +483,37 @@ def test_parity_doublet_ticket_order(order, monkeypatch):
     _check_event(toy_detector.generate_event(1200, 37), finder=finder, grid=spacepoint_grid_config(finder))
     got, _ = _check_event(toy_detector.generate_event(10000, 31), dump=False)
     assert got["counters"]["overflow"] == 0
+
+
+def test_overlapped_doublet_launches_are_repeatable(monkeypatch):
+    """From 32k spacepoints on (here forced) the doublet stage is two overlapping launches (k_doublets<0> and,
+    as a programmatic dependent that fills its tail, k_doublets<3> for the middles with a scarce
+    side). The same events, four in flight on different streams, 25 times: every run must return
+    the seeds and counters of the first one bit for bit, and those are the oracle's."""
+    import hashlib
+    import torch
+    from traccc_b200 import seedfilter_config, seedfinder_config, seeding, spacepoint_grid_config, toy_detector
+    monkeypatch.setenv("B200SEED_DOUBLET_ORDER", "cost")
+    f = seedfinder_config()
+    events = [toy_detector.generate_event(4000, 300 + i) for i in range(4)]
+    streams = [torch.cuda.Stream() for _ in events]
+    algs = [seeding.triplet_seeding_algorithm(f, spacepoint_grid_config(f), seedfilter_config()) for _ in events]
+    sps = [seeding.spacepoint_collection.from_event(e) for e in events]
+
+    def digest(out):
+        h, m = out.to_host(), hashlib.sha1()
+        for k in ("bottom", "middle", "top", "quality"):
+            m.update(np.ascontiguousarray(h[k]).tobytes())
+        return m.hexdigest(), _physics_counters(out.host_counters())
+
+    first = None
+    for _ in range(25):
+        outs = [algs[i](sps[i], stream=streams[i]) for i in range(len(events))]
+        torch.cuda.synchronize()
+        d = [digest(o) for o in outs]
+        first = first or d
+        assert d == first
+    _check_event(events[0], dump=False)
 
 
 def test_parity_pooled_triplet_kernel(monkeypatch):

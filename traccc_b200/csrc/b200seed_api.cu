@@ -75,7 +75,7 @@ struct b200seed_handle {
     // cp.async (B200SEED_DOUBLETS=warp|tile|ldgsts, read at b200seed_create)
     int doublet_mode = 2;
     // k_doublets<0> draws its tickets in cost order (longest middles first: k_cell_scan's classes)
-    // instead of grid order: 1 = for events of at least 16k spacepoints (default), 0 / 2 = never /
+    // instead of grid order: 1 = for events of at least 32k spacepoints (default), 0 / 2 = never /
     // always (B200SEED_DOUBLET_ORDER=grid / cost, for A/B runs and the tests)
     int ordered_tickets = 1;
     // ... and the classes with a scarce side in a launch of their own (B200SEED_DOUBLET_SIDES=0: off)
@@ -726,7 +726,7 @@ int b200seed_get_timings(b200seed_handle* h, const char** names, float* ms, int 
 int b200seed_launches_per_event(const b200seed_handle* h, int with_params) {
     // k_bin_count, k_cell_scan, k_bin_scatter, k_doublets<0>, k_doublets<1>, k_triplets,
     // k_seed_gather; the group kernel adds one launch (k_doublets_tile + k_doublets<2>)
-    // (events of at least 16k spacepoints: + k_doublets<3> for the middles with a scarce side)
+    // (events of at least 32k spacepoints: + k_doublets<3> for the middles with a scarce side)
     const bool sides = h && h->doublet_mode == 2 && h->ordered_tickets && h->split_sides && h->finder.deltaRMin >= 0.f;
     const int doublets = (h && h->doublet_mode != 2) ? 3 : (sides ? 3 : 2);
     const int triplets = (h && h->triplet_pool) ? 2 : 1;
@@ -788,9 +788,10 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
     float4* csp4 = reinterpret_cast<float4*>(at(L.csp4));
     uint32_t* ccanon = reinterpret_cast<uint32_t*>(at(L.ccanon));
     // ticket order of k_doublets<0> (cost classes per (bin, r row); B200SEED_DOUBLET_ORDER=grid: off)
-    // (from 16k spacepoints on: below that the launch is too short for its end to matter and the
-    // classification costs k_cell_scan / k_bin_scatter more than it saves; =cost forces it)
-    const bool ordered = h->ordered_tickets == 2 || (h->ordered_tickets == 1 && n_sp >= 16384u);
+    // (from 32k spacepoints on: below that the launch is too short for its end to matter, and the
+    // classification and the extra launch cost more than they save — measured crossover at 7000
+    // particles per event: 5000: -3 %, 7000: +1.5 %, 10000: +3 % events/s; =cost forces it)
+    const bool ordered = h->ordered_tickets == 2 || (h->ordered_tickets == 1 && n_sp >= 32768u);
     uint32_t* seg_info = ordered ? reinterpret_cast<uint32_t*>(at(L.seg_info)) : nullptr;
     uint32_t* mid_order = ordered ? reinterpret_cast<uint32_t*>(at(L.mid_order)) : nullptr;
     // the classes with an (almost) empty side get their own launch, which looks at that side first
