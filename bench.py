@@ -565,13 +565,20 @@ def run_b200(args):
     DIAG = args.e2e_records == "diag"
     rec_bytes = 56 if DIAG else 176
     ios, outs = pool.make_batch(events, diag=DIAG)
-    h2d = sum(e.xyz.nbytes + e.var_z.nbytes + e.var_r.nbytes + e.meas_index.nbytes + e.meas_local.nbytes
-              + e.meas_surface.nbytes for e in events)
+    # Bytes that actually cross PCIe. Default: the library computes only phi, theta, q/p and
+    # var(q/p) on the device (16 bytes per seed, b200seed_seed_params) and completes the records on
+    # the host, inside pool.process, from the caller's measurement columns — which then never go to
+    # the device. B200SEED_PCIE_PARAMS=records: the records themselves and all six input columns.
+    COMPACT = os.environ.get("B200SEED_PCIE_PARAMS") != "records"
+    h2d = sum(e.xyz.nbytes + e.var_z.nbytes + e.var_r.nbytes
+              + (0 if COMPACT else e.meas_index.nbytes + e.meas_local.nbytes + e.meas_surface.nbytes)
+              for e in events)
     d2h_box = [0]
 
     def step_e2e():
         pool.process(ios)
-        d2h_box[0] = sum(C.sizeof(_lib.Counters) + int(io.n_seeds) * (16 + rec_bytes) for io in ios)
+        d2h_box[0] = sum(C.sizeof(_lib.Counters) + int(io.n_seeds) * (16 + (16 if COMPACT else rec_bytes))
+                         for io in ios)
 
     def timed_wall(step_fn, k, w):
         for _ in range(w):
@@ -724,8 +731,11 @@ def run_b200(args):
                 "e2e": {"value": e2e_ev_per_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h_box[0],
                         "how": f"b200seed_pool_process from pinned host buffers: {PW} native worker threads, "
-                               f"2 algorithm instances/streams each; parameters as {rec_bytes}-byte "
-                               f"{'diagonal (b200seed_bound_params_diag)' if DIAG else 'full'} records",
+                               f"2 algorithm instances/streams each; parameters delivered as {rec_bytes}-byte "
+                               f"{'diagonal (b200seed_bound_params_diag)' if DIAG else 'full'} records"
+                               + ("; over PCIe only 16 bytes per seed (phi, theta, q/p, var(q/p)), the records "
+                                  "completed on the host inside the timed region from the caller's measurement "
+                                  "columns, which are not sent to the device" if COMPACT else ""),
                         "other_record_form": {"bytes_per_record": 176 if DIAG else 56, "value": e2e_other}},
                 "roofline": roof, "clocks": clocks,
                 "event_counters_mean": c_mean}

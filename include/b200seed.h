@@ -138,6 +138,17 @@ typedef struct b200seed_bound_params_diag {
     float cov_diag[6];
 } b200seed_bound_params_diag;
 
+/* The part of a parameter record that has to be computed from the seed: phi, theta, q/p and the
+ * variance of q/p (which depends on theta and q/p). Everything else in b200seed_bound_params is
+ * either copied from the measurement of the bottom spacepoint (surface_link, loc0, loc1), zero
+ * (time) or a constant of the b200seed_tpe_cfg (the other five variances):
+ * b200seed_expand_seed_params() rebuilds the records on the host, bit for bit. 16 bytes: the form in
+ * which the host-buffer entry points (b200seed_run_host, b200seed_pool_process) move the parameters
+ * over PCIe — and the reason they then need not send the measurement columns to the device. */
+typedef struct b200seed_seed_params {
+    float phi, theta, qop, var_qop;
+} b200seed_seed_params;
+
 /* Device-side counters of one event. Written by b200seed_run when d_counters != NULL;
  * they replace the reference's D->H size reads (triplet_seeding_algorithm.cpp:64-224)
  * for logging and for the parity tests. */
@@ -291,6 +302,22 @@ int b200seed_estimate_params_diag(b200seed_handle* h, void* stream, const uint32
                                   const float* d_xyz, const uint32_t* d_sp_meas_index_1,
                                   const float* d_meas_local, const uint64_t* d_meas_surface,
                                   const float bfield[3], b200seed_bound_params_diag* d_params);
+/* b200seed_estimate_params with the 16-byte b200seed_seed_params output (homogeneous field); the
+ * measurement columns are not needed on the device. */
+int b200seed_estimate_params_compact(b200seed_handle* h, void* stream, const uint32_t* d_n_seeds,
+                                     uint32_t seed_capacity, const uint32_t* d_bottom,
+                                     const uint32_t* d_middle, const uint32_t* d_top,
+                                     const float* d_xyz, const float bfield[3],
+                                     b200seed_seed_params* d_params);
+/* HOST helper: the records of n seeds from their b200seed_seed_params, the seeds' bottom
+ * spacepoints and the HOST copies of the columns b200seed_estimate_params reads on the device
+ * (sp_meas_index_1 / meas_local / meas_surface: NULL means what it means there). out_full and / or
+ * out_diag (either may be NULL) receive exactly what b200seed_estimate_params /
+ * b200seed_estimate_params_diag would have written. */
+void b200seed_expand_seed_params(const b200seed_handle* h, uint32_t n, const uint32_t* bottom,
+                                 const b200seed_seed_params* in, const uint32_t* sp_meas_index_1,
+                                 const float* meas_local, const uint64_t* meas_surface,
+                                 b200seed_bound_params* out_full, b200seed_bound_params_diag* out_diag);
 /* HOST helper: n diagonal records -> full 176-byte records (off-diagonal elements zero). */
 void b200seed_expand_params(const b200seed_bound_params_diag* in, uint32_t n,
                             b200seed_bound_params* out);

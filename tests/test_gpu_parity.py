@@ -556,6 +556,42 @@ def test_diagonal_parameter_records():
         assert np.array_equal(exp.view(np.uint8), full["params"].view(np.uint8))
 
 
+def test_compact_seed_parameters_expand_to_the_full_records():
+    """b200seed_estimate_params_compact + b200seed_expand_seed_params (the form in which the
+    host-buffer entry points move the parameters over PCIe: 16 bytes per seed, the measurement
+    columns stay on the host): bit for bit the records of b200seed_estimate_params, full and
+    diagonal, with and without a measurement index column, for non-default sigma / inflation."""
+    import torch
+    from traccc_b200 import seedfilter_config, seedfinder_config, seeding, spacepoint_grid_config, toy_detector
+    from traccc_b200.seeding import track_params_estimation_config
+    f = seedfinder_config()
+    sa = seeding.triplet_seeding_algorithm(f, spacepoint_grid_config(f), seedfilter_config())
+    cfgs = [None, track_params_estimation_config()]
+    cfgs[1].initial_sigma[0] = 0.3
+    cfgs[1].initial_sigma[4] = 0.02
+    cfgs[1].initial_inflation[3] = 7.0
+    cfgs[1].initial_inflation[4] = 13.0
+    for cfg in cfgs:
+        tp = seeding.seed_parameter_estimation_algorithm(cfg)
+        for n, seed in ((300, 1), (2500, 2)):
+            ev = toy_detector.with_modules(toy_detector.generate_event(n, seed), frac_1d=0.1, seed=seed)
+            sps = seeding.spacepoint_collection.from_event(ev)
+            meas = seeding.measurement_collection.from_event(ev)
+            seeds = sa(sps)
+            full = tp(ev.bfield, meas, sps, seeds)
+            comp = tp.compact(ev.bfield, sps, seeds)
+            torch.cuda.synchronize()
+            h = seeds.to_host()
+            ns = len(h["bottom"])
+            assert ns > 0
+            ref = tp.to_host(full, ns)
+            c = np.frombuffer(comp[: ns * 16].cpu().numpy().tobytes(), dtype=seeding.SEED_PARAMS_DTYPE)
+            got = tp.expand_seed_params(h["bottom"], c, ev.meas_index, ev.meas_local, ev.meas_surface)
+            assert np.array_equal(got.view(np.uint8), ref.view(np.uint8))
+            gd = tp.expand_seed_params(h["bottom"], c, ev.meas_index, ev.meas_local, ev.meas_surface, diag=True)
+            assert np.array_equal(seeding.expand_params(gd).view(np.uint8), ref.view(np.uint8))
+
+
 def test_stress_event_full_size():
     """BASELINE.json configs[4] at its full size (100k particles in |eta| < 1, 400k spacepoints,
     ~6e8 + 3e8 doublets, 1e12 triplet combinations): no capacity-bounded buffer may overflow with

@@ -96,6 +96,10 @@ struct b200seed_handle {
     void* d_stage = nullptr;
     size_t d_stage_bytes = 0;
     b200seed_counters* h_pinned = nullptr;  // counters + n_seeds read-back
+    // host-buffer path: pinned landing area of the 16-byte b200seed_seed_params records (and of the
+    // bottom indices when the caller did not ask for the seed columns), expanded on the host
+    void* h_compact = nullptr;
+    size_t h_compact_bytes = 0;
     // OR of the overflow masks of the events run on this handle since the last
     // b200seed_check_overflow: one pinned, device-mapped word that k_seed_gather writes only when
     // an event was truncated (so a caller that passes d_counters == NULL still learns about it)
@@ -606,6 +610,7 @@ void b200seed_destroy(b200seed_handle* h) {
     if (h->d_form) cudaFree(h->d_form);
     if (h->ev_host) cudaEventDestroy(h->ev_host);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    if (h->h_compact) cudaFreeHost(h->h_compact);
     if (h->h_sticky) cudaFreeHost(h->h_sticky);
     delete h;
 }
@@ -1062,11 +1067,13 @@ int estimate_impl(b200seed_handle* h, void* stream, const uint32_t* d_n_seeds,
                   const uint32_t* d_top, const float* d_xyz, const uint32_t* d_sp_meas_index_1,
                   const float* d_meas_local, const uint64_t* d_meas_surface, const float bfield[3],
                   const b200seed_field_grid& fg, b200seed_bound_params* d_params,
-                  b200seed_bound_params_diag* d_params_diag = nullptr) {
+                  b200seed_bound_params_diag* d_params_diag = nullptr,
+                  b200seed_seed_params* d_params_compact = nullptr) {
     if (!h) return B200SEED_EINVAL;
     if (seed_capacity == 0) return B200SEED_OK;
     if (!d_xyz) return B200SEED_OK;  // no spacepoints => no seeds (…estimation_algorithm.cpp:49-51)
-    if (!d_n_seeds || !d_bottom || !d_middle || !d_top || !bfield || (!d_params && !d_params_diag))
+    if (!d_n_seeds || !d_bottom || !d_middle || !d_top || !bfield ||
+        (!d_params && !d_params_diag && !d_params_compact))
         return fail(h, B200SEED_EINVAL, "b200seed_estimate_params: null pointer");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     CUDA_TRY(h, cudaSetDevice(h->device));
@@ -1074,7 +1081,8 @@ int estimate_impl(b200seed_handle* h, void* stream, const uint32_t* d_n_seeds,
         KernelTimer t(h, s, "estimate_params");
         k_estimate_params<<<(seed_capacity + 127) / 128, 128, 0, s>>>(
             h->tpe, d_n_seeds, seed_capacity, d_bottom, d_middle, d_top, d_xyz, d_sp_meas_index_1,
-            d_meas_local, d_meas_surface, bfield[0], bfield[1], bfield[2], fg, d_params, d_params_diag);
+            d_meas_local, d_meas_surface, bfield[0], bfield[1], bfield[2], fg, d_params, d_params_diag,
+            d_params_compact);
     }
     CUDA_TRY(h, cudaGetLastError());
     return B200SEED_OK;
@@ -1103,6 +1111,50 @@ int b200seed_estimate_params_diag(b200seed_handle* h, void* stream, const uint32
     b200seed_field_grid none{};
     return estimate_impl(h, stream, d_n_seeds, seed_capacity, d_bottom, d_middle, d_top, d_xyz,
                          d_sp_meas_index_1, d_meas_local, d_meas_surface, bfield, none, nullptr, d_params);
+}
+
+int b200seed_estimate_params_compact(b200seed_handle* h, void* stream, const uint32_t* d_n_seeds,
+                                     uint32_t seed_capacity, const uint32_t* d_bottom,
+                                     const uint32_t* d_middle, const uint32_t* d_top,
+                                     const float* d_xyz, const float bfield[3],
+                                     b200seed_seed_params* d_params) {
+    b200seed_field_grid none{};
+    return estimate_impl(h, stream, d_n_seeds, seed_capacity, d_bottom, d_middle, d_top, d_xyz, nullptr,
+                         nullptr, nullptr, bfield, none, nullptr, nullptr, d_params);
+}
+
+void b200seed_expand_seed_params(const b200seed_handle* h, uint32_t n, const uint32_t* bottom,
+                                 const b200seed_seed_params* in, const uint32_t* sp_meas_index_1,
+                                 const float* meas_local, const uint64_t* meas_surface,
+                                 b200seed_bound_params* out_full, b200seed_bound_params_diag* out_diag) {
+    if (!h || !bottom || !in) return;
+    // the variances that do not depend on the seed: the same two float multiplications as in
+    // k_estimate_params (track_params_estimation.cpp:64-86)
+    float var[6];
+    for (int j = 0; j < 6; ++j) {
+        float v = h->tpe.initial_sigma[j] * h->tpe.initial_sigma[j];
+        v *= h->tpe.initial_inflation[j];
+        var[j] = v;
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t ib = bottom[i];
+        const uint32_t mi = sp_meas_index_1 ? sp_meas_index_1[ib] : ib;
+        const uint64_t link = meas_surface ? meas_surface[mi] : 0ull;
+        const float loc0 = meas_local ? meas_local[2 * size_t(mi)] : 0.f;
+        const float loc1 = meas_local ? meas_local[2 * size_t(mi) + 1] : 0.f;
+        const float vec[6] = {loc0, loc1, in[i].phi, in[i].theta, in[i].qop, 0.f};
+        if (out_diag) {
+            b200seed_bound_params_diag& o = out_diag[i];
+            o.surface_link = link;
+            for (int k = 0; k < 6; ++k) o.vec[k] = vec[k], o.cov_diag[k] = (k == 4) ? in[i].var_qop : var[k];
+        }
+        if (out_full) {
+            b200seed_bound_params& o = out_full[i];
+            std::memset(&o, 0, sizeof(o));
+            o.surface_link = link;
+            for (int k = 0; k < 6; ++k) o.vec[k] = vec[k], o.cov[k * 7] = (k == 4) ? in[i].var_qop : var[k];
+        }
+    }
 }
 
 void b200seed_expand_params(const b200seed_bound_params_diag* in, uint32_t n, b200seed_bound_params* out) {
@@ -1159,6 +1211,8 @@ struct HostEvent {
     uint32_t *d_b = nullptr, *d_m = nullptr, *d_t = nullptr;
     float* d_q = nullptr;
     b200seed_bound_params* d_p = nullptr;
+    bool compact = false;  // the parameters cross PCIe as b200seed_seed_params
+    const uint32_t* h_bot_stage = nullptr;  // bottom indices on the host (for host_expand)
     bool submitted = false;
 };
 
@@ -1182,6 +1236,14 @@ int host_submit(b200seed_handle* h, cudaStream_t s, HostEvent& e) {
     const bool diag = e.h_params_diag != nullptr;
     const bool want_params = e.h_params != nullptr || diag;
     const uint32_t n_sp = e.n_sp, n_meas = e.n_meas, seed_capacity = e.seed_capacity;
+    // Parameters: only phi, theta, q/p and var(q/p) are computed on the device (16 bytes per seed);
+    // the records are completed on the host from the caller's own measurement columns, which then
+    // never travel to the device (B200SEED_PCIE_PARAMS=records: the records themselves, as before).
+    static const bool compact_ok = [] {
+        const char* m = std::getenv("B200SEED_PCIE_PARAMS");
+        return !(m && !std::strcmp(m, "records"));
+    }();
+    e.compact = want_params && compact_ok;
 
     // device staging: inputs | outputs | workspace
     size_t o = 0;
@@ -1195,8 +1257,10 @@ int host_submit(b200seed_handle* h, cudaStream_t s, HostEvent& e) {
                  o_ml = take(size_t(n_meas) * 8), o_ms = take(size_t(n_meas) * 8),
                  o_b = take(size_t(seed_capacity) * 4), o_m = take(size_t(seed_capacity) * 4),
                  o_t = take(size_t(seed_capacity) * 4), o_q = take(size_t(seed_capacity) * 4),
-                 o_p = take(want_params ? size_t(seed_capacity) * (diag ? sizeof(b200seed_bound_params_diag)
-                                                                         : sizeof(b200seed_bound_params))
+                 o_p = take(want_params ? size_t(seed_capacity) *
+                                              (e.compact ? sizeof(b200seed_seed_params)
+                                                         : (diag ? sizeof(b200seed_bound_params_diag)
+                                                                 : sizeof(b200seed_bound_params)))
                                         : 0),
                  o_n = take(256), o_c = take(sizeof(b200seed_counters));
     const size_t ws_bytes = b200seed_workspace_bytes(h, n_sp);
@@ -1210,6 +1274,16 @@ int host_submit(b200seed_handle* h, cudaStream_t s, HostEvent& e) {
         h->d_stage_bytes = want;
     }
     if (!h->h_pinned) CUDA_TRY(h, cudaMallocHost(&h->h_pinned, 256));
+    if (e.compact) {
+        const size_t need = size_t(seed_capacity) * (sizeof(b200seed_seed_params) + 4);
+        if (need > h->h_compact_bytes) {
+            if (h->h_compact) CUDA_TRY(h, cudaFreeHost(h->h_compact));
+            h->h_compact = nullptr;
+            h->h_compact_bytes = 0;
+            CUDA_TRY(h, cudaMallocHost(&h->h_compact, need + need / 4));
+            h->h_compact_bytes = need + need / 4;
+        }
+    }
     unsigned char* d = static_cast<unsigned char*>(h->d_stage);
     float* d_xyz = reinterpret_cast<float*>(d + o_xyz);
     float* d_vz = e.h_var_z ? reinterpret_cast<float*>(d + o_vz) : nullptr;
@@ -1228,7 +1302,7 @@ int host_submit(b200seed_handle* h, cudaStream_t s, HostEvent& e) {
     CUDA_TRY(h, cudaMemcpyAsync(d_xyz, e.h_xyz, size_t(n_sp) * 12, cudaMemcpyHostToDevice, s));
     if (d_vz) CUDA_TRY(h, cudaMemcpyAsync(d_vz, e.h_var_z, size_t(n_sp) * 4, cudaMemcpyHostToDevice, s));
     if (d_vr) CUDA_TRY(h, cudaMemcpyAsync(d_vr, e.h_var_r, size_t(n_sp) * 4, cudaMemcpyHostToDevice, s));
-    if (want_params) {
+    if (want_params && !e.compact) {
         if (d_smi)
             CUDA_TRY(h, cudaMemcpyAsync(d_smi, e.h_smi, size_t(n_sp) * 4, cudaMemcpyHostToDevice, s));
         if (d_ml)
@@ -1244,7 +1318,11 @@ int host_submit(b200seed_handle* h, cudaStream_t s, HostEvent& e) {
     int rc = b200seed_run(h, s, n_sp, d_xyz, d_vz, d_vr, d + o_ws, ws_bytes, seed_capacity, e.d_b,
                           e.d_m, e.d_t, e.d_q, d_n, d_c);
     if (rc != B200SEED_OK) return rc;
-    if (want_params) {
+    if (e.compact) {
+        rc = b200seed_estimate_params_compact(h, s, d_n, seed_capacity, e.d_b, e.d_m, e.d_t, d_xyz, e.bfield,
+                                              reinterpret_cast<b200seed_seed_params*>(e.d_p));
+        if (rc != B200SEED_OK) return rc;
+    } else if (want_params) {
         rc = diag ? b200seed_estimate_params_diag(h, s, d_n, seed_capacity, e.d_b, e.d_m, e.d_t, d_xyz, d_smi,
                                                   d_ml, d_ms, e.bfield,
                                                   reinterpret_cast<b200seed_bound_params_diag*>(e.d_p))
@@ -1276,22 +1354,51 @@ int host_finish(b200seed_handle* h, cudaStream_t s, HostEvent& e, uint32_t* h_n_
         if (e.h_middle) CUDA_TRY(h, cudaMemcpyAsync(e.h_middle, e.d_m, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
         if (e.h_top) CUDA_TRY(h, cudaMemcpyAsync(e.h_top, e.d_t, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
         if (e.h_quality) CUDA_TRY(h, cudaMemcpyAsync(e.h_quality, e.d_q, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
-        if (e.h_params_diag)
+        b200seed_seed_params* h_sp = static_cast<b200seed_seed_params*>(h->h_compact);
+        const uint32_t* h_bot = e.h_bottom;
+        if (e.compact) {
+            CUDA_TRY(h, cudaMemcpyAsync(h_sp, e.d_p, size_t(n) * sizeof(b200seed_seed_params),
+                                        cudaMemcpyDeviceToHost, s));
+            if (!h_bot) {  // the expansion needs the bottom spacepoint of every seed
+                uint32_t* stage = reinterpret_cast<uint32_t*>(h_sp + e.seed_capacity);
+                CUDA_TRY(h, cudaMemcpyAsync(stage, e.d_b, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
+                h_bot = stage;
+            }
+        } else if (e.h_params_diag) {
             CUDA_TRY(h, cudaMemcpyAsync(e.h_params_diag, e.d_p, size_t(n) * sizeof(b200seed_bound_params_diag),
                                         cudaMemcpyDeviceToHost, s));
-        else if (e.h_params)
+        } else if (e.h_params) {
             CUDA_TRY(h, cudaMemcpyAsync(e.h_params, e.d_p, size_t(n) * sizeof(b200seed_bound_params),
                                         cudaMemcpyDeviceToHost, s));
+        }
         CUDA_TRY(h, host_wait_point(h, s));
         CUDA_TRY(h, cudaEventSynchronize(h->ev_host));
-        // both forms requested: the full records are expanded on the host
-        if (e.h_params_diag && e.h_params) b200seed_expand_params(e.h_params_diag, n, e.h_params);
+        e.h_bot_stage = h_bot;
     }
+    // The device buffers of this handle are free again from here on; what is left (host_expand) is
+    // host work on the pinned landing area, which the next host_submit on this handle leaves alone.
     if (const uint32_t ovf = h->h_pinned->overflow) {
         *h->h_sticky = 0u;  // reported here
         return fail(h, B200SEED_EOVERFLOW, overflow_message(ovf));
     }
     return B200SEED_OK;
+}
+
+// Second half of a host-buffer event: the parameter records, completed on the host.
+void host_expand(b200seed_handle* h, const HostEvent& e, uint32_t n) {
+    if (n == 0) return;
+    if (e.compact)
+        b200seed_expand_seed_params(h, n, e.h_bot_stage, static_cast<const b200seed_seed_params*>(h->h_compact),
+                                    e.h_smi, e.h_ml, e.h_ms, e.h_params, e.h_params_diag);
+    // both forms requested: the full records are expanded on the host
+    else if (e.h_params_diag && e.h_params)
+        b200seed_expand_params(e.h_params_diag, n, e.h_params);
+}
+
+// host_submit would have to enlarge the pinned landing area of this handle (which may still hold an
+// event waiting for host_expand)
+bool host_submit_regrows_landing(const b200seed_handle* h, const HostEvent& e) {
+    return size_t(e.seed_capacity) * (sizeof(b200seed_seed_params) + 4) > h->h_compact_bytes;
 }
 
 }  // namespace
@@ -1361,25 +1468,44 @@ struct b200seed_pool {
             }
             cudaSetDevice(device);
             int k = 0;
+            // an event whose copies are done and whose records still have to be completed on the
+            // host: that happens after the next event went to the device, not before
+            Slot* todo = nullptr;
+            HostEvent todo_ev;
+            uint32_t todo_n = 0;
+            auto expand_todo = [&] {
+                if (todo) host_expand(todo->h, todo_ev, todo_n);
+                todo = nullptr;
+            };
             while (true) {
                 Slot& cur = w.slot[k];
                 const uint32_t idx = next.fetch_add(1);
                 if (idx < n_events) {
-                    cur.ev = host_event_of(events[idx]);
+                    const HostEvent ne = host_event_of(events[idx]);
+                    if (todo == &cur && host_submit_regrows_landing(cur.h, ne)) expand_todo();
+                    cur.ev = ne;
                     const int rc = host_submit(cur.h, cur.s, cur.ev);
                     events[idx].status = rc;
                     cur.pending = idx;
                 }
+                expand_todo();
                 Slot& oth = w.slot[k ^ 1];
                 if (oth.pending >= 0) {
                     b200seed_event_io& io = events[oth.pending];
-                    if (io.status == B200SEED_OK)
+                    if (io.status == B200SEED_OK) {
                         io.status = host_finish(oth.h, oth.s, oth.ev, &io.n_seeds, &io.counters);
+                        if (io.status == B200SEED_OK || io.status == B200SEED_EOVERFLOW) {
+                            todo = &oth;
+                            todo_ev = oth.ev;
+                            todo_n = io.n_seeds;
+                        }
+                    }
                     oth.pending = -1;
                 }
                 if (idx >= n_events && cur.pending < 0) break;
                 k ^= 1;
             }
+            expand_todo();
             {
                 std::lock_guard<std::mutex> lk(mu);
                 if (--running == 0) cv_done.notify_all();
@@ -1482,7 +1608,9 @@ int b200seed_run_host(b200seed_handle* h, void* stream, uint32_t n_sp, const flo
     if (h_counters) std::memset(h_counters, 0, sizeof(*h_counters));
     int rc = host_submit(h, s, e);
     if (rc != B200SEED_OK) return rc;
-    return host_finish(h, s, e, h_n_seeds, h_counters);
+    rc = host_finish(h, s, e, h_n_seeds, h_counters);
+    if (rc == B200SEED_OK || rc == B200SEED_EOVERFLOW) host_expand(h, e, *h_n_seeds);
+    return rc;
 }
 
 // Measured non-fused FP32 rate of the device (ops/s) — the denominator bench.py uses for the

@@ -2519,7 +2519,8 @@ k_estimate_params(const b200seed_tpe_cfg cfg, const uint32_t* __restrict__ n_see
                   const float* __restrict__ meas_local, const uint64_t* __restrict__ meas_surface,
                   const float bx, const float by, const float bz, const b200seed_field_grid fg,
                   b200seed_bound_params* __restrict__ out,
-                  b200seed_bound_params_diag* __restrict__ out_diag) {
+                  b200seed_bound_params_diag* __restrict__ out_diag,
+                  b200seed_seed_params* __restrict__ out_compact) {
     // Records are 176 B: written one per lane they would cost 32 sectors per store
     // instruction. Each warp builds its 32 records (5632 contiguous bytes) in shared memory
     // and streams them out as float4 rows.
@@ -2600,6 +2601,12 @@ k_estimate_params(const b200seed_tpe_cfg cfg, const uint32_t* __restrict__ n_see
         v *= cfg.initial_inflation[j];
         if (j == 3) var_theta = v;
         var[j] = v;
+    }
+    if (out_compact) {
+        // what only the device can compute: 16 bytes per seed (the rest of the record is copied
+        // from the bottom spacepoint's measurement or is a constant of the configuration)
+        if (live) reinterpret_cast<float4*>(out_compact)[i] = make_float4(phi, theta, qop, var[4]);
+        return;
     }
     const uint64_t link = meas_surface ? meas_surface[mi] : 0ull;
     const float loc0 = meas_local ? meas_local[2 * size_t(mi)] : 0.f;

@@ -28,6 +28,10 @@ BOUND_PARAMS_DIAG_DTYPE = np.dtype([("surface_link", "<u8"), ("vec", "<f4", (6,)
                                     ("cov_diag", "<f4", (6,))])
 
 
+# b200seed_seed_params: what only the device can compute of a record (16 bytes per seed)
+SEED_PARAMS_DTYPE = np.dtype([("phi", "<f4"), ("theta", "<f4"), ("qop", "<f4"), ("var_qop", "<f4")])
+
+
 def expand_params(diag: np.ndarray) -> np.ndarray:
     """b200seed_expand_params: 56-byte diagonal records -> full 176-byte records (host)."""
     diag = np.ascontiguousarray(diag)
@@ -458,6 +462,43 @@ class seed_parameter_estimation_algorithm:
             bf = (C.c_float * 3)(*[float(b) for b in bfield])
             rc = self.lib.b200seed_estimate_params(*head, C.byref(bf), _ptr(out))
         _lib.check(rc, self.h)
+        return out
+
+    def compact(self, bfield, spacepoints: spacepoint_collection, seeds: seed_collection,
+                stream=None) -> torch.Tensor:
+        """b200seed_estimate_params_compact: 16 bytes per seed (phi, theta, q/p, var(q/p)) — the
+        part of a record that has to be computed on the device; expand_seed_params() completes
+        the records on the host."""
+        cap = seeds.capacity
+        out = torch.empty(cap * SEED_PARAMS_DTYPE.itemsize, dtype=torch.uint8, device=f"cuda:{self.device}")
+        bf = (C.c_float * 3)(*[float(b) for b in bfield])
+        _lib.check(self.lib.b200seed_estimate_params_compact(
+            self.h, _stream_handle(stream or self.stream), _ptr(seeds.n_seeds), cap,
+            _ptr(seeds.bottom_index), _ptr(seeds.middle_index), _ptr(seeds.top_index),
+            _ptr(spacepoints.xyz), C.byref(bf), _ptr(out)), self.h)
+        return out
+
+    def expand_seed_params(self, bottom: np.ndarray, compact: np.ndarray, meas_index, meas_local,
+                           meas_surface, diag: bool = False) -> np.ndarray:
+        """b200seed_expand_seed_params (host): the full (or diagonal) records of the seeds from their
+        compact form and the HOST copies of the measurement columns."""
+        n = len(bottom)
+        bottom = np.ascontiguousarray(bottom, np.uint32)
+        compact = np.ascontiguousarray(compact)
+        out = np.zeros(n, dtype=BOUND_PARAMS_DIAG_DTYPE if diag else BOUND_PARAMS_DTYPE)
+
+        def hp(a, dt):
+            if a is None:
+                return None, None
+            a = np.ascontiguousarray(a, dt)
+            return a, a.ctypes.data_as(C.c_void_p)
+        k1, p1 = hp(meas_index, np.uint32)
+        k2, p2 = hp(meas_local, np.float32)
+        k3, p3 = hp(meas_surface, np.uint64)
+        o = out.ctypes.data_as(C.c_void_p)
+        self.lib.b200seed_expand_seed_params(self.h, n, bottom.ctypes.data_as(C.c_void_p),
+                                             compact.ctypes.data_as(C.c_void_p), p1, p2, p3,
+                                             None if diag else o, o if diag else None)
         return out
 
     @staticmethod
