@@ -11,7 +11,6 @@
 #include <cstddef>
 #include <cstdio>
 #include <atomic>
-#include <deque>
 #include <condition_variable>
 #include <cstring>
 #include <mutex>
@@ -1441,60 +1440,7 @@ struct b200seed_pool {
         cudaStream_t s = nullptr;
         HostEvent ev;
         long pending = -1;
-        // the records of the slot's previous event are still being completed from its pinned
-        // landing area (by an expander thread): no copy into that area before this is false
-        std::atomic<bool> expanding{false};
     };
-    // Completing the parameter records on the host (host_expand: ~0.3 ms per 10k-particle event) is
-    // handed to expander threads: on the worker threads it delayed the next submit / collect and cost
-    // 7 % of the end-to-end rate.
-    struct ExpandTask {
-        Slot* slot;
-        HostEvent ev;
-        uint32_t n;
-    };
-    std::vector<std::thread> expanders;
-    std::deque<ExpandTask> tasks;
-    std::mutex mu_x;
-    std::condition_variable cv_x, cv_x_done;
-    int outstanding = 0;  // tasks queued or running
-    bool stop_x = false;
-
-    void expand_loop() {
-        while (true) {
-            ExpandTask t;
-            {
-                std::unique_lock<std::mutex> lk(mu_x);
-                cv_x.wait(lk, [&] { return stop_x || !tasks.empty(); });
-                if (tasks.empty()) return;  // stop
-                t = tasks.front();
-                tasks.pop_front();
-            }
-            host_expand(t.slot->h, t.ev, t.n);
-            t.slot->expanding.store(false, std::memory_order_release);
-            {
-                std::lock_guard<std::mutex> lk(mu_x);
-                --outstanding;
-            }
-            cv_x_done.notify_all();
-        }
-    }
-    void expand_async(Slot& sl, const HostEvent& ev, uint32_t n) {
-        if (expanders.empty() || n == 0 || !(ev.compact || (ev.h_params_diag && ev.h_params))) {
-            host_expand(sl.h, ev, n);
-            return;
-        }
-        sl.expanding.store(true, std::memory_order_relaxed);
-        {
-            std::lock_guard<std::mutex> lk(mu_x);
-            tasks.push_back(ExpandTask{&sl, ev, n});
-            ++outstanding;
-        }
-        cv_x.notify_one();
-    }
-    static void wait_expanded(Slot& sl) {
-        while (sl.expanding.load(std::memory_order_acquire)) std::this_thread::yield();
-    }
     struct Worker {
         Slot slot[2];
         std::thread th;
@@ -1522,32 +1468,44 @@ struct b200seed_pool {
             }
             cudaSetDevice(device);
             int k = 0;
+            // an event whose copies are done and whose records still have to be completed on the
+            // host: that happens after the next event went to the device, not before
+            Slot* todo = nullptr;
+            HostEvent todo_ev;
+            uint32_t todo_n = 0;
+            auto expand_todo = [&] {
+                if (todo) host_expand(todo->h, todo_ev, todo_n);
+                todo = nullptr;
+            };
             while (true) {
                 Slot& cur = w.slot[k];
                 const uint32_t idx = next.fetch_add(1);
                 if (idx < n_events) {
                     const HostEvent ne = host_event_of(events[idx]);
-                    // (host_submit may have to enlarge the landing area the expander is reading)
-                    if (host_submit_regrows_landing(cur.h, ne)) wait_expanded(cur);
+                    if (todo == &cur && host_submit_regrows_landing(cur.h, ne)) expand_todo();
                     cur.ev = ne;
                     const int rc = host_submit(cur.h, cur.s, cur.ev);
                     events[idx].status = rc;
                     cur.pending = idx;
                 }
+                expand_todo();
                 Slot& oth = w.slot[k ^ 1];
                 if (oth.pending >= 0) {
                     b200seed_event_io& io = events[oth.pending];
                     if (io.status == B200SEED_OK) {
-                        wait_expanded(oth);  // its landing area is about to be overwritten
                         io.status = host_finish(oth.h, oth.s, oth.ev, &io.n_seeds, &io.counters);
-                        if (io.status == B200SEED_OK || io.status == B200SEED_EOVERFLOW)
-                            expand_async(oth, oth.ev, io.n_seeds);
+                        if (io.status == B200SEED_OK || io.status == B200SEED_EOVERFLOW) {
+                            todo = &oth;
+                            todo_ev = oth.ev;
+                            todo_n = io.n_seeds;
+                        }
                     }
                     oth.pending = -1;
                 }
                 if (idx >= n_events && cur.pending < 0) break;
                 k ^= 1;
             }
+            expand_todo();
             {
                 std::lock_guard<std::mutex> lk(mu);
                 if (--running == 0) cv_done.notify_all();
@@ -1579,11 +1537,6 @@ int b200seed_pool_create(const b200seed_finder_cfg* finder, const b200seed_grid_
         }
     }
     for (auto& w : p->workers) w.th = std::thread([p, &w] { p->work(w); });
-    // one expander per two workers (B200SEED_POOL_EXPANDERS=n; 0: the workers expand themselves)
-    int nx = (n_workers + 1) / 2;
-    if (const char* m = std::getenv("B200SEED_POOL_EXPANDERS")) nx = std::atoi(m);
-    nx = nx < 0 ? 0 : (nx > 64 ? 64 : nx);
-    for (int i = 0; i < nx; ++i) p->expanders.emplace_back([p] { p->expand_loop(); });
     *out = p;
     return B200SEED_OK;
 }
@@ -1602,10 +1555,6 @@ int b200seed_pool_process(b200seed_pool* p, b200seed_event_io* events, uint32_t 
     {
         std::unique_lock<std::mutex> lk(p->mu);
         p->cv_done.wait(lk, [&] { return p->running == 0; });
-    }
-    {
-        std::unique_lock<std::mutex> lk(p->mu_x);
-        p->cv_x_done.wait(lk, [&] { return p->outstanding == 0; });
     }
     for (uint32_t i = 0; i < n_events; ++i)
         if (events[i].status != B200SEED_OK) {
@@ -1626,13 +1575,6 @@ void b200seed_pool_destroy(b200seed_pool* p) {
         p->stop = true;
     }
     p->cv_job.notify_all();
-    {
-        std::lock_guard<std::mutex> lk(p->mu_x);
-        p->stop_x = true;
-    }
-    p->cv_x.notify_all();
-    for (auto& x : p->expanders)
-        if (x.joinable()) x.join();
     for (auto& w : p->workers) {
         if (w.th.joinable()) w.th.join();
         for (auto& sl : w.slot) {
