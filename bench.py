@@ -565,11 +565,11 @@ def run_b200(args):
     DIAG = args.e2e_records == "diag"
     rec_bytes = 56 if DIAG else 176
     ios, outs = pool.make_batch(events, diag=DIAG)
-    # Bytes that actually cross PCIe. Default: the library computes only phi, theta, q/p and
-    # var(q/p) on the device (16 bytes per seed, b200seed_seed_params) and completes the records on
-    # the host, inside pool.process, from the caller's measurement columns — which then never go to
-    # the device. B200SEED_PCIE_PARAMS=records: the records themselves and all six input columns.
-    COMPACT = os.environ.get("B200SEED_PCIE_PARAMS") != "records"
+    # Bytes that actually cross PCIe. Default: the records themselves and all six input columns.
+    # B200SEED_PCIE_PARAMS=compact: the library computes only phi, theta, q/p and var(q/p) on the
+    # device (16 bytes per seed, b200seed_seed_params) and completes the records on the host, inside
+    # pool.process, from the caller's measurement columns — which then never go to the device.
+    COMPACT = os.environ.get("B200SEED_PCIE_PARAMS") == "compact"
     h2d = sum(e.xyz.nbytes + e.var_z.nbytes + e.var_r.nbytes
               + (0 if COMPACT else e.meas_index.nbytes + e.meas_local.nbytes + e.meas_surface.nbytes)
               for e in events)

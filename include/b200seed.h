@@ -142,9 +142,12 @@ typedef struct b200seed_bound_params_diag {
  * variance of q/p (which depends on theta and q/p). Everything else in b200seed_bound_params is
  * either copied from the measurement of the bottom spacepoint (surface_link, loc0, loc1), zero
  * (time) or a constant of the b200seed_tpe_cfg (the other five variances):
- * b200seed_expand_seed_params() rebuilds the records on the host, bit for bit. 16 bytes: the form in
- * which the host-buffer entry points (b200seed_run_host, b200seed_pool_process) move the parameters
- * over PCIe — and the reason they then need not send the measurement columns to the device. */
+ * b200seed_expand_seed_params() rebuilds the records on the host, bit for bit. 16 bytes per seed
+ * instead of 56 / 176, and the measurement columns need not go to the device at all. With
+ * B200SEED_PCIE_PARAMS=compact in the environment of b200seed_create / b200seed_pool_create the
+ * host-buffer entry points (b200seed_run_host, b200seed_pool_process) move the parameters over PCIe
+ * in this form and complete the records on the host (for hosts whose D->H rate is the limit; the
+ * host then pays ~1 ms of gathers per 10k-particle event, which is why it is not the default). */
 typedef struct b200seed_seed_params {
     float phi, theta, qop, var_qop;
 } b200seed_seed_params;

@@ -535,18 +535,28 @@ def test_parity_pooled_triplet_kernel(monkeypatch):
     _check_event(toy_detector.generate_event(10000, 43), dump=False)
 
 
-def test_diagonal_parameter_records():
+@pytest.mark.parametrize("pcie", ["records", "compact"])
+def test_diagonal_parameter_records(pcie, monkeypatch):
     """b200seed_event_io::params_diag: the parameters leave the device as 56-byte diagonal
     records (a third of the PCIe bytes); b200seed_expand_params restores the full records,
-    bit for bit what the 176-byte path delivers."""
+    bit for bit what the 176-byte path delivers. Also with B200SEED_PCIE_PARAMS=compact: 16 bytes
+    per seed over PCIe, the records completed on the host from the caller's measurement columns."""
     from traccc_b200 import seeding, toy_detector
+    monkeypatch.setenv("B200SEED_PCIE_PARAMS", pcie)
     events = [toy_detector.generate_event(400 + 200 * i, 70 + i) for i in range(5)]
+    events = [toy_detector.with_modules(e, frac_1d=0.1, seed=i) for i, e in enumerate(events)]
     pool = seeding.EventPool(n_workers=2)
     ios_f, outs_f = pool.make_batch(events)
     ios_d, outs_d = pool.make_batch(events, diag=True)
     pool.process(ios_f)
     pool.process(ios_d)
-    for io_f, of, io_d, od in zip(ios_f, outs_f, ios_d, outs_d):
+    # the device-resident path (176-byte records written by the kernel) is the reference
+    import torch
+    from traccc_b200 import seedfilter_config, seedfinder_config, spacepoint_grid_config
+    f = seedfinder_config()
+    sa = seeding.triplet_seeding_algorithm(f, spacepoint_grid_config(f), seedfilter_config())
+    tp = seeding.seed_parameter_estimation_algorithm()
+    for ev, io_f, of, io_d, od in zip(events, ios_f, outs_f, ios_d, outs_d):
         full = seeding.EventPool.result(io_f, of)
         diag = seeding.EventPool.result(io_d, od)
         assert full["n_seeds"] == diag["n_seeds"] > 0
@@ -554,6 +564,11 @@ def test_diagonal_parameter_records():
             assert np.array_equal(full[k], diag[k])
         exp = seeding.expand_params(diag["params_diag"])
         assert np.array_equal(exp.view(np.uint8), full["params"].view(np.uint8))
+        sps = seeding.spacepoint_collection.from_event(ev)
+        seeds = sa(sps)
+        ref = tp(ev.bfield, seeding.measurement_collection.from_event(ev), sps, seeds)
+        torch.cuda.synchronize()
+        assert np.array_equal(tp.to_host(ref, full["n_seeds"]).view(np.uint8), full["params"].view(np.uint8))
 
 
 def test_compact_seed_parameters_expand_to_the_full_records():

@@ -100,6 +100,7 @@ struct b200seed_handle {
     // bottom indices when the caller did not ask for the seed columns), expanded on the host
     void* h_compact = nullptr;
     size_t h_compact_bytes = 0;
+    bool pcie_compact = false;  // B200SEED_PCIE_PARAMS=compact
     // OR of the overflow masks of the events run on this handle since the last
     // b200seed_check_overflow: one pinned, device-mapped word that k_seed_gather writes only when
     // an event was truncated (so a caller that passes d_counters == NULL still learns about it)
@@ -564,6 +565,7 @@ int b200seed_create(const b200seed_finder_cfg* finder, const b200seed_grid_cfg* 
                          h->smem_optin - 1024);
     cudaFuncSetAttribute(k_doublets_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          h->smem_optin - 1024);
+    if (const char* m = std::getenv("B200SEED_PCIE_PARAMS")) h->pcie_compact = !std::strcmp(m, "compact");
     if (const char* m = std::getenv("B200SEED_DOUBLET_SIDES")) h->split_sides = std::strcmp(m, "0") != 0;
     if (const char* m = std::getenv("B200SEED_PDL")) h->pdl = std::strcmp(m, "0") != 0;
     if (const char* m = std::getenv("B200SEED_DOUBLET_ORDER"))
@@ -1236,14 +1238,14 @@ int host_submit(b200seed_handle* h, cudaStream_t s, HostEvent& e) {
     const bool diag = e.h_params_diag != nullptr;
     const bool want_params = e.h_params != nullptr || diag;
     const uint32_t n_sp = e.n_sp, n_meas = e.n_meas, seed_capacity = e.seed_capacity;
-    // Parameters: only phi, theta, q/p and var(q/p) are computed on the device (16 bytes per seed);
-    // the records are completed on the host from the caller's own measurement columns, which then
-    // never travel to the device (B200SEED_PCIE_PARAMS=records: the records themselves, as before).
-    static const bool compact_ok = [] {
-        const char* m = std::getenv("B200SEED_PCIE_PARAMS");
-        return !(m && !std::strcmp(m, "records"));
-    }();
-    e.compact = want_params && compact_ok;
+    // B200SEED_PCIE_PARAMS=compact: only phi, theta, q/p and var(q/p) are computed on the device
+    // (16 bytes per seed); the records are completed on the host from the caller's own measurement
+    // columns, which then never travel to the device. Less than half the PCIe bytes, but the host
+    // pays ~0.9 ms of cache-cold gathers per 10k-particle event: on one GPU 3.67k instead of 3.76k
+    // events/s (3.90k if the expansion cost nothing) — for hosts whose D->H rate is the limit, not
+    // the default.
+    // (read at b200seed_create)
+    e.compact = want_params && h->pcie_compact;
 
     // device staging: inputs | outputs | workspace
     size_t o = 0;
