@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """End-to-end rate of b200seed_pool_process (8 workers, diagonal records delivered) — run it under
-B200SEED_PCIE_PARAMS=records / default to compare the two PCIe forms of the parameters.
+B200SEED_PCIE_PARAMS=compact / default (records) to compare the two PCIe forms of the parameters.
 usage: e2e_forms.py [events] [particles]"""
 import os, sys, time
 import numpy as np, torch
