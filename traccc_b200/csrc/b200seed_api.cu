@@ -892,7 +892,15 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
                 at1.val.programmaticStreamSerializationAllowed = h->pdl ? 1 : 0;
                 lc.attrs = &at1;
                 lc.numAttrs = 1;
-                CUDA_TRY(h, cudaLaunchKernelEx(&lc, k_doublets<3>, h->dev, a));
+                cudaError_t le = cudaLaunchKernelEx(&lc, k_doublets<3>, h->dev, a);
+                if (le != cudaSuccess && h->pdl) {
+                    // a driver without programmatic dependent launch: plain stream order from now on
+                    (void)cudaGetLastError();
+                    h->pdl = 0;
+                    at1.val.programmaticStreamSerializationAllowed = 0;
+                    le = cudaLaunchKernelEx(&lc, k_doublets<3>, h->dev, a);
+                }
+                CUDA_TRY(h, le);
             }
         } else {
             TileArgs ta{};
