@@ -784,6 +784,52 @@ __host__ __device__ inline uint32_t doublet_smem_words(uint32_t cap_b, uint32_t 
     return cap_b + 3u * cap_t;
 }
 
+// One LANE decides whether middle m has any doublet partner on its scarce side (lower == true:
+// a bottom partner in the rows up to its own; else a top partner from its own row upwards): the
+// same windows, cells and cuts as the warp-wide scan of k_doublets, one candidate after the
+// other. 32 middles per warp at a time instead of one: the middles of these classes almost never
+// have one (barrel layers without a layer below / above them), and a warp-wide pass over a
+// handful of candidates is all latency. n_pairs: the middle's contribution to pair_tests.
+__device__ __forceinline__ bool sided_has_partner(const DevCfg& cfg, const DoubletArgs& a, const CellGrid& g,
+                                                  const uint32_t m, const bool lower, const bool bounded,
+                                                  uint32_t& n_pairs, uint32_t& n_visited) {
+    const float4 M = __ldg(a.sp4 + m);
+    NeighbourWalk walk;
+    walk.init(cfg, __ldg(a.sorted_bin + m), M.z);
+    n_pairs = 0;
+    for (uint32_t q = 0; q < walk.nq; ++q) {
+        const uint32_t b = walk.bin(cfg, q);
+        n_pairs += __ldg(a.bin_off + b + 1) - __ldg(a.bin_off + b);
+    }
+    const float er = 1e-2f + 1e-5f * (M.w + absf(cfg.deltaRMax));
+    const uint32_t row_lo = cell_row(g, M.w - cfg.deltaRMax - er);
+    const uint32_t row_hi = cell_row(g, M.w + cfg.deltaRMax + er);
+    const uint32_t rowM = cell_row(g, M.w);
+    const uint32_t r0 = lower ? row_lo : (rowM > row_lo ? rowM : row_lo);
+    const uint32_t r1 = lower ? (rowM < row_hi ? rowM : row_hi) : row_hi;
+    const int want = lower ? 1 : 2;
+    for (uint32_t row = r0; row <= r1; ++row) {
+        float L, U;
+        if (!cell_row_window(cfg, g, M.w, M.z, row, L, U)) continue;
+        for (uint32_t q = 0; q < walk.nq; ++q) {
+            const uint32_t zb = walk.zbin(q);
+            const uint32_t base = walk.bin(cfg, q) * g.CPB + row * g.NZc;
+            const uint32_t lo = __ldg(a.cell_off + base + cell_z(g, zb, L));
+            const uint32_t hi = __ldg(a.cell_off + base + cell_z(g, zb, U) + 1u);
+            n_visited += hi - lo;
+            for (uint32_t c = lo; c < hi; ++c) {
+                const float4 P = __ldg(a.csp4 + c);
+                if (doublet_stage1(cfg, M.w, M.z, P.w, P.z) != want) continue;
+                int d = bounded ? doublet_stage2_fast_bounded(cfg, M.x, M.y, P.x, P.y)
+                                : doublet_stage2_fast(cfg, M.x, M.y, P.x, P.y);
+                if (d == 2) d = doublet_stage2(cfg, M.x, M.y, P.x, P.y) ? 1 : 0;
+                if (d != 0) return true;
+            }
+        }
+    }
+    return false;
+}
+
 // Arena records. The order of a mid-bottom list is arbitrary (nothing downstream depends on
 // it; the parity tests sort it by canon_key). Mid-top lists are sorted by cotTheta so that
 // k_triplets can binary-search the scattering window of each mid-bottom doublet, and carry
@@ -842,12 +888,50 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
         if (SIDES) asm volatile("griddepcontrol.wait;" ::: "memory");  // (see the end of the kernel)
         return;
     }
+    // MODE 3: the middles come in batches of 32, one per lane for the pre-screening of the scarce
+    // side; the (rare) survivors are then processed one after the other like any middle
+    uint32_t alive_mask = 0, batch_entry = 0;
     while (true) {
         uint32_t m = 0;
+        if (SIDES) {
+            bool exhausted = false;
+            while (alive_mask == 0u) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&a.ctrl->ticket_e, 32u);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= n_work) {
+                    exhausted = true;
+                    break;
+                }
+                bool alive = false;
+                uint32_t seen = 0;
+                batch_entry = 0u;
+                if (base + lane < n_work) {
+                    batch_entry = __ldg(a.mid_order + (n_valid - n_work) + base + lane);
+                    const uint32_t mm = batch_entry & ~MID_LOWER_SCARCE;
+                    uint32_t np = 0;
+                    alive = !(cfg.deltaRMin >= 0.f) ||
+                            sided_has_partner(cfg, a, g, mm, (batch_entry & MID_LOWER_SCARCE) != 0u, bounded, np, seen);
+                    if (!alive) {  // cannot seed (seed_finding.cpp:85-95): what the full scan would leave
+                        pairs += np;
+                        a.cnt_b[mm] = 0u, a.cnt_t[mm] = 0u, a.off_b[mm] = 0u, a.off_t[mm] = 0u;
+                        a.seed_cnt[mm] = 0u;
+                    }
+                }
+                alive_mask = __ballot_sync(0xffffffffu, alive);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) seen += __shfl_xor_sync(0xffffffffu, seen, o);
+                if (lane == 0) visited += seen;
+            }
+            if (exhausted) break;
+            const uint32_t src = __ffs(int(alive_mask)) - 1u;
+            alive_mask &= alive_mask - 1u;
+            m = __shfl_sync(0xffffffffu, batch_entry, src);
+        } else {
         if (lane == 0)
-            m = atomicAdd(SPILL ? &a.ctrl->ticket_s
-                                : (LISTED ? &a.ctrl->ticket_f : (SIDES ? &a.ctrl->ticket_e : &a.ctrl->ticket_d)), 1u);
+            m = atomicAdd(SPILL ? &a.ctrl->ticket_s : (LISTED ? &a.ctrl->ticket_f : &a.ctrl->ticket_d), 1u);
         m = __shfl_sync(0xffffffffu, m, 0);
+        }
 #ifdef B200_TAIL_PROBE
         if (MODE == 0 && lane == 0) {
             const uint32_t w = blockIdx.x * WARPS_PER_CTA + warp;
@@ -858,13 +942,12 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
         }
         const long long probe_c0 = clock64();
 #endif
-        if (m >= n_work) break;
+        if (!SIDES && m >= n_work) break;
         if (SPILL) m = a.spill_list[m];
         if (LISTED) m = a.fallback_list[m];
         if (MODE == 0 && a.mid_order) m = __ldg(a.mid_order + m);  // longest middles first
         bool lower_scarce = false;
         if (SIDES) {
-            m = __ldg(a.mid_order + (n_valid - n_work) + m);
             lower_scarce = (m & MID_LOWER_SCARCE) != 0u;
             m &= ~MID_LOWER_SCARCE;
         }
