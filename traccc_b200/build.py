@@ -7,7 +7,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "b200seed_api.cu")
-DEPS = [SRC, os.path.join(_HERE, "csrc", "seed_kernels.cuh"), os.path.join(_HERE, "csrc", "seed_math.cuh"),
+DEPS = [SRC, os.path.join(_HERE, "csrc", "seed_kernels.cuh"), os.path.join(_HERE, "csrc", "seed_math.cuh"), os.path.join(_HERE, "csrc", "seed_lanes.cuh"),
         os.path.join(_HERE, "csrc", "seed_tile.cuh"),
         os.path.join(_HERE, "..", "include", "b200seed.h")]
 OUT = os.path.join(_HERE, "libb200seed.so")

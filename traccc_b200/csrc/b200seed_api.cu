@@ -23,6 +23,7 @@
 #include "seed_kernels.cuh"
 #include "seed_tile.cuh"
 #include "seed_pool.cuh"
+#include "seed_lanes.cuh"
 
 using namespace b200seed;
 
@@ -84,6 +85,9 @@ struct b200seed_handle {
     // triplet search of the light middles: 0 = k_triplets for all (default: faster),
     // 1 = k_triplets_pool (several middles per warp); B200SEED_TRIPLETS=warp|pool
     int triplet_pool = 0;
+    // the light middles go to k_triplets_lanes (one middle per lane), launched as a programmatic
+    // dependent of k_triplets; B200SEED_TRIPLETS=warp: all middles in k_triplets
+    int triplet_lanes = 1;
     uint32_t group_max = 0;      // 0 = automatic (by event size)
     float group_zspan_mm = 0.f;  // 0 = default
     int num_sms = 148;
@@ -575,7 +579,10 @@ int b200seed_create(const b200seed_finder_cfg* finder, const b200seed_grid_cfg* 
         else if (!std::strcmp(m, "ldgsts")) h->doublet_mode = 1;
         else h->doublet_mode = 2;  // "warp" / "legacy"
     }
-    if (const char* m = std::getenv("B200SEED_TRIPLETS")) h->triplet_pool = std::strcmp(m, "pool") == 0;
+    if (const char* m = std::getenv("B200SEED_TRIPLETS")) {
+        h->triplet_pool = std::strcmp(m, "pool") == 0;
+        h->triplet_lanes = std::strcmp(m, "lanes") == 0;
+    }
     cudaFuncSetAttribute(k_triplets_pool, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          h->smem_optin - 1024);
     if (const char* m = std::getenv("B200SEED_GROUP_MAX")) h->group_max = uint32_t(std::atoi(m));
@@ -736,7 +743,7 @@ int b200seed_launches_per_event(const b200seed_handle* h, int with_params) {
     // (events of at least 32k spacepoints: + k_doublets<3> for the middles with a scarce side)
     const bool sides = h && h->doublet_mode == 2 && h->ordered_tickets && h->split_sides && h->finder.deltaRMin >= 0.f;
     const int doublets = (h && h->doublet_mode != 2) ? 3 : (sides ? 3 : 2);
-    const int triplets = (h && h->triplet_pool) ? 2 : 1;
+    const int triplets = (h && (h->triplet_pool || h->triplet_lanes)) ? 2 : 1;  // (lanes: not for > 80k spacepoints)
     return 4 + doublets + triplets + (with_params ? 1 : 0);
 }
 
@@ -969,7 +976,8 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
         const uint32_t max_grid = uint32_t(h->num_sms) * (32 / WARPS_PER_CTA) * B200_TRIPLET_GRID_X2 / 2;
         if (grid > max_grid) grid = max_grid;
         KernelTimer t(h, s, "triplets");
-        a.heavy_only = h->triplet_pool ? 1u : 0u;
+        const bool lanes = h->triplet_lanes && !h->triplet_pool && !dense;
+        a.heavy_only = (h->triplet_pool || lanes) ? 1u : 0u;
         if (dense)
             k_triplets<true><<<grid, WARPS_PER_CTA * 32, smem, s>>>(h->dev, a);
         else
@@ -981,6 +989,30 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
             const uint32_t pmax = uint32_t(h->num_sms) * B200_POOL_MIN_CTAS;
             if (pgrid > pmax) pgrid = pmax;
             k_triplets_pool<<<pgrid, POOL_WARPS * 32, psmem, s>>>(h->dev, a);
+        }
+        if (lanes) {
+            // the light middles, one per lane; no data dependence on k_triplets (disjoint middles):
+            // launched as a programmatic dependent, its CTAs fill that launch's tail
+            cudaLaunchConfig_t lc{};
+            uint32_t lgrid = (n_sp / 32u + LANES_WARPS) / LANES_WARPS;
+            const uint32_t lmax = uint32_t(h->num_sms) * 4u;
+            lc.gridDim = dim3(lgrid < lmax ? lgrid : lmax);
+            lc.blockDim = dim3(LANES_WARPS * 32);
+            lc.dynamicSmemBytes = lanes_smem_bytes();
+            lc.stream = s;
+            cudaLaunchAttribute at1{};
+            at1.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at1.val.programmaticStreamSerializationAllowed = h->pdl ? 1 : 0;
+            lc.attrs = &at1;
+            lc.numAttrs = 1;
+            cudaError_t le = cudaLaunchKernelEx(&lc, k_triplets_lanes, h->dev, a);
+            if (le != cudaSuccess && h->pdl) {
+                (void)cudaGetLastError();
+                h->pdl = 0;
+                at1.val.programmaticStreamSerializationAllowed = 0;
+                le = cudaLaunchKernelEx(&lc, k_triplets_lanes, h->dev, a);
+            }
+            CUDA_TRY(h, le);
         }
 
 

@@ -1751,6 +1751,8 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
         s_tests = s_visited = 0ull;
     }
     work_prefix(a.ctrl->n_cls, s_pre);
+    // (k_triplets_lanes, launched behind this kernel as a programmatic dependent, shares no data with it)
+    asm volatile("griddepcontrol.launch_dependents;");
     __syncthreads();
     const uint32_t n_valid = a.ctrl->n_valid;
     const uint32_t K = cfg.maxSeedsPerSpM;
