@@ -977,7 +977,7 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
         if (grid > max_grid) grid = max_grid;
         KernelTimer t(h, s, "triplets");
         const bool lanes = h->triplet_lanes && !h->triplet_pool && !dense;
-        a.heavy_only = (h->triplet_pool || lanes) ? 1u : 0u;
+        a.heavy_only = h->triplet_pool ? WORK_HEAVY_CLASSES : (lanes ? LANES_FIRST_CLASS : 0u);
         if (dense)
             k_triplets<true><<<grid, WARPS_PER_CTA * 32, smem, s>>>(h->dev, a);
         else

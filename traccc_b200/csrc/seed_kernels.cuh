@@ -85,6 +85,7 @@ __host__ __device__ inline bool pool_is_light(uint32_t nB, uint32_t nT) {
 // spends on a middle follows its number of mid-bottom rows). Classes 0-3: the heavy middles
 // (see pool_is_light), 4-7: the light ones.
 constexpr uint32_t WORK_CLASSES = 8, WORK_HEAVY_CLASSES = 4;
+constexpr uint32_t LANES_FIRST_CLASS = 5;  // light middles with fewer than 32 mid-bottom rows
 __host__ __device__ inline uint32_t work_class(uint32_t nB, uint32_t nT) {
     if (!pool_is_light(nB, nT)) return (nB < 192u ? 1u : 0u) + (nB < 96u ? 1u : 0u) + (nB < 48u ? 1u : 0u);
     return 4u + (nB < 32u ? 1u : 0u) + (nB < 16u ? 1u : 0u) + (nB < 8u ? 1u : 0u);
@@ -1353,7 +1354,9 @@ struct TripletArgs {
     uint32_t list_cap;      // triplets of one 32-row block kept in shared memory
     const uint32_t* active_list;  // work list written by k_doublets (heavy first)
     uint32_t n_sp;
-    uint32_t heavy_only;          // 1: the light middles are k_triplets_pool's
+    uint32_t heavy_only;          // != 0: k_triplets takes the first `heavy_only` work classes only
+                                  // (WORK_HEAVY_CLASSES: the rest is k_triplets_pool's; LANES_FIRST_CLASS:
+                                  // the rest is k_triplets_lanes')
     DoubletRec* scratch_t;        // the mid-top arena again, writable: its unused tail holds the
                                   // triplets of a row that outgrows the shared-memory list
     uint32_t max_doublets;
@@ -1761,7 +1764,7 @@ k_triplets(const DevCfg cfg, const TripletArgs a) {
 
     // Work items: the active middles k_doublets listed, longest jobs first (see work_class),
     // middles without work never drawn.
-    const uint32_t n_work = s_pre[a.heavy_only ? WORK_HEAVY_CLASSES : WORK_CLASSES];
+    const uint32_t n_work = s_pre[a.heavy_only ? a.heavy_only : WORK_CLASSES];
     while (true) {
         uint32_t m = 0;
         if (lane == 0) m = atomicAdd(&a.ctrl->ticket, 1u);

@@ -1,7 +1,7 @@
 // b200seed — triplet search for the LIGHT middles, one middle per lane.
 //
 // k_triplets gives every middle a warp. For the light middles (few mid-bottom rows, at most 64
-// mid-tops: work classes WORK_HEAVY_CLASSES .. WORK_CLASSES-1) that is one long chain of dependent
+// mid-tops, fewer than 32 rows: work classes LANES_FIRST_CLASS .. WORK_CLASSES-1) that is one long chain of dependent
 // loads and warp-wide phases over a handful of elements — 8.5 us even for a middle with six
 // bottoms and four tops (profiles/r02_phases_and_tails.md). Here a warp draws 32 of them and
 // every LANE runs the reference's loop nest for its own middle, serially
@@ -49,7 +49,7 @@ k_triplets_lanes(const __grid_constant__ DevCfg cfg, const __grid_constant__ Tri
     __syncthreads();
     const uint32_t n_valid = a.ctrl->n_valid;
     const uint32_t K = cfg.maxSeedsPerSpM;
-    const uint32_t first = s_pre[WORK_HEAVY_CLASSES], n_items = s_pre[WORK_CLASSES] - first;
+    const uint32_t first = s_pre[LANES_FIRST_CLASS], n_items = s_pre[WORK_CLASSES] - first;
     uint32_t acc_trip = 0;
     unsigned long long acc_tests = 0ull, acc_visited = 0ull;
 
