@@ -536,6 +536,24 @@ def test_parity_pooled_triplet_kernel(monkeypatch):
 
 
 @pytest.mark.parametrize("pcie", ["records", "compact"])
+def test_parity_lane_triplet_kernel(monkeypatch):
+    """k_triplets_lanes (one light middle per lane, the reference's loop nest run serially;
+    B200SEED_TRIPLETS=lanes, off by default — measured slower) against the oracle: triplet sets
+    with curvature / weight after the bonus, seeds, parameters; default and tight-filter
+    configurations, maxSeedsPerSpM = 12, non-zero variances, rows that outgrow the lane's buffer."""
+    from traccc_b200 import seedfilter_config, seedfinder_config, spacepoint_grid_config, toy_detector
+    monkeypatch.setenv("B200SEED_TRIPLETS", "lanes")
+    _check_event(toy_detector.generate_event(1000, 3))
+    _check_event(toy_detector.generate_event(1000, 4, shuffle=True, variances=0.05))
+    _check_event(toy_detector.generate_event(3000, 5, eta_max=1.0))
+    finder = seedfinder_config(maxSeedsPerSpM=12)
+    _check_event(toy_detector.generate_event(1500, 6), finder=finder, grid=spacepoint_grid_config(finder))
+    _check_event(_rays_event(n_rays=12, n_tops=20, seed=8))
+    got, _ = _check_event(toy_detector.generate_event(10000, 31), dump=False)
+    assert got["counters"]["overflow"] == 0
+
+
+@pytest.mark.parametrize("pcie", ["records", "compact"])
 def test_diagonal_parameter_records(pcie, monkeypatch):
     """b200seed_event_io::params_diag: the parameters leave the device as 56-byte diagonal
     records (a third of the PCIe bytes); b200seed_expand_params restores the full records,

@@ -85,9 +85,11 @@ struct b200seed_handle {
     // triplet search of the light middles: 0 = k_triplets for all (default: faster),
     // 1 = k_triplets_pool (several middles per warp); B200SEED_TRIPLETS=warp|pool
     int triplet_pool = 0;
-    // the light middles go to k_triplets_lanes (one middle per lane), launched as a programmatic
-    // dependent of k_triplets; B200SEED_TRIPLETS=warp: all middles in k_triplets
-    int triplet_lanes = 1;
+    // B200SEED_TRIPLETS=lanes: the light middles with fewer than 32 rows go to k_triplets_lanes (one
+    // middle per lane), launched as a programmatic dependent of k_triplets. Bit-identical, measured
+    // slower (a lane's serial program over <= 31 rows is ~450 us of dependent loads and there are
+    // only ~300 such warps per event: triplet stage 110 -> 546 us): off by default.
+    int triplet_lanes = 0;
     uint32_t group_max = 0;      // 0 = automatic (by event size)
     float group_zspan_mm = 0.f;  // 0 = default
     int num_sms = 148;

@@ -1,4 +1,9 @@
-// b200seed — triplet search for the LIGHT middles, one middle per lane.
+// b200seed — triplet search for the LIGHT middles, one middle per lane. EXPERIMENTAL
+// (B200SEED_TRIPLETS=lanes; bit-identical to k_triplets, test_parity_lane_triplet_kernel): the
+// pattern that pays in k_doublets<3> — 32 short latency chains per warp instead of one — does not
+// pay here: a lane's program over up to 31 mid-bottom rows is ~450 us of dependent loads, and an
+// event has only ~300 such warps, so the launch is one long tail (triplet stage 110 -> 546 us on the
+// 10k-particle event; with the 32+-row light class included: 948 us).
 //
 // k_triplets gives every middle a warp. For the light middles (few mid-bottom rows, at most 64
 // mid-tops, fewer than 32 rows: work classes LANES_FIRST_CLASS .. WORK_CLASSES-1) that is one long chain of dependent
