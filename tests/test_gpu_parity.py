@@ -535,7 +535,6 @@ def test_parity_pooled_triplet_kernel(monkeypatch):
     _check_event(toy_detector.generate_event(10000, 43), dump=False)
 
 
-@pytest.mark.parametrize("pcie", ["records", "compact"])
 def test_parity_lane_triplet_kernel(monkeypatch):
     """k_triplets_lanes (one light middle per lane, the reference's loop nest run serially;
     B200SEED_TRIPLETS=lanes, off by default — measured slower) against the oracle: triplet sets
