@@ -892,7 +892,9 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
                 // no data dependence on k_doublets<0> (disjoint middles, shared atomics only): its
                 // CTAs start as soon as that launch frees slots, i.e. they fill its tail
                 cudaLaunchConfig_t lc{};
-                lc.gridDim = dim3(grid_s);
+                // a warp takes 32 middles at a time: no more CTAs than there can be batches
+                const uint32_t grid_e = n_sp / (32u * WARPS_PER_CTA) + 1u;
+                lc.gridDim = dim3(grid_e < grid_s ? grid_e : grid_s);
                 lc.blockDim = dim3(WARPS_PER_CTA * 32);
                 lc.dynamicSmemBytes = smem;
                 lc.stream = s;

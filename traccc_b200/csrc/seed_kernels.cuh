@@ -886,7 +886,7 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
                                   : (LISTED ? a.ctrl->n_fallback
                                             : (SIDES ? n_valid - a.ctrl->n_main : a.ctrl->n_main));
     if ((SPILL || LISTED || SIDES) && n_work == 0u) {  // the usual case: no ticket traffic at all
-        if (SIDES) asm volatile("griddepcontrol.wait;" ::: "memory");  // (see the end of the kernel)
+        if (SIDES && blockIdx.x == 0) asm volatile("griddepcontrol.wait;" ::: "memory");  // (see the end of the kernel)
         return;
     }
     // MODE 3: the middles come in batches of 32, one per lane for the pre-screening of the scarce
@@ -1328,7 +1328,8 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
     // needs nothing from it — but the launches behind it do, and they only wait for this one: it
     // must not complete first (PTX: a grid launched as a dependent has to execute
     // griddepcontrol.wait for the stream order to hold).
-    if (SIDES) asm volatile("griddepcontrol.wait;" ::: "memory");
+    // (one CTA is enough to keep the grid from completing; the others give their slots back)
+    if (SIDES && blockIdx.x == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------
