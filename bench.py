@@ -431,20 +431,27 @@ def extras(args, rank, world, local, dev, finder, grid, filt, events):
     evs = [rotated(events[i % len(events)], angles[i]) for i in mine]
     pool = seeding.EventPool(finder, grid, filt, device=local, n_workers=max(1, args.pool_workers))
     CH = 64
-    n_seeds, chk, secs = 0, 0, 0.0
-    for c0 in range(0, len(evs), CH):
-        ios, outs = pool.make_batch(evs[c0:c0 + CH], diag=True)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        pool.process(ios)
-        secs += time.perf_counter() - t0
-        for io, o in zip(ios, outs):
-            assert io.counters.overflow == 0
-            n = int(io.n_seeds)
-            n_seeds += n
-            chk += int(o["middle"][:n].numpy().astype(np.int64).sum())
-        del ios, outs
-    out["_stream"] = (len(evs), n_seeds, chk, secs)
+    # two passes over the stream, the faster one counts (a pass is 0.3 s of wall time on a shared
+    # host: single passes were seen anywhere between 1.3k and 3.4k events/s on the same build)
+    passes = []
+    for _ in range(2):
+        n_seeds, chk, secs = 0, 0, 0.0
+        for c0 in range(0, len(evs), CH):
+            ios, outs = pool.make_batch(evs[c0:c0 + CH], diag=True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            pool.process(ios)
+            secs += time.perf_counter() - t0
+            for io, o in zip(ios, outs):
+                assert io.counters.overflow == 0
+                n = int(io.n_seeds)
+                n_seeds += n
+                chk += int(o["middle"][:n].numpy().astype(np.int64).sum())
+            del ios, outs
+        passes.append((len(evs), n_seeds, chk, secs))
+    assert passes[0][1:3] == passes[1][1:3]
+    out["_stream"] = min(passes, key=lambda p_: p_[3])
+    out["_stream_passes_s"] = [p_[3] for p_ in passes]
     return out
 
 
@@ -745,6 +752,7 @@ def run_b200(args):
         del pool, ios, outs
         ex = extras(args, rank, world, local, dev, finder, grid, filt, events)
         n_ev, n_sd, chk, secs = ex.pop("_stream")
+        pass_s = ex.pop("_stream_passes_s")
         t = torch.tensor([float(n_ev), float(n_sd), float(chk)], dtype=torch.float64, device=dev)
         tm = torch.tensor([secs], dtype=torch.float64, device=dev)
         if world > 1:
@@ -757,7 +765,9 @@ def run_b200(args):
                             f"random rotations about the beam axis), event i -> rank i mod {world}, host buffers "
                             "through b200seed_pool_process in calls of 64 events",
                 "events": int(t[0].item()), "events_per_s": float(t[0].item() / tm[0].item()),
-                "seconds_max_over_ranks": float(tm[0].item()), "seeds": int(t[1].item()),
+                "seconds_max_over_ranks": float(tm[0].item()),
+                "passes": "two, the faster one counts; seconds on rank 0: " + ", ".join(f"{x:.3f}" for x in pass_s),
+                "seeds": int(t[1].item()),
                 "checksum_middle_indices": int(t[2].item())}
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ----
