@@ -152,6 +152,15 @@ typedef struct b200seed_seed_params {
     float phi, theta, qop, var_qop;
 } b200seed_seed_params;
 
+/* A parameter record without the five variances that are constants of the b200seed_tpe_cfg and
+ * without the time (zero): what the host-buffer entry points move over PCIe (32 bytes instead of
+ * 56 / 176). b200seed_expand_packed_params() restores the records on the host — a sequential
+ * copy, no look-ups. */
+typedef struct b200seed_bound_params_packed {
+    uint64_t surface_link;
+    float loc0, loc1, phi, theta, qop, var_qop;
+} b200seed_bound_params_packed;
+
 /* Device-side counters of one event. Written by b200seed_run when d_counters != NULL;
  * they replace the reference's D->H size reads (triplet_seeding_algorithm.cpp:64-224)
  * for logging and for the parity tests. */
@@ -321,6 +330,18 @@ void b200seed_expand_seed_params(const b200seed_handle* h, uint32_t n, const uin
                                  const b200seed_seed_params* in, const uint32_t* sp_meas_index_1,
                                  const float* meas_local, const uint64_t* meas_surface,
                                  b200seed_bound_params* out_full, b200seed_bound_params_diag* out_diag);
+/* b200seed_estimate_params with the 32-byte packed output records (homogeneous field). */
+int b200seed_estimate_params_packed(b200seed_handle* h, void* stream, const uint32_t* d_n_seeds,
+                                    uint32_t seed_capacity, const uint32_t* d_bottom,
+                                    const uint32_t* d_middle, const uint32_t* d_top,
+                                    const float* d_xyz, const uint32_t* d_sp_meas_index_1,
+                                    const float* d_meas_local, const uint64_t* d_meas_surface,
+                                    const float bfield[3], b200seed_bound_params_packed* d_params);
+/* HOST helper: n packed records -> full and / or diagonal records (either may be NULL), exactly
+ * what b200seed_estimate_params / _diag would have written. */
+void b200seed_expand_packed_params(const b200seed_handle* h, uint32_t n,
+                                   const b200seed_bound_params_packed* in,
+                                   b200seed_bound_params* out_full, b200seed_bound_params_diag* out_diag);
 /* HOST helper: n diagonal records -> full 176-byte records (off-diagonal elements zero). */
 void b200seed_expand_params(const b200seed_bound_params_diag* in, uint32_t n,
                             b200seed_bound_params* out);

@@ -107,6 +107,7 @@ struct b200seed_handle {
     void* h_compact = nullptr;
     size_t h_compact_bytes = 0;
     bool pcie_compact = false;  // B200SEED_PCIE_PARAMS=compact
+    bool pcie_packed = true;    // 32-byte packed records over PCIe (B200SEED_PCIE_PARAMS=records: off)
     // OR of the overflow masks of the events run on this handle since the last
     // b200seed_check_overflow: one pinned, device-mapped word that k_seed_gather writes only when
     // an event was truncated (so a caller that passes d_counters == NULL still learns about it)
@@ -571,7 +572,10 @@ int b200seed_create(const b200seed_finder_cfg* finder, const b200seed_grid_cfg* 
                          h->smem_optin - 1024);
     cudaFuncSetAttribute(k_doublets_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          h->smem_optin - 1024);
-    if (const char* m = std::getenv("B200SEED_PCIE_PARAMS")) h->pcie_compact = !std::strcmp(m, "compact");
+    if (const char* m = std::getenv("B200SEED_PCIE_PARAMS")) {
+        h->pcie_compact = !std::strcmp(m, "compact");
+        h->pcie_packed = !std::strcmp(m, "packed");
+    }
     if (const char* m = std::getenv("B200SEED_DOUBLET_SIDES")) h->split_sides = std::strcmp(m, "0") != 0;
     if (const char* m = std::getenv("B200SEED_PDL")) h->pdl = std::strcmp(m, "0") != 0;
     if (const char* m = std::getenv("B200SEED_DOUBLET_ORDER"))
@@ -1114,12 +1118,13 @@ int estimate_impl(b200seed_handle* h, void* stream, const uint32_t* d_n_seeds,
                   const float* d_meas_local, const uint64_t* d_meas_surface, const float bfield[3],
                   const b200seed_field_grid& fg, b200seed_bound_params* d_params,
                   b200seed_bound_params_diag* d_params_diag = nullptr,
-                  b200seed_seed_params* d_params_compact = nullptr) {
+                  b200seed_seed_params* d_params_compact = nullptr,
+                  b200seed_bound_params_packed* d_params_packed = nullptr) {
     if (!h) return B200SEED_EINVAL;
     if (seed_capacity == 0) return B200SEED_OK;
     if (!d_xyz) return B200SEED_OK;  // no spacepoints => no seeds (…estimation_algorithm.cpp:49-51)
     if (!d_n_seeds || !d_bottom || !d_middle || !d_top || !bfield ||
-        (!d_params && !d_params_diag && !d_params_compact))
+        (!d_params && !d_params_diag && !d_params_compact && !d_params_packed))
         return fail(h, B200SEED_EINVAL, "b200seed_estimate_params: null pointer");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     CUDA_TRY(h, cudaSetDevice(h->device));
@@ -1128,7 +1133,7 @@ int estimate_impl(b200seed_handle* h, void* stream, const uint32_t* d_n_seeds,
         k_estimate_params<<<(seed_capacity + 127) / 128, 128, 0, s>>>(
             h->tpe, d_n_seeds, seed_capacity, d_bottom, d_middle, d_top, d_xyz, d_sp_meas_index_1,
             d_meas_local, d_meas_surface, bfield[0], bfield[1], bfield[2], fg, d_params, d_params_diag,
-            d_params_compact);
+            d_params_compact, d_params_packed);
     }
     CUDA_TRY(h, cudaGetLastError());
     return B200SEED_OK;
@@ -1167,6 +1172,47 @@ int b200seed_estimate_params_compact(b200seed_handle* h, void* stream, const uin
     b200seed_field_grid none{};
     return estimate_impl(h, stream, d_n_seeds, seed_capacity, d_bottom, d_middle, d_top, d_xyz, nullptr,
                          nullptr, nullptr, bfield, none, nullptr, nullptr, d_params);
+}
+
+int b200seed_estimate_params_packed(b200seed_handle* h, void* stream, const uint32_t* d_n_seeds,
+                                    uint32_t seed_capacity, const uint32_t* d_bottom,
+                                    const uint32_t* d_middle, const uint32_t* d_top,
+                                    const float* d_xyz, const uint32_t* d_sp_meas_index_1,
+                                    const float* d_meas_local, const uint64_t* d_meas_surface,
+                                    const float bfield[3], b200seed_bound_params_packed* d_params) {
+    b200seed_field_grid none{};
+    return estimate_impl(h, stream, d_n_seeds, seed_capacity, d_bottom, d_middle, d_top, d_xyz,
+                         d_sp_meas_index_1, d_meas_local, d_meas_surface, bfield, none, nullptr, nullptr,
+                         nullptr, d_params);
+}
+
+void b200seed_expand_packed_params(const b200seed_handle* h, uint32_t n,
+                                   const b200seed_bound_params_packed* in,
+                                   b200seed_bound_params* out_full, b200seed_bound_params_diag* out_diag) {
+    if (!h || !in) return;
+    // the variances that do not depend on the seed: the same two float multiplications as in
+    // k_estimate_params (track_params_estimation.cpp:64-86)
+    float var[6];
+    for (int j = 0; j < 6; ++j) {
+        float v = h->tpe.initial_sigma[j] * h->tpe.initial_sigma[j];
+        v *= h->tpe.initial_inflation[j];
+        var[j] = v;
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        const b200seed_bound_params_packed p = in[i];
+        const float vec[6] = {p.loc0, p.loc1, p.phi, p.theta, p.qop, 0.f};
+        if (out_diag) {
+            b200seed_bound_params_diag& o = out_diag[i];
+            o.surface_link = p.surface_link;
+            for (int k = 0; k < 6; ++k) o.vec[k] = vec[k], o.cov_diag[k] = (k == 4) ? p.var_qop : var[k];
+        }
+        if (out_full) {
+            b200seed_bound_params& o = out_full[i];
+            std::memset(&o, 0, sizeof(o));
+            o.surface_link = p.surface_link;
+            for (int k = 0; k < 6; ++k) o.vec[k] = vec[k], o.cov[k * 7] = (k == 4) ? p.var_qop : var[k];
+        }
+    }
 }
 
 void b200seed_expand_seed_params(const b200seed_handle* h, uint32_t n, const uint32_t* bottom,
@@ -1258,6 +1304,7 @@ struct HostEvent {
     float* d_q = nullptr;
     b200seed_bound_params* d_p = nullptr;
     bool compact = false;  // the parameters cross PCIe as b200seed_seed_params
+    bool packed = false;   // ... as b200seed_bound_params_packed
     const uint32_t* h_bot_stage = nullptr;  // bottom indices on the host (for host_expand)
     bool submitted = false;
 };
@@ -1290,6 +1337,9 @@ int host_submit(b200seed_handle* h, cudaStream_t s, HostEvent& e) {
     // the default.
     // (read at b200seed_create)
     e.compact = want_params && h->pcie_compact;
+    // default: 32-byte packed records (no constant variances), completed on the host by a
+    // sequential copy (b200seed_expand_packed_params)
+    e.packed = want_params && !e.compact && h->pcie_packed;
 
     // device staging: inputs | outputs | workspace
     size_t o = 0;
@@ -1305,8 +1355,9 @@ int host_submit(b200seed_handle* h, cudaStream_t s, HostEvent& e) {
                  o_t = take(size_t(seed_capacity) * 4), o_q = take(size_t(seed_capacity) * 4),
                  o_p = take(want_params ? size_t(seed_capacity) *
                                               (e.compact ? sizeof(b200seed_seed_params)
-                                                         : (diag ? sizeof(b200seed_bound_params_diag)
-                                                                 : sizeof(b200seed_bound_params)))
+                                               : e.packed ? sizeof(b200seed_bound_params_packed)
+                                                          : (diag ? sizeof(b200seed_bound_params_diag)
+                                                                  : sizeof(b200seed_bound_params)))
                                         : 0),
                  o_n = take(256), o_c = take(sizeof(b200seed_counters));
     const size_t ws_bytes = b200seed_workspace_bytes(h, n_sp);
@@ -1320,8 +1371,9 @@ int host_submit(b200seed_handle* h, cudaStream_t s, HostEvent& e) {
         h->d_stage_bytes = want;
     }
     if (!h->h_pinned) CUDA_TRY(h, cudaMallocHost(&h->h_pinned, 256));
-    if (e.compact) {
-        const size_t need = size_t(seed_capacity) * (sizeof(b200seed_seed_params) + 4);
+    if (e.compact || e.packed) {
+        const size_t need = size_t(seed_capacity) * (e.packed ? sizeof(b200seed_bound_params_packed)
+                                                              : sizeof(b200seed_seed_params) + 4);
         if (need > h->h_compact_bytes) {
             if (h->h_compact) CUDA_TRY(h, cudaFreeHost(h->h_compact));
             h->h_compact = nullptr;
@@ -1368,6 +1420,11 @@ int host_submit(b200seed_handle* h, cudaStream_t s, HostEvent& e) {
         rc = b200seed_estimate_params_compact(h, s, d_n, seed_capacity, e.d_b, e.d_m, e.d_t, d_xyz, e.bfield,
                                               reinterpret_cast<b200seed_seed_params*>(e.d_p));
         if (rc != B200SEED_OK) return rc;
+    } else if (e.packed) {
+        rc = b200seed_estimate_params_packed(h, s, d_n, seed_capacity, e.d_b, e.d_m, e.d_t, d_xyz, d_smi, d_ml,
+                                             d_ms, e.bfield,
+                                             reinterpret_cast<b200seed_bound_params_packed*>(e.d_p));
+        if (rc != B200SEED_OK) return rc;
     } else if (want_params) {
         rc = diag ? b200seed_estimate_params_diag(h, s, d_n, seed_capacity, e.d_b, e.d_m, e.d_t, d_xyz, d_smi,
                                                   d_ml, d_ms, e.bfield,
@@ -1410,6 +1467,9 @@ int host_finish(b200seed_handle* h, cudaStream_t s, HostEvent& e, uint32_t* h_n_
                 CUDA_TRY(h, cudaMemcpyAsync(stage, e.d_b, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
                 h_bot = stage;
             }
+        } else if (e.packed) {
+            CUDA_TRY(h, cudaMemcpyAsync(h->h_compact, e.d_p, size_t(n) * sizeof(b200seed_bound_params_packed),
+                                        cudaMemcpyDeviceToHost, s));
         } else if (e.h_params_diag) {
             CUDA_TRY(h, cudaMemcpyAsync(e.h_params_diag, e.d_p, size_t(n) * sizeof(b200seed_bound_params_diag),
                                         cudaMemcpyDeviceToHost, s));
@@ -1436,6 +1496,9 @@ void host_expand(b200seed_handle* h, const HostEvent& e, uint32_t n) {
     if (e.compact)
         b200seed_expand_seed_params(h, n, e.h_bot_stage, static_cast<const b200seed_seed_params*>(h->h_compact),
                                     e.h_smi, e.h_ml, e.h_ms, e.h_params, e.h_params_diag);
+    else if (e.packed)
+        b200seed_expand_packed_params(h, n, static_cast<const b200seed_bound_params_packed*>(h->h_compact),
+                                      e.h_params, e.h_params_diag);
     // both forms requested: the full records are expanded on the host
     else if (e.h_params_diag && e.h_params)
         b200seed_expand_params(e.h_params_diag, n, e.h_params);
@@ -1444,7 +1507,7 @@ void host_expand(b200seed_handle* h, const HostEvent& e, uint32_t n) {
 // host_submit would have to enlarge the pinned landing area of this handle (which may still hold an
 // event waiting for host_expand)
 bool host_submit_regrows_landing(const b200seed_handle* h, const HostEvent& e) {
-    return size_t(e.seed_capacity) * (sizeof(b200seed_seed_params) + 4) > h->h_compact_bytes;
+    return size_t(e.seed_capacity) * sizeof(b200seed_bound_params_packed) > h->h_compact_bytes;
 }
 
 }  // namespace

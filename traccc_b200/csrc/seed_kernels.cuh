@@ -2609,7 +2609,8 @@ k_estimate_params(const b200seed_tpe_cfg cfg, const uint32_t* __restrict__ n_see
                   const float bx, const float by, const float bz, const b200seed_field_grid fg,
                   b200seed_bound_params* __restrict__ out,
                   b200seed_bound_params_diag* __restrict__ out_diag,
-                  b200seed_seed_params* __restrict__ out_compact) {
+                  b200seed_seed_params* __restrict__ out_compact,
+                  b200seed_bound_params_packed* __restrict__ out_packed) {
     // Records are 176 B: written one per lane they would cost 32 sectors per store
     // instruction. Each warp builds its 32 records (5632 contiguous bytes) in shared memory
     // and streams them out as float4 rows.
@@ -2701,6 +2702,17 @@ k_estimate_params(const b200seed_tpe_cfg cfg, const uint32_t* __restrict__ n_see
     const float loc0 = meas_local ? meas_local[2 * size_t(mi)] : 0.f;
     const float loc1 = meas_local ? meas_local[2 * size_t(mi) + 1] : 0.f;
     const uint32_t nrec = (n - i0 < 32u) ? (n - i0) : 32u;
+    if (out_packed) {
+        // 32-byte records (no constant variances, no time): 8 floats per lane, streamed out as float4 rows
+        b200seed_bound_params_packed* o = reinterpret_cast<b200seed_bound_params_packed*>(rec + lane * 8);
+        o->surface_link = link;
+        o->loc0 = loc0, o->loc1 = loc1, o->phi = phi, o->theta = theta, o->qop = qop, o->var_qop = var[4];
+        __syncwarp();
+        const float4* s4 = reinterpret_cast<const float4*>(rec);
+        float4* d4 = reinterpret_cast<float4*>(out_packed + i0);
+        for (uint32_t k = lane; k < nrec * 2u; k += 32) d4[k] = s4[k];
+        return;
+    }
     if (out_diag) {
         // 56-byte diagonal records: 14 floats per lane, streamed out as float2 rows
         b200seed_bound_params_diag* o = reinterpret_cast<b200seed_bound_params_diag*>(rec + lane * 14);
