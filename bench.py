@@ -572,11 +572,15 @@ def run_b200(args):
     DIAG = args.e2e_records == "diag"
     rec_bytes = 56 if DIAG else 176
     ios, outs = pool.make_batch(events, diag=DIAG)
-    # Bytes that actually cross PCIe. Default: the records themselves and all six input columns.
+    # Bytes that actually cross PCIe. Default (packed): 32-byte records without the constant
+    # variances and the time, completed inside pool.process by a sequential host copy; all six input
+    # columns go to the device. B200SEED_PCIE_PARAMS=records: the delivered records themselves.
     # B200SEED_PCIE_PARAMS=compact: the library computes only phi, theta, q/p and var(q/p) on the
     # device (16 bytes per seed, b200seed_seed_params) and completes the records on the host, inside
     # pool.process, from the caller's measurement columns — which then never go to the device.
-    COMPACT = os.environ.get("B200SEED_PCIE_PARAMS") == "compact"
+    PCIE = os.environ.get("B200SEED_PCIE_PARAMS", "packed")
+    COMPACT = PCIE == "compact"
+    pcie_rec_bytes = {"compact": 16, "packed": 32}.get(PCIE)   # None: the delivered records themselves
     h2d = sum(e.xyz.nbytes + e.var_z.nbytes + e.var_r.nbytes
               + (0 if COMPACT else e.meas_index.nbytes + e.meas_local.nbytes + e.meas_surface.nbytes)
               for e in events)
@@ -584,7 +588,7 @@ def run_b200(args):
 
     def step_e2e():
         pool.process(ios)
-        d2h_box[0] = sum(C.sizeof(_lib.Counters) + int(io.n_seeds) * (16 + (16 if COMPACT else rec_bytes))
+        d2h_box[0] = sum(C.sizeof(_lib.Counters) + int(io.n_seeds) * (16 + (pcie_rec_bytes or rec_bytes))
                          for io in ios)
 
     def timed_wall(step_fn, k, w):
@@ -742,7 +746,10 @@ def run_b200(args):
                                f"{'diagonal (b200seed_bound_params_diag)' if DIAG else 'full'} records"
                                + ("; over PCIe only 16 bytes per seed (phi, theta, q/p, var(q/p)), the records "
                                   "completed on the host inside the timed region from the caller's measurement "
-                                  "columns, which are not sent to the device" if COMPACT else ""),
+                                  "columns, which are not sent to the device" if COMPACT else
+                                  "; over PCIe as 32-byte packed records (b200seed_bound_params_packed: no constant "
+                                  "variances, no time), completed on the host inside the timed region"
+                                  if PCIE == "packed" else ""),
                         "other_record_form": {"bytes_per_record": 176 if DIAG else 56, "value": e2e_other}},
                 "roofline": roof, "clocks": clocks,
                 "event_counters_mean": c_mean}

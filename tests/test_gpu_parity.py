@@ -552,7 +552,7 @@ def test_parity_lane_triplet_kernel(monkeypatch):
     assert got["counters"]["overflow"] == 0
 
 
-@pytest.mark.parametrize("pcie", ["records", "compact"])
+@pytest.mark.parametrize("pcie", ["records", "packed", "compact"])
 def test_diagonal_parameter_records(pcie, monkeypatch):
     """b200seed_event_io::params_diag: the parameters leave the device as 56-byte diagonal
     records (a third of the PCIe bytes); b200seed_expand_params restores the full records,
@@ -622,6 +622,13 @@ def test_compact_seed_parameters_expand_to_the_full_records():
             assert np.array_equal(got.view(np.uint8), ref.view(np.uint8))
             gd = tp.expand_seed_params(h["bottom"], c, ev.meas_index, ev.meas_local, ev.meas_surface, diag=True)
             assert np.array_equal(seeding.expand_params(gd).view(np.uint8), ref.view(np.uint8))
+            # the 32-byte packed records (the default PCIe form of the host-buffer path)
+            pk = tp.packed(ev.bfield, meas, sps, seeds)
+            torch.cuda.synchronize()
+            p = np.frombuffer(pk[: ns * 32].cpu().numpy().tobytes(), dtype=seeding.PACKED_PARAMS_DTYPE)
+            assert np.array_equal(tp.expand_packed_params(p).view(np.uint8), ref.view(np.uint8))
+            assert np.array_equal(seeding.expand_params(tp.expand_packed_params(p, diag=True)).view(np.uint8),
+                                  ref.view(np.uint8))
 
 
 def test_stress_event_full_size():

@@ -130,6 +130,7 @@ EXPORTS = (
     "b200seed_form_spacepoints", "b200seed_run_n_on_device", "b200seed_estimate_params_inhom",
     "b200seed_estimate_params_diag", "b200seed_expand_params",
     "b200seed_estimate_params_compact", "b200seed_expand_seed_params",
+    "b200seed_estimate_params_packed", "b200seed_expand_packed_params",
     "b200seed_workspace_layout", "b200seed_set_triplet_dump", "b200seed_set_timing",
     "b200seed_get_timings", "b200seed_launches_per_event", "b200seed_measure_fp32_peak",
     "b200seed_version")
@@ -185,6 +186,10 @@ def lib() -> C.CDLL:
                                                    C.POINTER(C.c_float * 3), vp]
     L.b200seed_expand_seed_params.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp, vp]
     L.b200seed_expand_seed_params.restype = None
+    L.b200seed_estimate_params_packed.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp, vp, vp,
+                                                  C.POINTER(C.c_float * 3), vp]
+    L.b200seed_expand_packed_params.argtypes = [vp, u32, vp, vp, vp]
+    L.b200seed_expand_packed_params.restype = None
     L.b200seed_estimate_params_inhom.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp, vp, vp,
                                                  C.POINTER(FieldGrid), vp]
     L.b200seed_run_host.argtypes = [vp, vp, u32, vp, vp, vp, vp, u32, vp, vp,

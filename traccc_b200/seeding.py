@@ -28,6 +28,9 @@ BOUND_PARAMS_DIAG_DTYPE = np.dtype([("surface_link", "<u8"), ("vec", "<f4", (6,)
                                     ("cov_diag", "<f4", (6,))])
 
 
+# b200seed_bound_params_packed: a record without its constant variances and the time (32 bytes)
+PACKED_PARAMS_DTYPE = np.dtype([("surface_link", "<u8"), ("loc0", "<f4"), ("loc1", "<f4"), ("phi", "<f4"),
+                                ("theta", "<f4"), ("qop", "<f4"), ("var_qop", "<f4")])
 # b200seed_seed_params: what only the device can compute of a record (16 bytes per seed)
 SEED_PARAMS_DTYPE = np.dtype([("phi", "<f4"), ("theta", "<f4"), ("qop", "<f4"), ("var_qop", "<f4")])
 
@@ -462,6 +465,28 @@ class seed_parameter_estimation_algorithm:
             bf = (C.c_float * 3)(*[float(b) for b in bfield])
             rc = self.lib.b200seed_estimate_params(*head, C.byref(bf), _ptr(out))
         _lib.check(rc, self.h)
+        return out
+
+    def packed(self, bfield, measurements: measurement_collection, spacepoints: spacepoint_collection,
+               seeds: seed_collection, stream=None) -> torch.Tensor:
+        """b200seed_estimate_params_packed: 32-byte records (no constant variances, no time)."""
+        cap = seeds.capacity
+        out = torch.empty(cap * PACKED_PARAMS_DTYPE.itemsize, dtype=torch.uint8, device=f"cuda:{self.device}")
+        bf = (C.c_float * 3)(*[float(b) for b in bfield])
+        _lib.check(self.lib.b200seed_estimate_params_packed(
+            self.h, _stream_handle(stream or self.stream), _ptr(seeds.n_seeds), cap,
+            _ptr(seeds.bottom_index), _ptr(seeds.middle_index), _ptr(seeds.top_index),
+            _ptr(spacepoints.xyz), _ptr(spacepoints.measurement_index_1),
+            _ptr(measurements.local_position), _ptr(measurements.surface_link), C.byref(bf), _ptr(out)), self.h)
+        return out
+
+    def expand_packed_params(self, packed: np.ndarray, diag: bool = False) -> np.ndarray:
+        """b200seed_expand_packed_params (host): full (or diagonal) records from the packed ones."""
+        packed = np.ascontiguousarray(packed)
+        out = np.zeros(len(packed), dtype=BOUND_PARAMS_DIAG_DTYPE if diag else BOUND_PARAMS_DTYPE)
+        o = out.ctypes.data_as(C.c_void_p)
+        self.lib.b200seed_expand_packed_params(self.h, len(packed), packed.ctypes.data_as(C.c_void_p),
+                                               None if diag else o, o if diag else None)
         return out
 
     def compact(self, bfield, spacepoints: spacepoint_collection, seeds: seed_collection,
