@@ -572,13 +572,13 @@ def run_b200(args):
     DIAG = args.e2e_records == "diag"
     rec_bytes = 56 if DIAG else 176
     ios, outs = pool.make_batch(events, diag=DIAG)
-    # Bytes that actually cross PCIe. Default (packed): 32-byte records without the constant
-    # variances and the time, completed inside pool.process by a sequential host copy; all six input
-    # columns go to the device. B200SEED_PCIE_PARAMS=records: the delivered records themselves.
+    # Bytes that actually cross PCIe. Default: the delivered records themselves and all six input
+    # columns. B200SEED_PCIE_PARAMS=packed: 32-byte records without the constant variances and the
+    # time, completed inside pool.process by a sequential host copy.
     # B200SEED_PCIE_PARAMS=compact: the library computes only phi, theta, q/p and var(q/p) on the
     # device (16 bytes per seed, b200seed_seed_params) and completes the records on the host, inside
     # pool.process, from the caller's measurement columns — which then never go to the device.
-    PCIE = os.environ.get("B200SEED_PCIE_PARAMS", "packed")
+    PCIE = os.environ.get("B200SEED_PCIE_PARAMS", "records")
     COMPACT = PCIE == "compact"
     pcie_rec_bytes = {"compact": 16, "packed": 32}.get(PCIE)   # None: the delivered records themselves
     h2d = sum(e.xyz.nbytes + e.var_z.nbytes + e.var_r.nbytes

@@ -153,9 +153,10 @@ typedef struct b200seed_seed_params {
 } b200seed_seed_params;
 
 /* A parameter record without the five variances that are constants of the b200seed_tpe_cfg and
- * without the time (zero): what the host-buffer entry points move over PCIe (32 bytes instead of
- * 56 / 176). b200seed_expand_packed_params() restores the records on the host — a sequential
- * copy, no look-ups. */
+ * without the time (zero): 32 bytes instead of 56 / 176. b200seed_expand_packed_params() restores
+ * the records on the host — a sequential copy, no look-ups. With B200SEED_PCIE_PARAMS=packed the
+ * host-buffer entry points move the parameters over PCIe in this form (measured slower than the
+ * records themselves on the hosts tried: not the default). */
 typedef struct b200seed_bound_params_packed {
     uint64_t surface_link;
     float loc0, loc1, phi, theta, qop, var_qop;
