@@ -468,7 +468,7 @@ def test_parity_group_kernel(mode, monkeypatch):
 def test_parity_doublet_ticket_order(order, monkeypatch):
     """k_doublets draws its tickets in cost order (k_cell_scan classifies every (bin, r row) by the
     populations of the rows below / above it, k_bin_scatter lays the middles out class by class;
-    automatic from 32k spacepoints on) or in grid order: forced either way with
+    automatic from 8k spacepoints on) or in grid order: forced either way with
     B200SEED_DOUBLET_ORDER, the binning, doublet and triplet sets, seeds and parameters must be the
     oracle's — small and ragged events, 7 z bins, spacepoints outside the grid, an empty event."""
     from traccc_b200 import seedfinder_config, spacepoint_grid_config, toy_detector
@@ -486,7 +486,7 @@ def test_parity_doublet_ticket_order(order, monkeypatch):
 
 
 def test_overlapped_doublet_launches_are_repeatable(monkeypatch):
-    """From 32k spacepoints on (here forced) the doublet stage is two overlapping launches (k_doublets<0> and,
+    """From 20k spacepoints on (here forced) the doublet stage is two overlapping launches (k_doublets<0> and,
     as a programmatic dependent that fills its tail, k_doublets<3> for the middles with a scarce
     side). The same events, four in flight on different streams, 25 times: every run must return
     the seeds and counters of the first one bit for bit, and those are the oracle's."""

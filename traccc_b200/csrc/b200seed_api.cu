@@ -76,10 +76,11 @@ struct b200seed_handle {
     // cp.async (B200SEED_DOUBLETS=warp|tile|ldgsts, read at b200seed_create)
     int doublet_mode = 2;
     // k_doublets<0> draws its tickets in cost order (longest middles first: k_cell_scan's classes)
-    // instead of grid order: 1 = for events of at least 32k spacepoints (default), 0 / 2 = never /
+    // instead of grid order: 1 = for events of at least 8k spacepoints (default), 0 / 2 = never /
     // always (B200SEED_DOUBLET_ORDER=grid / cost, for A/B runs and the tests)
     int ordered_tickets = 1;
-    // ... and the classes with a scarce side in a launch of their own (B200SEED_DOUBLET_SIDES=0: off)
+    // ... and the classes with a scarce side in a launch of their own, from 20k spacepoints on
+    // (B200SEED_DOUBLET_SIDES=0: off, =force: at any size)
     int split_sides = 1;
     int pdl = 1;  // ... overlapping the end of k_doublets<0> (B200SEED_PDL=0: plain stream order)
     // triplet search of the light middles: 0 = k_triplets for all (default: faster),
@@ -576,7 +577,8 @@ int b200seed_create(const b200seed_finder_cfg* finder, const b200seed_grid_cfg* 
         h->pcie_compact = !std::strcmp(m, "compact");
         h->pcie_packed = !std::strcmp(m, "packed");
     }
-    if (const char* m = std::getenv("B200SEED_DOUBLET_SIDES")) h->split_sides = std::strcmp(m, "0") != 0;
+    if (const char* m = std::getenv("B200SEED_DOUBLET_SIDES"))
+        h->split_sides = !std::strcmp(m, "0") ? 0 : (!std::strcmp(m, "force") ? 2 : 1);
     if (const char* m = std::getenv("B200SEED_PDL")) h->pdl = std::strcmp(m, "0") != 0;
     if (const char* m = std::getenv("B200SEED_DOUBLET_ORDER"))
         h->ordered_tickets = !std::strcmp(m, "grid") ? 0 : (!std::strcmp(m, "cost") ? 2 : 1);
@@ -746,7 +748,7 @@ int b200seed_get_timings(b200seed_handle* h, const char** names, float* ms, int 
 int b200seed_launches_per_event(const b200seed_handle* h, int with_params) {
     // k_bin_count, k_cell_scan, k_bin_scatter, k_doublets<0>, k_doublets<1>, k_triplets,
     // k_seed_gather; the group kernel adds one launch (k_doublets_tile + k_doublets<2>)
-    // (events of at least 32k spacepoints: + k_doublets<3> for the middles with a scarce side)
+    // (events of at least 20k spacepoints: + k_doublets<3> for the middles with a scarce side)
     const bool sides = h && h->doublet_mode == 2 && h->ordered_tickets && h->split_sides && h->finder.deltaRMin >= 0.f;
     const int doublets = (h && h->doublet_mode != 2) ? 3 : (sides ? 3 : 2);
     const int triplets = (h && (h->triplet_pool || h->triplet_lanes)) ? 2 : 1;  // (lanes: not for > 80k spacepoints)
@@ -808,15 +810,19 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
     float4* csp4 = reinterpret_cast<float4*>(at(L.csp4));
     uint32_t* ccanon = reinterpret_cast<uint32_t*>(at(L.ccanon));
     // ticket order of k_doublets<0> (cost classes per (bin, r row); B200SEED_DOUBLET_ORDER=grid: off)
-    // (from 32k spacepoints on: below that the launch is too short for its end to matter, and the
-    // classification and the extra launch cost more than they save — measured crossover at 7000
-    // particles per event: 5000: -3 %, 7000: +1.5 %, 10000: +3 % events/s; =cost forces it)
-    const bool ordered = h->ordered_tickets == 2 || (h->ordered_tickets == 1 && n_sp >= 32768u);
+    // (from 8k spacepoints on: below that the launch is too short for its end to matter; =cost
+    // forces it)
+    const bool ordered = h->ordered_tickets == 2 || (h->ordered_tickets == 1 && n_sp >= 8192u);
     uint32_t* seg_info = ordered ? reinterpret_cast<uint32_t*>(at(L.seg_info)) : nullptr;
     uint32_t* mid_order = ordered ? reinterpret_cast<uint32_t*>(at(L.mid_order)) : nullptr;
     // the classes with an (almost) empty side get their own launch, which looks at that side first
     // (k_doublets<3>; needs deltaRMin >= 0: bottoms below, tops above the middle's row)
-    const bool split_sides = ordered && h->split_sides && h->finder.deltaRMin >= 0.f && h->doublet_mode == 2;
+    // From 20k spacepoints on: a batch of 32 lane-serial pre-screenings takes 35-60 us, which only
+    // hides behind a main launch that long (2000 particles per event: doublet stage 36 -> 63 us with
+    // it, 5000: 70 -> 63 us, 10000: 148 -> 130 us).
+    // (B200SEED_DOUBLET_ORDER=cost or B200SEED_DOUBLET_SIDES=force: at any size, for the tests)
+    const bool split_sides = ordered && h->split_sides && h->finder.deltaRMin >= 0.f && h->doublet_mode == 2 &&
+                             (h->split_sides == 2 || h->ordered_tickets == 2 || n_sp >= 20000u);
     uint32_t row_reach = uint32_t(h->finder.deltaRMax * L.g.invRw) + 1u;  // rows a partner can be away
     if (!(h->finder.deltaRMax >= 0.f) || row_reach > 31u) row_reach = 31u;
     // canon_key (seed_kernels.cuh) is a 32-bit word
