@@ -750,7 +750,7 @@ int b200seed_launches_per_event(const b200seed_handle* h, int with_params) {
     // k_seed_gather; the group kernel adds one launch (k_doublets_tile + k_doublets<2>)
     // (events of at least 20k spacepoints: + k_doublets<3> for the middles with a scarce side)
     const bool sides = h && h->doublet_mode == 2 && h->ordered_tickets && h->split_sides && h->finder.deltaRMin >= 0.f;
-    const int doublets = (h && h->doublet_mode != 2) ? 3 : (sides ? 3 : 2);
+    const int doublets = (h && h->doublet_mode != 2) ? 3 : (sides ? 4 : 2);
     const int triplets = (h && (h->triplet_pool || h->triplet_lanes)) ? 2 : 1;  // (lanes: not for > 80k spacepoints)
     return 4 + doublets + triplets + (with_params ? 1 : 0);
 }
@@ -922,6 +922,10 @@ int run_impl(b200seed_handle* h, void* stream, uint32_t n_sp, const uint32_t* d_
                     le = cudaLaunchKernelEx(&lc, k_doublets<3>, h->dev, a);
                 }
                 CUDA_TRY(h, le);
+                // survivors beyond SIDED_INLINE per batch (normally none: the CTAs find an empty
+                // list and exit): warp per middle
+                const uint32_t grid_f = grid_s < uint32_t(h->num_sms) ? grid_s : uint32_t(h->num_sms);
+                k_doublets<2><<<grid_f, WARPS_PER_CTA * 32, smem, s>>>(h->dev, a);
             }
         } else {
             TileArgs ta{};

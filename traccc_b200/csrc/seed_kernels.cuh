@@ -93,6 +93,10 @@ __host__ __device__ inline uint32_t work_class(uint32_t nB, uint32_t nT) {
 
 // Flag in the entries of mid_order for the classes with a scarce side: it is the lower one.
 constexpr uint32_t MID_LOWER_SCARCE = 0x80000000u;
+#ifndef B200_SIDED_INLINE
+#define B200_SIDED_INLINE 4u
+#endif
+constexpr uint32_t SIDED_INLINE = B200_SIDED_INLINE;  // survivors of a pre-screened batch scanned by the same warp
 
 // Small control block at the start of the workspace, zeroed at the start of each event.
 struct Control {
@@ -920,6 +924,23 @@ k_doublets(const DevCfg cfg, const DoubletArgs a) {
                     }
                 }
                 alive_mask = __ballot_sync(0xffffffffu, alive);
+                // This warp scans at most SIDED_INLINE of the survivors itself; more than that (not
+                // in the toy detector, where ~1 % survive) go to the fallback list, which
+                // k_doublets<2> works off with a warp each — a batch full of survivors must not
+                // become 32 warp-wide scans in a row on one warp.
+                if (__popc(alive_mask) > int(SIDED_INLINE)) {
+                    uint32_t rest = alive_mask, keep = 0;
+#pragma unroll
+                    for (uint32_t k = 0; k < SIDED_INLINE; ++k) {
+                        const uint32_t b = rest & (0u - rest);
+                        keep |= b;
+                        rest ^= b;
+                    }
+                    if ((rest >> lane) & 1u)
+                        const_cast<uint32_t*>(a.fallback_list)[atomicAdd(&a.ctrl->n_fallback, 1u)] =
+                            batch_entry & ~MID_LOWER_SCARCE;
+                    alive_mask = keep;
+                }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) seen += __shfl_xor_sync(0xffffffffu, seen, o);
                 if (lane == 0) visited += seen;
