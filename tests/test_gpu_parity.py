@@ -516,6 +516,34 @@ def test_overlapped_doublet_launches_are_repeatable(monkeypatch):
     _check_event(events[0], dump=False)
 
 
+def test_parity_scarce_side_survivors(monkeypatch):
+    """k_doublets<3> pre-screens the middles whose row populations leave one side (almost) empty,
+    32 per warp; those that do have a partner there are scanned by the same warp, at most four per
+    batch — the others go to the fallback list (k_doublets<2>). The toy detector has no such
+    survivors, so some are planted: spacepoints at r = 20 mm on the line from the origin to 60
+    spacepoints of the innermost barrel layer inside a few phi bins. Doublet and triplet sets, seeds
+    and parameters must be the oracle's, and the fallback list must have been used."""
+    import copy
+    from traccc_b200 import toy_detector
+    monkeypatch.setenv("B200SEED_DOUBLET_ORDER", "cost")
+    ev = toy_detector.generate_event(3000, 77)
+    r = np.hypot(ev.xyz[:, 0], ev.xyz[:, 1])
+    phi = np.arctan2(ev.xyz[:, 1], ev.xyz[:, 0])
+    pick = np.flatnonzero((np.abs(r - 32.0) < 0.5) & (np.abs(phi - 0.4) < 0.12))[:60]
+    assert len(pick) >= 40
+    extra = (ev.xyz[pick] * np.float32(20.0 / 32.0)).astype(np.float32)
+    big = copy.copy(ev)
+    big.xyz = np.concatenate([ev.xyz, extra])
+    n = len(big.xyz)
+    big.var_z = np.zeros(n, np.float32)
+    big.var_r = np.zeros(n, np.float32)
+    big.meas_index = np.arange(n, dtype=np.uint32)
+    big.meas_local = np.zeros((n, 2), np.float32)
+    big.meas_surface = np.arange(n, dtype=np.uint64)
+    got, ref = _check_event(big)
+    assert got["counters"]["n_fallback_middles"] > 0
+
+
 def test_parity_pooled_triplet_kernel(monkeypatch):
     """k_triplets_pool (eight light middles per warp, one pair queue and one triplet list for all of
     them; B200SEED_TRIPLETS=pool, off by default — DESIGN.md §5) against the oracle: triplet sets
