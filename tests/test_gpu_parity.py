@@ -520,8 +520,9 @@ def test_parity_scarce_side_survivors(monkeypatch):
     """k_doublets<3> pre-screens the middles whose row populations leave one side (almost) empty,
     32 per warp; those that do have a partner there are scanned by the same warp, at most four per
     batch — the others go to the fallback list (k_doublets<2>). The toy detector has no such
-    survivors, so some are planted: spacepoints at r = 20 mm on the line from the origin to 60
-    spacepoints of the innermost barrel layer inside a few phi bins. Doublet and triplet sets, seeds
+    survivors, so some are planted: three spacepoints at r = 8 mm (deltaRMin is 20 mm) on the line
+    from the origin to spacepoints of the innermost barrel layer — so close to the beam line, each
+    is a bottom partner of about a hundred middles of that layer. Doublet and triplet sets, seeds
     and parameters must be the oracle's, and the fallback list must have been used."""
     import copy
     from traccc_b200 import toy_detector
@@ -529,9 +530,9 @@ def test_parity_scarce_side_survivors(monkeypatch):
     ev = toy_detector.generate_event(3000, 77)
     r = np.hypot(ev.xyz[:, 0], ev.xyz[:, 1])
     phi = np.arctan2(ev.xyz[:, 1], ev.xyz[:, 0])
-    pick = np.flatnonzero((np.abs(r - 32.0) < 0.5) & (np.abs(phi - 0.4) < 0.12))[:60]
-    assert len(pick) >= 40
-    extra = (ev.xyz[pick] * np.float32(20.0 / 32.0)).astype(np.float32)
+    b = np.floor((phi + np.pi) / (2 * np.pi / 78)).astype(int)
+    pick = [np.flatnonzero((np.abs(r - 32.0) < 0.5) & (b == bb) & (np.abs(ev.xyz[:, 2]) < 200))[0] for bb in (30, 40, 50)]
+    extra = (ev.xyz[pick] * np.float32(8.0 / 32.0)).astype(np.float32)
     big = copy.copy(ev)
     big.xyz = np.concatenate([ev.xyz, extra])
     n = len(big.xyz)
@@ -541,7 +542,7 @@ def test_parity_scarce_side_survivors(monkeypatch):
     big.meas_local = np.zeros((n, 2), np.float32)
     big.meas_surface = np.arange(n, dtype=np.uint64)
     got, ref = _check_event(big)
-    assert got["counters"]["n_fallback_middles"] > 0
+    assert got["counters"]["n_fallback_middles"] > 100
 
 
 def test_parity_pooled_triplet_kernel(monkeypatch):
