@@ -62,3 +62,25 @@ if os.environ.get("SANITIZE_SLOW"):
     c = seeds.host_counters()
     print("slow", n, c["n_seeds"], c["overflow"])
     assert c["overflow"] == 0 and c["n_seeds"] > 0
+if os.environ.get("SANITIZE_SIDES"):
+    # cost-ordered tickets, k_doublets<3> (lane-level pre-screening, programmatic dependent launch)
+    # and k_doublets<2> for surplus survivors (planted: three spacepoints near the beam line)
+    ev = toy_detector.generate_event(6000, 11)
+    f = seedfinder_config()
+    sa = seeding.triplet_seeding_algorithm(f, spacepoint_grid_config(f), seedfilter_config())
+    seeds = sa(seeding.spacepoint_collection.from_event(ev))
+    torch.cuda.synchronize()
+    print("sides", ev.n_spacepoints, seeds.host_counters()["n_seeds"], seeds.host_counters()["overflow"])
+    r = np.hypot(ev.xyz[:, 0], ev.xyz[:, 1])
+    pick = np.flatnonzero((np.abs(r - 32.0) < 0.5) & (np.abs(ev.xyz[:, 2]) < 200))[:3]
+    xyz = np.concatenate([ev.xyz, (ev.xyz[pick] * np.float32(0.25)).astype(np.float32)])
+    n = len(xyz)
+    ev2 = toy_detector.ToyEvent(xyz, np.zeros(n, np.float32), np.zeros(n, np.float32),
+                                np.arange(n, dtype=np.uint32), np.zeros((n, 2), np.float32),
+                                np.arange(1, n + 1, dtype=np.uint64), np.zeros(n, np.uint32), 6000,
+                                np.array([0.0, 0.0, 5.9958e-4], np.float32))
+    seeds = sa(seeding.spacepoint_collection.from_event(ev2))
+    torch.cuda.synchronize()
+    c = seeds.host_counters()
+    print("survivors", n, c["n_seeds"], c["n_fallback_middles"], c["overflow"])
+    assert c["overflow"] == 0 and c["n_fallback_middles"] > 0
