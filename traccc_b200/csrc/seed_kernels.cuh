@@ -5,18 +5,27 @@
 //
 //   k_form_spacepoints  (optional, the step before the path) 2D measurements -> spacepoints in
 //                    measurement order; single-pass compaction with decoupled look-back
-//   k_bin_count      is_valid_sp + bin index per spacepoint, per-block bin histogram,
+//   k_bin_count      is_valid_sp + bin index per spacepoint, per-block bin histogram, bin totals,
 //                    population of the fine (r, z) cells inside every bin
-//   k_scan           single-CTA exclusive scan of the [bin][block] histogram matrix
-//   k_cell_scan      CTA per bin: start of every (r row, z cell) inside the bin
+//   k_cell_scan      CTA per bin: start of the bin (sum of the totals before it), scan of its row
+//                    of per-block counts, start of every (r row, z cell) inside the bin; cost
+//                    class of every (bin, r row) for the ticket order of k_doublets
 //   k_bin_scatter    stable scatter into bin-sorted float4 {x,y,z,r} / float2 {varZ,varR}
-//                    (the reference's grid order) + the cell-sorted copy used for pruning
-//   k_doublets<false> warp per middle (ticket queue): cell windows of the neighbour bins ->
+//                    (the reference's grid order) + the cell-sorted copy used for pruning + the
+//                    ticket order (mid_order: longest middles first)
+//   k_doublets<0>    warp per middle (ticket queue): cell windows of the neighbour bins ->
 //                    flattened candidate list -> doublet cuts at full lane occupancy (helix cut
 //                    decided by a division-free polynomial, exact chain only near its boundary),
 //                    ballot/popc compaction, lin_circle, arena write; work lists for the next
-//                    kernels (active middles heavy-first, middles whose lists outgrow shared memory)
-//   k_doublets<true> the latter middles only: records written straight to the arena, bucket sort
+//                    kernels (active middles in eight classes, longest first; middles whose lists
+//                    outgrow shared memory)
+//   k_doublets<3>    the middles whose row populations leave one side (almost) empty: 32 per warp
+//                    pre-screened for a partner on that side, one per LANE; survivors scanned
+//                    warp-wide, that side first. Programmatic dependent of k_doublets<0>: no
+//                    shared data, fills its tail
+//   k_doublets<2>    survivors beyond four per batch (fallback list; normally empty)
+//   k_doublets<1>    the middles whose lists outgrew the staging area: records written straight
+//                    to the arena, bucket sort (normally empty)
 //   k_triplets<DENSE> warp per active middle, longest jobs first: lane-owns-mid-bottom windows in
 //                    the cotTheta-sorted mid-tops -> flattened pairs -> exact cuts, compatible-seed
 //                    bonus, per-middle top-N in shared memory (DENSE: candidate compaction, warp
