@@ -50,8 +50,6 @@ namespace b200seed {
 
 constexpr uint32_t INVALID_BIN = 0xFFFFFFFFu;
 constexpr int BIN_THREADS = 256;    // spacepoints per binning block
-constexpr int SCAN_THREADS = 1024;  // single-CTA scan
-constexpr int SCAN_ITEMS = 4;
 #ifndef B200_WARPS_PER_CTA
 #define B200_WARPS_PER_CTA 8
 #endif
@@ -345,68 +343,6 @@ k_bin_count(const DevCfg cfg, const CellGrid g, const uint32_t n_sp_max,
         const uint32_t c = s_hist[b];
         blk_hist[size_t(b) * nblk + blockIdx.x] = c;
         if (c) atomicAdd(&bin_tot[b], c);  // population of the bin (k_cell_scan sums them into bin_off)
-    }
-}
-
-// ---------------------------------------------------------------------------
-// single-CTA exclusive scan of in[] into data[] (may alias). len_dev, if not null,
-// overrides len. Epilogue: total -> *total_out; if bin_off != null,
-// bin_off[b] = data[b * stride].
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(SCAN_THREADS)
-k_scan(const uint32_t* in, uint32_t* data, uint32_t len, const uint32_t* __restrict__ len_dev,
-       uint32_t* __restrict__ total_out, uint32_t* __restrict__ bin_off, const uint32_t nbins,
-       const uint32_t stride) {
-    __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_total;
-    if (len_dev) len = *len_dev;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t carry = 0;
-    constexpr uint32_t CHUNK = SCAN_THREADS * SCAN_ITEMS;
-    for (uint32_t base = 0; base < len; base += CHUNK) {
-        const uint32_t idx = base + threadIdx.x * SCAN_ITEMS;
-        uint32_t v[SCAN_ITEMS];
-        uint32_t s = 0;
-#pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; ++k) {
-            v[k] = (idx + k < len) ? in[idx + k] : 0u;
-            s += v[k];
-        }
-        uint32_t incl = s;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
-            if (lane >= uint32_t(off)) incl += t;
-        }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            const uint32_t ws = s_warp[lane];
-            uint32_t wincl = ws;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, wincl, off);
-                if (lane >= uint32_t(off)) wincl += t;
-            }
-            s_warp[lane] = wincl - ws;
-            if (lane == 31) s_total = wincl;
-        }
-        __syncthreads();
-        uint32_t run = carry + s_warp[warp] + incl - s;
-#pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; ++k) {
-            if (idx + k < len) data[idx + k] = run;
-            run += v[k];
-        }
-        carry += s_total;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0 && total_out) *total_out = carry;
-    if (bin_off) {
-        __syncthreads();  // make the scanned values of this CTA visible to all its threads
-        for (uint32_t b = threadIdx.x; b < nbins; b += SCAN_THREADS)
-            bin_off[b] = data[size_t(b) * stride];
-        if (threadIdx.x == 0) bin_off[nbins] = carry;
     }
 }
 
