@@ -49,10 +49,11 @@ def parse_args():
     ap.add_argument("--pool-workers", type=int, default=8,
                     help="host worker threads of the end-to-end leg (2 events in flight each; "
                          "they sleep on blocking-sync events, so ranks x workers may exceed the cores)")
-    ap.add_argument("--e2e-records", default="diag", choices=["diag", "full"],
-                    help="parameter records of the end-to-end leg: 56-byte diagonal records "
-                         "(b200seed_event_io::params_diag; the covariance of this path is diagonal) or "
-                         "the full 176-byte records")
+    ap.add_argument("--e2e-records", default="packed", choices=["packed", "diag", "full"],
+                    help="parameter records delivered by the end-to-end leg: 32-byte packed records "
+                         "(b200seed_event_io::params_packed: no constant variances, no time), 56-byte diagonal "
+                         "records (params_diag; the covariance of this path is diagonal) or the full 176-byte "
+                         "records — all three expand to the same 176 bytes (b200seed_expand_*)")
     ap.add_argument("--particles", type=int, default=N_PARTICLES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true",
@@ -437,7 +438,7 @@ def extras(args, rank, world, local, dev, finder, grid, filt, events):
     for _ in range(2):
         n_seeds, chk, secs = 0, 0, 0.0
         for c0 in range(0, len(evs), CH):
-            ios, outs = pool.make_batch(evs[c0:c0 + CH], diag=True)
+            ios, outs = pool.make_batch(evs[c0:c0 + CH], packed=True)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             pool.process(ios)
@@ -570,8 +571,9 @@ def run_b200(args):
     PW = max(1, args.pool_workers)
     pool = seeding.EventPool(finder, grid, filt, device=local, n_workers=PW)
     DIAG = args.e2e_records == "diag"
-    rec_bytes = 56 if DIAG else 176
-    ios, outs = pool.make_batch(events, diag=DIAG)
+    PACKED = args.e2e_records == "packed"
+    rec_bytes = 32 if PACKED else (56 if DIAG else 176)
+    ios, outs = pool.make_batch(events, diag=DIAG, packed=PACKED)
     # Bytes that actually cross PCIe. Default: the delivered records themselves and all six input
     # columns. B200SEED_PCIE_PARAMS=packed: 32-byte records without the constant variances and the
     # time, completed inside pool.process by a sequential host copy.
@@ -613,10 +615,11 @@ def run_b200(args):
     ref0 = d_out[0].to_host()
     assert chk["n_seeds"] == len(ref0["bottom"]) and np.array_equal(chk["top"], ref0["top"])
     par0 = tpes[0].to_host(d_par[0], chk["n_seeds"])
-    got0 = seeding.expand_params(chk["params_diag"]) if DIAG else chk["params"]
+    got0 = (tpes[0].expand_packed_params(chk["params_packed"]) if PACKED
+            else seeding.expand_params(chk["params_diag"]) if DIAG else chk["params"])
     assert np.array_equal(got0.view(np.uint8), par0.view(np.uint8)), "pool parameters != device path"
     # the other record form, a few steps, for the record (not the headline)
-    ios2, outs2 = pool.make_batch(events, diag=not DIAG)
+    ios2, outs2 = pool.make_batch(events, diag=(not DIAG) and not PACKED)   # packed / diag -> full, full -> diag
     e2e_other_s = timed_wall(lambda: pool.process(ios2), max(2, args.steps // 4), 1)
     e2e_other = world * E * max(2, args.steps // 4) / e2e_other_s
     del ios2, outs2
@@ -743,14 +746,14 @@ def run_b200(args):
                         "d2h_bytes_per_step": d2h_box[0],
                         "how": f"b200seed_pool_process from pinned host buffers: {PW} native worker threads, "
                                f"2 algorithm instances/streams each; parameters delivered as {rec_bytes}-byte "
-                               f"{'diagonal (b200seed_bound_params_diag)' if DIAG else 'full'} records"
+                               f"{'packed (b200seed_bound_params_packed)' if PACKED else 'diagonal (b200seed_bound_params_diag)' if DIAG else 'full'} records"
                                + ("; over PCIe only 16 bytes per seed (phi, theta, q/p, var(q/p)), the records "
                                   "completed on the host inside the timed region from the caller's measurement "
                                   "columns, which are not sent to the device" if COMPACT else
                                   "; over PCIe as 32-byte packed records (b200seed_bound_params_packed: no constant "
                                   "variances, no time), completed on the host inside the timed region"
                                   if PCIE == "packed" else ""),
-                        "other_record_form": {"bytes_per_record": 176 if DIAG else 56, "value": e2e_other}},
+                        "other_record_form": {"bytes_per_record": 176 if (DIAG or PACKED) else 56, "value": e2e_other}},
                 "roofline": roof, "clocks": clocks,
                 "event_counters_mean": c_mean}
 

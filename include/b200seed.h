@@ -437,6 +437,11 @@ typedef struct b200seed_event_io {
     /* the parameters as 56-byte diagonal records (may be NULL). When set, the parameters cross
      * PCIe in this form (a third of the bytes); `params` may be set as well (both are filled). */
     b200seed_bound_params_diag* params_diag;
+    /* the parameters as 32-byte packed records (may be NULL): delivered as they come off the
+     * device, no host work; b200seed_expand_packed_params() restores the other forms on demand.
+     * When set, the parameters cross PCIe in this form; `params` / `params_diag` are then expanded
+     * from it on the host if they are set as well. */
+    b200seed_bound_params_packed* params_packed;
 } b200seed_event_io;
 
 typedef struct b200seed_pool b200seed_pool;

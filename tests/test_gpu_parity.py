@@ -594,15 +594,17 @@ def test_diagonal_parameter_records(pcie, monkeypatch):
     pool = seeding.EventPool(n_workers=2)
     ios_f, outs_f = pool.make_batch(events)
     ios_d, outs_d = pool.make_batch(events, diag=True)
+    ios_p, outs_p = pool.make_batch(events, packed=True)   # 32-byte records delivered as such
     pool.process(ios_f)
     pool.process(ios_d)
+    pool.process(ios_p)
     # the device-resident path (176-byte records written by the kernel) is the reference
     import torch
     from traccc_b200 import seedfilter_config, seedfinder_config, spacepoint_grid_config
     f = seedfinder_config()
     sa = seeding.triplet_seeding_algorithm(f, spacepoint_grid_config(f), seedfilter_config())
     tp = seeding.seed_parameter_estimation_algorithm()
-    for ev, io_f, of, io_d, od in zip(events, ios_f, outs_f, ios_d, outs_d):
+    for ev, io_f, of, io_d, od, io_p, op in zip(events, ios_f, outs_f, ios_d, outs_d, ios_p, outs_p):
         full = seeding.EventPool.result(io_f, of)
         diag = seeding.EventPool.result(io_d, od)
         assert full["n_seeds"] == diag["n_seeds"] > 0
@@ -610,6 +612,10 @@ def test_diagonal_parameter_records(pcie, monkeypatch):
             assert np.array_equal(full[k], diag[k])
         exp = seeding.expand_params(diag["params_diag"])
         assert np.array_equal(exp.view(np.uint8), full["params"].view(np.uint8))
+        pk = seeding.EventPool.result(io_p, op)
+        assert pk["n_seeds"] == full["n_seeds"] and np.array_equal(pk["top"], full["top"])
+        assert np.array_equal(tp.expand_packed_params(pk["params_packed"]).view(np.uint8),
+                              full["params"].view(np.uint8))
         sps = seeding.spacepoint_collection.from_event(ev)
         seeds = sa(sps)
         ref = tp(ev.bfield, seeding.measurement_collection.from_event(ev), sps, seeds)

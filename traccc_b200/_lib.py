@@ -102,7 +102,7 @@ class EventIO(C.Structure):
                 ("seed_capacity", C.c_uint32), ("bottom", C.c_void_p), ("middle", C.c_void_p),
                 ("top", C.c_void_p), ("quality", C.c_void_p), ("params", C.c_void_p),
                 ("n_seeds", C.c_uint32), ("status", C.c_int32), ("counters", Counters),
-                ("params_diag", C.c_void_p)]
+                ("params_diag", C.c_void_p), ("params_packed", C.c_void_p)]
 
 
 class FieldGrid(C.Structure):

@@ -1309,6 +1309,7 @@ struct HostEvent {
     b200seed_bound_params* h_params = nullptr;
     b200seed_bound_params_diag* h_params_diag = nullptr;  // when set, the parameters cross PCIe as
                                                           // 56-byte diagonal records
+    b200seed_bound_params_packed* h_params_packed = nullptr;  // ... as 32-byte packed records, delivered as such
     // device staging of the outputs (set by submit)
     uint32_t *d_b = nullptr, *d_m = nullptr, *d_t = nullptr;
     float* d_q = nullptr;
@@ -1337,7 +1338,7 @@ int host_submit(b200seed_handle* h, cudaStream_t s, HostEvent& e) {
     if (e.n_sp == 0) return B200SEED_OK;
     if (!e.h_xyz) return fail(h, B200SEED_EINVAL, "b200seed_run_host: h_xyz is null");
     const bool diag = e.h_params_diag != nullptr;
-    const bool want_params = e.h_params != nullptr || diag;
+    const bool want_params = e.h_params != nullptr || diag || e.h_params_packed != nullptr;
     const uint32_t n_sp = e.n_sp, n_meas = e.n_meas, seed_capacity = e.seed_capacity;
     // B200SEED_PCIE_PARAMS=compact: only phi, theta, q/p and var(q/p) are computed on the device
     // (16 bytes per seed); the records are completed on the host from the caller's own measurement
@@ -1351,7 +1352,7 @@ int host_submit(b200seed_handle* h, cudaStream_t s, HostEvent& e) {
     // a sequential copy (b200seed_expand_packed_params). Measured like the compact form: the host
     // writing the records costs more than the copy engine saving a third of the bytes — 3.90k vs
     // 4.00k events/s on one GPU, 13.0k vs 18.4k on eight (whose host is the limit either way).
-    e.packed = want_params && !e.compact && h->pcie_packed;
+    e.packed = want_params && !e.compact && (h->pcie_packed || e.h_params_packed != nullptr);
 
     // device staging: inputs | outputs | workspace
     size_t o = 0;
@@ -1383,7 +1384,7 @@ int host_submit(b200seed_handle* h, cudaStream_t s, HostEvent& e) {
         h->d_stage_bytes = want;
     }
     if (!h->h_pinned) CUDA_TRY(h, cudaMallocHost(&h->h_pinned, 256));
-    if (e.compact || e.packed) {
+    if (e.compact || (e.packed && !e.h_params_packed)) {
         const size_t need = size_t(seed_capacity) * (e.packed ? sizeof(b200seed_bound_params_packed)
                                                               : sizeof(b200seed_seed_params) + 4);
         if (need > h->h_compact_bytes) {
@@ -1480,7 +1481,9 @@ int host_finish(b200seed_handle* h, cudaStream_t s, HostEvent& e, uint32_t* h_n_
                 h_bot = stage;
             }
         } else if (e.packed) {
-            CUDA_TRY(h, cudaMemcpyAsync(h->h_compact, e.d_p, size_t(n) * sizeof(b200seed_bound_params_packed),
+            // straight into the caller's buffer if that form was asked for
+            CUDA_TRY(h, cudaMemcpyAsync(e.h_params_packed ? static_cast<void*>(e.h_params_packed) : h->h_compact,
+                                        e.d_p, size_t(n) * sizeof(b200seed_bound_params_packed),
                                         cudaMemcpyDeviceToHost, s));
         } else if (e.h_params_diag) {
             CUDA_TRY(h, cudaMemcpyAsync(e.h_params_diag, e.d_p, size_t(n) * sizeof(b200seed_bound_params_diag),
@@ -1508,9 +1511,13 @@ void host_expand(b200seed_handle* h, const HostEvent& e, uint32_t n) {
     if (e.compact)
         b200seed_expand_seed_params(h, n, e.h_bot_stage, static_cast<const b200seed_seed_params*>(h->h_compact),
                                     e.h_smi, e.h_ml, e.h_ms, e.h_params, e.h_params_diag);
-    else if (e.packed)
-        b200seed_expand_packed_params(h, n, static_cast<const b200seed_bound_params_packed*>(h->h_compact),
-                                      e.h_params, e.h_params_diag);
+    else if (e.packed) {
+        if (e.h_params || e.h_params_diag)
+            b200seed_expand_packed_params(
+                h, n,
+                e.h_params_packed ? e.h_params_packed : static_cast<const b200seed_bound_params_packed*>(h->h_compact),
+                e.h_params, e.h_params_diag);
+    }
     // both forms requested: the full records are expanded on the host
     else if (e.h_params_diag && e.h_params)
         b200seed_expand_params(e.h_params_diag, n, e.h_params);
@@ -1544,6 +1551,7 @@ HostEvent host_event_of(const b200seed_event_io& io) {
     e.h_bottom = io.bottom, e.h_middle = io.middle, e.h_top = io.top, e.h_quality = io.quality;
     e.h_params = io.params;
     e.h_params_diag = io.params_diag;
+    e.h_params_packed = io.params_packed;
     return e;
 }
 

@@ -624,7 +624,7 @@ class EventPool:
             self.lib.b200seed_pool_destroy(p)
             self.p = None
 
-    def make_batch(self, events, with_params: bool = True, diag: bool = False):
+    def make_batch(self, events, with_params: bool = True, diag: bool = False, packed: bool = False):
         """Pinned host buffers + the b200seed_event_io array for a list of ToyEvent-like
         objects. Returns (io_array, outputs) where outputs[i] holds the pinned result tensors
         (and, under "_inputs", the pinned inputs): the caller owns the batch, the pool keeps
@@ -643,10 +643,13 @@ class EventPool:
                    "top": torch.empty(cap, dtype=torch.int32, pin_memory=True),
                    "quality": torch.empty(cap, dtype=torch.float32, pin_memory=True),
                    "params": torch.empty(cap * BOUND_PARAMS_DTYPE.itemsize, dtype=torch.uint8,
-                                         pin_memory=True) if (with_params and not diag) else None,
+                                         pin_memory=True) if (with_params and not diag and not packed) else None,
+                   # packed: 32-byte records (no constant variances, no time), delivered as such
+                   "params_packed": torch.empty(cap * PACKED_PARAMS_DTYPE.itemsize, dtype=torch.uint8,
+                                                pin_memory=True) if (with_params and packed) else None,
                    # diag: the parameters cross PCIe as 56-byte diagonal records
                    "params_diag": torch.empty(cap * BOUND_PARAMS_DIAG_DTYPE.itemsize, dtype=torch.uint8,
-                                              pin_memory=True) if (with_params and diag) else None}
+                                              pin_memory=True) if (with_params and diag and not packed) else None}
             io = ios[i]
             io.n_spacepoints, io.n_measurements = n, int(e.meas_local.shape[0])
             io.xyz, io.var_z, io.var_r = inp[0].data_ptr(), inp[1].data_ptr(), inp[2].data_ptr()
@@ -660,6 +663,7 @@ class EventPool:
             io.quality = out["quality"].data_ptr()
             io.params = out["params"].data_ptr() if out["params"] is not None else None
             io.params_diag = out["params_diag"].data_ptr() if out["params_diag"] is not None else None
+            io.params_packed = out["params_packed"].data_ptr() if out["params_packed"] is not None else None
             out["_inputs"] = inp   # the pinned input buffers live as long as the caller's batch
             outs.append(out)
         return ios, outs
@@ -684,4 +688,7 @@ class EventPool:
         if out.get("params_diag") is not None:
             res["params_diag"] = out["params_diag"][: ns * BOUND_PARAMS_DIAG_DTYPE.itemsize].numpy().view(
                 BOUND_PARAMS_DIAG_DTYPE)
+        if out.get("params_packed") is not None:
+            res["params_packed"] = out["params_packed"][: ns * PACKED_PARAMS_DTYPE.itemsize].numpy().view(
+                PACKED_PARAMS_DTYPE)
         return res
