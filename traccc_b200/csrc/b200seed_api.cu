@@ -1347,7 +1347,7 @@ int host_submit(b200seed_handle* h, cudaStream_t s, HostEvent& e) {
     // events/s (3.90k if the expansion cost nothing) — for hosts whose D->H rate is the limit, not
     // the default.
     // (read at b200seed_create)
-    e.compact = want_params && h->pcie_compact;
+    e.compact = want_params && h->pcie_compact && !e.h_params_packed;  // (a packed delivery is its own wire form)
     // B200SEED_PCIE_PARAMS=packed: 32-byte records (no constant variances), completed on the host by
     // a sequential copy (b200seed_expand_packed_params). Measured like the compact form: the host
     // writing the records costs more than the copy engine saving a third of the bytes — 3.90k vs
