@@ -33,6 +33,25 @@ def test_struct_layouts():
     assert seedfilter_config.compatSeedLimit.offset == 16
     assert C.sizeof(track_params_estimation_config) == 56
     assert C.sizeof(_lib.Counters) == 72
+    # record forms of the parameters (include/b200seed.h) and the host-buffer event record, checked
+    # against the C compiler's view of the header
+    from traccc_b200 import seeding
+    assert seeding.BOUND_PARAMS_DTYPE.itemsize == 176 and seeding.BOUND_PARAMS_DIAG_DTYPE.itemsize == 56
+    assert seeding.PACKED_PARAMS_DTYPE.itemsize == 32 and seeding.SEED_PARAMS_DTYPE.itemsize == 16
+    import os
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = ('#include <stdio.h>\n#include "b200seed.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n",'
+           'sizeof(b200seed_bound_params),sizeof(b200seed_bound_params_diag),sizeof(b200seed_bound_params_packed),'
+           'sizeof(b200seed_seed_params),sizeof(b200seed_counters),sizeof(b200seed_event_io));return 0;}\n')
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "s.c"), "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.join(root, "include"), "-o", os.path.join(d, "s"), os.path.join(d, "s.c")],
+                       check=True)
+        sizes = [int(x) for x in subprocess.run([os.path.join(d, "s")], capture_output=True, text=True,
+                                                check=True).stdout.split()]
+    assert sizes == [176, 56, 32, 16, 72, C.sizeof(_lib.EventIO)]
     assert seedfinder_config.maxSeedsPerSpM.offset == 64 and seedfinder_config.neighbor_scope.offset == 124
 
 
