@@ -700,12 +700,17 @@ def test_stress_event_full_size():
     assert np.isfinite(a["params"]["vec"]).all()
 
 
-def test_event_is_stream_capturable():
+@pytest.mark.parametrize("order", ["default", "cost"])
+def test_event_is_stream_capturable(order, monkeypatch):
     """b200seed_run + b200seed_estimate_params never touch the host between their launches (every
     size the reference reads back stays on the device), so a whole event can be captured into a
     CUDA graph and replayed: same seeds and parameters as the eager call, also after the input
-    buffers were overwritten with another event of the same size."""
+    buffers were overwritten with another event of the same size. "cost": with the launches larger
+    events get — cost-ordered tickets, k_doublets<3> as a programmatic dependent launch (a
+    programmatic edge in the graph), k_doublets<2>."""
     import torch
+    if order == "cost":
+        monkeypatch.setenv("B200SEED_DOUBLET_ORDER", "cost")
     from traccc_b200 import (seedfilter_config, seedfinder_config, seeding, spacepoint_grid_config,
                              toy_detector)
     ev1 = toy_detector.generate_event(300, 81)
